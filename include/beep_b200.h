@@ -1,0 +1,202 @@
+/* beep_b200.h -- C ABI of the B200-native BEEP latent-state engine.
+ *
+ * The reference (ScottishCovidResponse/BEEP @ d70908f) has no plugin or FFI
+ * layer; its seam is the public surface of three C++ classes that every
+ * inference driver calls directly:
+ *     State              src/state.hh:11-133
+ *     Mbp                src/mbp.hh:15-82
+ *     ObservationModel   src/obsmodel.hh:8-39
+ * plus the three particle movers of Mpi (src/mpi.hh:16-24).  Each entry point
+ * below names the reference member function(s) whose body it replaces; the
+ * drivers (mbp.cc, pas.cc, abcsmc.cc, abcmbp.cc, pmcmc.cc, mc3.cc, ml.cc)
+ * keep their host loops and call these with a BATCH of particles instead of
+ * one State at a time (see INTEGRATION.md for the reference-side adapter).
+ *
+ * Conventions
+ *   - plain C types only; no torch/STL types cross this boundary;
+ *   - every function returns BEEP_OK (0) or a negative BeepStatus and never
+ *     calls exit() (the reference's emsg() exits, utils.cc:296-316);
+ *     beep_last_error() gives the message for the calling thread;
+ *   - the engine owns all device memory; the caller owns host arrays;
+ *   - pointers named *_host are host memory (any, pinned is faster); pointers
+ *     named *_dev are device memory on the engine's GPU;
+ *   - particle trajectories cross the boundary in exactly Particle::transnum
+ *     order [sett][area][trans][dp] (struct.hh:176-188, state.cc:728-737);
+ *   - there is no global RNG: every draw is a pure function of
+ *     (seed, stream_id[p], sett, area, dp, draw index) -- see beep_rng.h;
+ *   - calls on one batch are asynchronous on the batch's CUDA stream and are
+ *     ordered; any function returning data to the host synchronises.
+ *   - there is no CPU fallback: without a CUDA device engine creation fails.
+ */
+#ifndef BEEP_B200_H
+#define BEEP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Model description (flattened Details + Data + Model)                      */
+/* ------------------------------------------------------------------------ */
+typedef struct BeepModelDesc {
+#define BEEP_I32(name)  int32_t name;
+#define BEEP_F64(name)  double name;
+#define BEEP_AI32(name) const int32_t *name; int64_t n_##name;
+#define BEEP_AF64(name) const double *name; int64_t n_##name;
+#include "beep_model_fields.def"
+#undef BEEP_I32
+#undef BEEP_F64
+#undef BEEP_AI32
+#undef BEEP_AF64
+} BeepModelDesc;
+
+/* Sentinels compared as doubles, reference src/consts.hh:159-161 */
+#define BEEP_UNSET   999999999.0
+#define BEEP_THRESH  999999998.0
+#define BEEP_UNKNOWN 999999997.0
+
+/* ObsModelFunc, reference src/consts.hh:40 */
+enum { BEEP_OBS_NORMAL = 0, BEEP_OBS_NORMAL_PERCENT = 1, BEEP_OBS_POISSON = 2, BEEP_OBS_NEGBIN = 3 };
+
+typedef enum BeepStatus {
+	BEEP_OK = 0,
+	BEEP_ERR_INVALID = -1,      /* bad argument / inconsistent model description   */
+	BEEP_ERR_UNSUPPORTED = -2,  /* feature outside the hot-path scope              */
+	BEEP_ERR_CUDA = -3,         /* CUDA runtime error (message has the detail)     */
+	BEEP_ERR_NO_DEVICE = -4,    /* no CUDA device: there is no CPU fallback        */
+	BEEP_ERR_STATE = -5,        /* call order (e.g. simulate before set_params)    */
+	BEEP_ERR_NUMERIC = -6       /* NaN / non-convergence (reference emsgEC sites)  */
+} BeepStatus;
+
+typedef struct BeepEngine BeepEngine;
+typedef struct BeepBatch BeepBatch;
+
+/* Batch allocation flags */
+enum {
+	BEEP_KEEP_TRANSNUM  = 1,  /* store transnum[P][T][A][J][D] (MBP chains, samples)  */
+	BEEP_KEEP_TRANSMEAN = 2,  /* store transmean likewise (MBP initial state, K5)     */
+	BEEP_KEEP_POP       = 4   /* store pop[P][T][A][C][D] (outputs / parity tests)    */
+};
+
+/* Selectors for beep_get_derived (outputs of State::set_param, state.hh:56-64) */
+enum {
+	BEEP_DERIVED_TRANSRATE = 0,      /* [J][D]                                        */
+	BEEP_DERIVED_DISC_SPLINE = 1,    /* [nspline][T]                                  */
+	BEEP_DERIVED_SUSCEPTIBILITY = 2, /* [D]                                           */
+	BEEP_DERIVED_AREAFACTOR = 3,     /* [period][A]                                   */
+	BEEP_DERIVED_BETA = 4,           /* [S][A][T]                                     */
+	BEEP_DERIVED_AGEFACTOR = 5       /* [T][G] g with Ntime[t][a][b]=N0[a][b] g_a g_b  */
+};
+
+/* Selectors for beep_get_trajectory */
+enum { BEEP_TRAJ_TRANSNUM = 0, BEEP_TRAJ_TRANSMEAN = 1, BEEP_TRAJ_POP = 2 };
+
+/* InfUpdate, reference src/consts.hh:131 */
+enum { BEEP_INF_UPDATE = 0, BEEP_INF_DIF_UPDATE = 1 };
+
+/* beep_permute `what` */
+enum { BEEP_PERMUTE_FULL = 0, BEEP_PERMUTE_SECTION_STATE = 1 };
+
+const char *beep_last_error(void);
+int beep_version(void);
+
+/* Replaces: construction of Data/Model tables per MPI rank (mpi.cc:26-77
+ * broadcast) -- uploads the read-only tables once to `device`.              */
+int beep_engine_create(const BeepModelDesc *desc, int device, BeepEngine **out);
+void beep_engine_destroy(BeepEngine *eng);
+
+/* Replaces: `vector<State> particle` / `vector<Particle> part` owned by the
+ * drivers (pmcmc.cc:60-66, abcmbp.cc:41-48, mc3.cc:99-118).                 */
+int beep_batch_create(BeepEngine *eng, int nparticle, unsigned flags, BeepBatch **out);
+void beep_batch_destroy(BeepBatch *batch);
+int beep_batch_size(const BeepBatch *batch);
+/* bytes of device memory held by the batch (memory-frontier planning)       */
+int64_t beep_batch_bytes(const BeepBatch *batch);
+
+/* K0.  Replaces State::set_param (state.cc:66-91) for all P particles.
+ * theta is [P][nparam], raw (pre-Dirichlet) parameter values.               */
+int beep_set_params(BeepBatch *batch, const double *theta_host);
+int beep_set_params_dev(BeepBatch *batch, const double *theta_dev);
+
+/* K1+K2 (+K4 accumulation).  Replaces State::simulate(ti,tf)
+ * (state.cc:596-638): tau-leap from step ti to tf for every particle,
+ * accumulating the observation sums of those steps.  ti == 0 resets the
+ * population to pop_init (state.cc:600) and clears the accumulators.
+ * stream_id_host: [P] per-particle stream ids or NULL (= slot index).       */
+int beep_simulate(BeepBatch *batch, int ti, int tf, uint64_t seed, const uint64_t *stream_id_host);
+
+/* K3.  Replaces Mbp::mbp (mbp.cc:252-330): proposes a trajectory for every
+ * particle of `prop` (whose parameters were set with beep_set_params) coupled
+ * to the same slot of `init`, which must hold transnum and transmean.
+ * simu_mask_host: [P][T][A] bytes, 1 = SIMU, 0 = MBP (consts.hh:99), or NULL
+ * for pure MBP.  inf_update is accepted for signature parity; the engine
+ * always derives the infectivity map from the proposed population.          */
+int beep_mbp(BeepBatch *init, BeepBatch *prop, const uint8_t *simu_mask_host, int inf_update,
+             uint64_t seed, const uint64_t *stream_id_host);
+
+/* Replaces State::initialise_from_particle (state.cc:294-322) and the
+ * set_transmean sweep of Mbp::parameter_proposal (mbp.cc:470-476): with the
+ * batch's current parameters and stored transnum, recompute pop, transmean
+ * and the observation sums.                                                 */
+int beep_replay(BeepBatch *batch);
+
+/* K4.  Replaces ObservationModel::calculate (obsmodel.cc:22-35, section < 0),
+ * calculate_section (:39-58, section >= 0) and get_EF_datatable (:309-322).
+ * L_host[P] receives the log observation probability (EF = -2 L,
+ * state.cc:95-98); EF_table_host[P][ntable] may be NULL.                    */
+int beep_obs_loglik(BeepBatch *batch, int section, double *L_host, double *EF_table_host);
+int beep_obs_loglik_dev(BeepBatch *batch, int section, double *L_dev, double *EF_table_dev);
+/* Replaces ObservationModel::get_obs_value (obsmodel.cc:62-70): [P][nobs]   */
+int beep_obs_values(BeepBatch *batch, double *obs_value_host);
+/* number of PMCMC sections and their step ranges (obsmodel.cc:326-348)      */
+int beep_num_sections(const BeepEngine *eng);
+int beep_section_range(const BeepEngine *eng, int section, int *ti, int *tf);
+
+/* K5.  Replaces State::likelihood (state.cc:812-826): Li_host[P]            */
+int beep_latent_loglik(BeepBatch *batch, double *Li_host);
+
+/* K6.  Replaces Mpi::copy_particles (mpi.cc:81-165, what = FULL) and
+ * Mpi::end_sec_swap (mpi.cc:215-327, what = SECTION_STATE) within one GPU:
+ * slot p takes the state of slot src_of_host[p] (0xFFFFFFFF = keep).        */
+int beep_permute(BeepBatch *batch, const uint32_t *src_of_host, int what);
+/* Swap the roles of two batches for the slots with accept_host[p] != 0:
+ * Mbp::swap_initial_propose_state (mbp.cc:243-248) per particle.            */
+int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *accept_host);
+
+/* Replaces State::create_particle (state.cc:326-335) / State::save
+ * (:709-739): theta[nparam], transnum[T][A][J][D] as doubles.               */
+int beep_export_particle(BeepBatch *batch, int slot, double *theta_host, double *transnum_host);
+/* Replaces State::load / initialise_from_particle (state.cc:294-322,743-808):
+ * stores theta + transnum in the slot; call beep_set_params is NOT needed
+ * afterwards for that slot, but beep_replay is (it is batch-wide).          */
+int beep_import_particle(BeepBatch *batch, int slot, const double *theta_host, const double *transnum_host);
+
+/* Read-back used by the parity tests and by output code on the host.        */
+int beep_get_derived(BeepBatch *batch, int slot, int which, double *out_host, int64_t n);
+int beep_get_trajectory(BeepBatch *batch, int slot, int which, double *out_host, int64_t n);
+/* population at the batch's current step, [A][C][D]                         */
+int beep_get_pop(BeepBatch *batch, int slot, double *out_host, int64_t n);
+
+int beep_sync(BeepBatch *batch);
+/* the batch's cudaStream_t, for callers that time or enqueue on it          */
+void *beep_batch_stream(BeepBatch *batch);
+/* number of engine kernel launches since creation (bench accounting)        */
+int64_t beep_launch_count(const BeepEngine *eng);
+/* last kernel-only duration of beep_simulate in ms (CUDA events on the
+ * batch stream), -1 if none.                                                */
+double beep_last_simulate_ms(const BeepBatch *batch);
+
+/* PMCMC bootstrap step, pmcmc.cc:211-268, on the weights of ALL ranks
+ * (already all-gathered by the caller): computes the log-likelihood
+ * increment and the ancestor vector with the stay-in-place rule.  Pure host
+ * arithmetic on O(Ntot) scalars, replicated on every rank from a shared
+ * (seed, section) key so no broadcast is needed.                            */
+int beep_bootstrap(const double *L_all_host, int ntot, double invT, uint64_t seed, int section,
+                   double *loglik_inc, uint32_t *backpart_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEEP_B200_H */

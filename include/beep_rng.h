@@ -1,0 +1,337 @@
+/* beep_rng.h -- counter-based random streams and exact Poisson / binomial
+ * samplers with ONE floating-point op sequence on host and device.
+ *
+ * Replaces (reference src/utils.cc:32-34,148-153,174-180):
+ *     std::default_random_engine generator;            // minstd_rand0, global
+ *     poisson_sample(lam)   -> std::poisson_distribution<int>
+ *     binomial_sample(p,n)  -> std::binomial_distribution<int>
+ * whose algorithms are implementation-defined (libstdc++) and whose draw
+ * order is a global sequential side effect.  Here every draw is a pure
+ * function of a 64-bit key and a 128-bit counter (Philox4x32-10, Salmon et
+ * al. SC'11), and the samplers use only IEEE-754 correctly rounded
+ * operations (+ - * / sqrt, integer ops) written without contraction, plus
+ * software log/exp built from those, so that the CUDA kernels, the CPU
+ * oracle and the reference harness (which links this header in place of the
+ * std:: distributions) produce bit-identical integers from the same stream.
+ *
+ * Samplers (both exact in distribution):
+ *     Poisson(lam):  lam < 10  sequential-search inversion
+ *                    lam >= 10 PTRS transformed rejection (Hormann 1993)
+ *     Binomial(n,p): n*min(p,1-p) < 10  BINV inversion (Kachitvichyanukul
+ *                    & Schmeiser 1988), else BTRS (Hormann 1993)
+ *
+ * Host compilation of any TU including this header must use
+ * -ffp-contract=off (the build recipes do); device code uses the *_rn
+ * intrinsics, which nvcc never contracts into FMAs.
+ */
+#ifndef BEEP_RNG_H
+#define BEEP_RNG_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BEEP_HD __host__ __device__ __forceinline__
+#else
+#define BEEP_HD static inline
+#include <math.h>
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define BR_MUL(a, b) __dmul_rn((a), (b))
+#define BR_ADD(a, b) __dadd_rn((a), (b))
+#define BR_SUB(a, b) __dsub_rn((a), (b))
+#define BR_DIV(a, b) __ddiv_rn((a), (b))
+#define BR_SQRT(a) __dsqrt_rn((a))
+#define BR_MULHI(a, b) __umulhi((a), (b))
+#define BR_FLOOR(a) floor((a))
+#define BR_FABS(a) fabs((a))
+#else
+#define BR_MUL(a, b) ((a) * (b))
+#define BR_ADD(a, b) ((a) + (b))
+#define BR_SUB(a, b) ((a) - (b))
+#define BR_DIV(a, b) ((a) / (b))
+#define BR_SQRT(a) sqrt((a))
+#define BR_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#define BR_FLOOR(a) floor((a))
+#define BR_FABS(a) fabs((a))
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Philox4x32-10                                                             */
+/* ------------------------------------------------------------------------ */
+typedef struct BeepStream {
+	uint32_t key[2]; /* seed                                                   */
+	uint32_t ctr[4]; /* ctr[0] = block index within the stream; ctr[1..3] = id */
+	uint32_t buf[4];
+	int have;        /* unread words in buf                                    */
+} BeepStream;
+
+BEEP_HD void beep_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+	uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+	uint32_t k0 = key[0], k1 = key[1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int r = 0; r < 10; r++) {
+		uint32_t hi0 = BR_MULHI(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		uint32_t hi1 = BR_MULHI(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* A stream is identified by (seed, id0, id1, id2).  The engine uses
+ *   id0 = low 32 bits of the particle's stream id
+ *   id1 = high 32 bits of the particle's stream id
+ *   id2 = column index ((sett*A + c)*D + dp), or 0xFFFFFFFF for the
+ *         sequential stream of the reference harness.                       */
+BEEP_HD void beep_stream_init(BeepStream *s, uint64_t seed, uint32_t id0, uint32_t id1, uint32_t id2)
+{
+	s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
+	s->ctr[0] = 0; s->ctr[1] = id0; s->ctr[2] = id1; s->ctr[3] = id2;
+	s->have = 0;
+}
+
+BEEP_HD uint32_t beep_next_u32(BeepStream *s)
+{
+	if (s->have == 0) {
+		beep_philox4x32_10(s->ctr, s->key, s->buf);
+		s->ctr[0]++;
+		s->have = 4;
+	}
+	uint32_t w = s->buf[4 - s->have];
+	s->have--;
+	return w;
+}
+
+/* uniform on (0,1): (x + 1/2) 2^-52 with x a 52-bit integer; exact, never 0/1 */
+BEEP_HD double beep_next_uniform(BeepStream *s)
+{
+	/* always consume an aligned pair so that a Philox block yields 2 uniforms */
+	if (s->have & 1) s->have--;
+	uint32_t a = beep_next_u32(s);
+	uint32_t b = beep_next_u32(s);
+	uint64_t x = (((uint64_t)a << 32) | (uint64_t)b) >> 12;
+	return BR_MUL(BR_ADD((double)x, 0.5), 2.220446049250313080847263336181640625e-16);
+}
+
+/* ------------------------------------------------------------------------ */
+/* software log / exp (fdlibm e_log.c / e_exp.c formulation, written with    */
+/* explicit non-contracted operations; ~1 ulp, identical on host and device) */
+/* ------------------------------------------------------------------------ */
+BEEP_HD uint64_t beep_d2u(double x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint64_t)__double_as_longlong(x);
+#else
+	union { double d; uint64_t u; } v; v.d = x; return v.u;
+#endif
+}
+BEEP_HD double beep_u2d(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+	return __longlong_as_double((long long)u);
+#else
+	union { double d; uint64_t u; } v; v.u = u; return v.d;
+#endif
+}
+
+/* natural log of a positive finite double */
+BEEP_HD double beep_log(double x)
+{
+	const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+	const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+	             Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+	             Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+	             Lg7 = 1.479819860511658591e-01;
+	uint64_t ux = beep_d2u(x);
+	int k = 0;
+	if ((ux >> 52) == 0) { /* subnormal: scale by 2^54 */
+		x = BR_MUL(x, 18014398509481984.0);
+		ux = beep_d2u(x);
+		k = -54;
+	}
+	int e = (int)((ux >> 52) & 0x7ff) - 1023;
+	uint64_t m = ux & 0x000fffffffffffffULL;
+	/* normalise to [sqrt(2)/2, sqrt(2)) */
+	if (m >= 0x6a09e667f3bcdULL) { e += 1; ux = m | 0x3fe0000000000000ULL; }
+	else ux = m | 0x3ff0000000000000ULL;
+	k += e;
+	double f = BR_SUB(beep_u2d(ux), 1.0);
+	double dk = (double)k;
+	double s = BR_DIV(f, BR_ADD(2.0, f));
+	double z = BR_MUL(s, s);
+	double w = BR_MUL(z, z);
+	double t1 = BR_MUL(w, BR_ADD(Lg2, BR_MUL(w, BR_ADD(Lg4, BR_MUL(w, Lg6)))));
+	double t2 = BR_MUL(z, BR_ADD(Lg1, BR_MUL(w, BR_ADD(Lg3, BR_MUL(w, BR_ADD(Lg5, BR_MUL(w, Lg7)))))));
+	double R = BR_ADD(t2, t1);
+	double hfsq = BR_MUL(0.5, BR_MUL(f, f));
+	/* k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f) */
+	double inner = BR_ADD(BR_MUL(s, BR_ADD(hfsq, R)), BR_MUL(dk, ln2_lo));
+	return BR_SUB(BR_MUL(dk, ln2_hi), BR_SUB(BR_SUB(hfsq, inner), f));
+}
+
+/* exp(x) for x in [-700, 700] (callers guarantee the range) */
+BEEP_HD double beep_exp(double x)
+{
+	const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
+	             invln2 = 1.44269504088896338700e+00;
+	const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+	             P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+	             P5 = 4.13813679705723846039e-08;
+	int k = (int)BR_ADD(BR_MUL(invln2, x), (x < 0.0 ? -0.5 : 0.5));
+	double dk = (double)k;
+	double hi = BR_SUB(x, BR_MUL(dk, ln2HI));
+	double lo = BR_MUL(dk, ln2LO);
+	double r = BR_SUB(hi, lo);
+	double t = BR_MUL(r, r);
+	double c = BR_SUB(r, BR_MUL(t, BR_ADD(P1, BR_MUL(t, BR_ADD(P2, BR_MUL(t, BR_ADD(P3, BR_MUL(t, BR_ADD(P4, BR_MUL(t, P5))))))))));
+	double y = BR_SUB(1.0, BR_SUB(BR_SUB(lo, BR_DIV(BR_MUL(r, c), BR_SUB(2.0, c))), hi));
+	/* scale by 2^k, k in [-1010, 1010]: two-step to stay in the normal range */
+	int k1 = k / 2, k2 = k - k1;
+	double s1 = beep_u2d((uint64_t)(1023 + k1) << 52);
+	double s2 = beep_u2d((uint64_t)(1023 + k2) << 52);
+	return BR_MUL(BR_MUL(y, s1), s2);
+}
+
+/* log(k!) for integer k >= 0: table below 16, Stirling series above
+ * (truncation error < 2e-14 at k = 16)                                     */
+BEEP_HD double beep_lfact(double k)
+{
+	if (k < 16.0) {
+		switch ((int)k) {
+		case 0: case 1: return 0.0;
+		case 2: return 0.693147180559945309417232121458;
+		case 3: return 1.791759469228055000812477358381;
+		case 4: return 3.178053830347945619646941601297;
+		case 5: return 4.787491742782045994247700934523;
+		case 6: return 6.579251212010100995060178292904;
+		case 7: return 8.525161361065414300165531036347;
+		case 8: return 10.60460290274525022841722740072;
+		case 9: return 12.80182748008146961120771787457;
+		case 10: return 15.10441257307551529522570932925;
+		case 11: return 17.50230784587388583928765290722;
+		case 12: return 19.98721449566188614951736238706;
+		case 13: return 22.55216385312342288557084982862;
+		case 14: return 25.19122118273868150009343469352;
+		default: return 27.89927138384089156608943926367;
+		}
+	}
+	/* lgamma(k+1) = (k+1/2) log k - k + log(2 pi)/2 + 1/(12k) - 1/(360k^3) + 1/(1260k^5) - 1/(1680k^7) */
+	double ik = BR_DIV(1.0, k);
+	double ik2 = BR_MUL(ik, ik);
+	double ser = BR_MUL(ik, BR_ADD(8.333333333333333333e-02,
+	             BR_MUL(ik2, BR_ADD(-2.777777777777777778e-03,
+	             BR_MUL(ik2, BR_ADD(7.936507936507936508e-04,
+	             BR_MUL(ik2, -5.952380952380952381e-04)))))));
+	return BR_ADD(BR_ADD(BR_SUB(BR_MUL(BR_ADD(k, 0.5), beep_log(k)), k), 9.189385332046727417803297364056e-01), ser);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Poisson                                                                   */
+/* ------------------------------------------------------------------------ */
+#define BEEP_POISSON_INV_MAX 10.0
+
+BEEP_HD int beep_poisson(BeepStream *s, double lam)
+{
+	if (!(lam > 0.0)) return 0;
+	if (lam < BEEP_POISSON_INV_MAX) {
+		double u = beep_next_uniform(s);
+		double p = beep_exp(BR_SUB(0.0, lam));
+		double cdf = p;
+		int k = 0;
+		while (u > cdf && k < 1000) {
+			k++;
+			p = BR_DIV(BR_MUL(p, lam), (double)k);
+			cdf = BR_ADD(cdf, p);
+		}
+		return k;
+	}
+	/* PTRS */
+	double slam = BR_SQRT(lam);
+	double b = BR_ADD(0.931, BR_MUL(2.53, slam));
+	double a = BR_ADD(-0.059, BR_MUL(0.02483, b));
+	double vr = BR_SUB(0.9277, BR_DIV(3.6224, BR_SUB(b, 2.0)));
+	double loglam = 0.0, lhs_c = 0.0;
+	int have_slow = 0;
+	for (int it = 0; it < 100000; it++) {
+		double U = BR_SUB(beep_next_uniform(s), 0.5);
+		double V = beep_next_uniform(s);
+		double us = BR_SUB(0.5, BR_FABS(U));
+		double kf = BR_FLOOR(BR_ADD(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), lam), 0.43));
+		if (us >= 0.07 && V <= vr) return (int)kf;
+		if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+		if (!have_slow) {
+			double invalpha = BR_ADD(1.1239, BR_DIV(1.1328, BR_SUB(b, 3.4)));
+			loglam = beep_log(lam);
+			lhs_c = beep_log(invalpha);
+			have_slow = 1;
+		}
+		double lhs = BR_SUB(BR_ADD(beep_log(V), lhs_c), beep_log(BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
+		double rhs = BR_SUB(BR_SUB(BR_MUL(kf, loglam), lam), beep_lfact(kf));
+		if (lhs <= rhs) return (int)kf;
+	}
+	return (int)lam;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Binomial                                                                  */
+/* ------------------------------------------------------------------------ */
+BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
+{
+	if (n <= 0 || !(p > 0.0)) return 0;
+	if (p >= 1.0) return n;
+	int flip = p > 0.5;
+	double q = flip ? BR_SUB(1.0, p) : p;
+	double dn = (double)n;
+	double omq = BR_SUB(1.0, q);
+	int k;
+	if (BR_MUL(dn, q) < 10.0) {
+		/* BINV */
+		double sr = BR_DIV(q, omq);
+		double a = BR_MUL(BR_ADD(dn, 1.0), sr);
+		double r = beep_exp(BR_MUL(dn, beep_log(omq)));
+		double u = beep_next_uniform(s);
+		k = 0;
+		while (u > r && k < n) {
+			u = BR_SUB(u, r);
+			k++;
+			r = BR_MUL(r, BR_SUB(BR_DIV(a, (double)k), sr));
+			if (!(r > 0.0)) break;
+		}
+	} else {
+		/* BTRS */
+		double spq = BR_SQRT(BR_MUL(BR_MUL(dn, q), omq));
+		double b = BR_ADD(1.15, BR_MUL(2.53, spq));
+		double a = BR_ADD(BR_ADD(-0.0873, BR_MUL(0.0248, b)), BR_MUL(0.01, q));
+		double c = BR_ADD(BR_MUL(dn, q), 0.5);
+		double vr = BR_SUB(0.92, BR_DIV(4.2, b));
+		double alpha = 0.0, lpq = 0.0, m = 0.0, h = 0.0;
+		int have_slow = 0;
+		k = (int)BR_MUL(dn, q);
+		for (int it = 0; it < 100000; it++) {
+			double U = BR_SUB(beep_next_uniform(s), 0.5);
+			double V = beep_next_uniform(s);
+			double us = BR_SUB(0.5, BR_FABS(U));
+			double kf = BR_FLOOR(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), c));
+			if (kf < 0.0 || kf > dn) continue;
+			if (us >= 0.07 && V <= vr) { k = (int)kf; break; }
+			if (!have_slow) {
+				alpha = BR_MUL(BR_ADD(2.83, BR_DIV(5.1, b)), spq);
+				lpq = beep_log(BR_DIV(q, omq));
+				m = BR_FLOOR(BR_MUL(BR_ADD(dn, 1.0), q));
+				h = BR_ADD(beep_lfact(m), beep_lfact(BR_SUB(dn, m)));
+				have_slow = 1;
+			}
+			double lv = beep_log(BR_DIV(BR_MUL(V, alpha), BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
+			double rhs = BR_ADD(BR_SUB(BR_SUB(h, beep_lfact(kf)), beep_lfact(BR_SUB(dn, kf))), BR_MUL(BR_SUB(kf, m), lpq));
+			if (lv <= rhs) { k = (int)kf; break; }
+		}
+	}
+	return flip ? n - k : k;
+}
+
+#endif /* BEEP_RNG_H */

@@ -1,0 +1,502 @@
+// ref_harness.cc -- TEST INFRASTRUCTURE (never shipped, never on the product path).
+//
+// Links against the UNMODIFIED reference objects compiled where they lie under
+// /root/reference (oracle/ref/build_ref.sh) and does two jobs:
+//
+//  1. the reference-side ADAPTER: flattens the reference's Details / Data / Model
+//     into the BeepModelDesc arrays of include/beep_model_fields.def (this is the
+//     code a BEEP maintainer would add next to main.cc:125-162);
+//  2. the GOLDEN-VECTOR generator: runs the reference's own State::set_param,
+//     State::simulate, ObservationModel::calculate*, State::likelihood and
+//     Mbp::mbp and records their outputs, so that oracle/ (the CPU restatement)
+//     and the CUDA engine can be pinned against the real thing.
+//
+// For the stochastic runs the reference's poisson_sample / binomial_sample
+// (utils.cc:148-153,174-180) are replaced AT LINK TIME (utils.cc is compiled with
+// -Dpoisson_sample=beepref_poisson_sample ..., sources untouched) by the
+// counter-based samplers of include/beep_rng.h consuming ONE sequential stream, so
+// that integer event counts can be compared bit for bit.
+//
+// Output: a "BPK1" container (named little-endian arrays) read by
+// tests/golden/make_golden.py.
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <map>
+#include <random>
+#include <algorithm>
+
+// The hot-path seam has private members we must read (Model::inf_state,
+// Mbp::mbp/initial/propose/simu_or_mbp, ObservationModel::split_observations);
+// access specifiers do not change layout, so open them for this TU only.
+#define private public
+#define protected public
+#include "inputs.hh"
+#include "details.hh"
+#include "data.hh"
+#include "model.hh"
+#include "obsmodel.hh"
+#include "state.hh"
+#include "output.hh"
+#include "mpi.hh"
+#include "mbp.hh"
+#include "utils.hh"
+#undef private
+#undef protected
+
+#include "beep_rng.h"
+
+using namespace std;
+
+// ---------------------------------------------------------------------------
+// link-time replacement of the reference samplers
+// ---------------------------------------------------------------------------
+int beepref_poisson_sample(const double lam);                       // original, utils.cc:148
+unsigned int beepref_binomial_sample(const double p, const unsigned int n); // original, utils.cc:174
+
+static bool g_inject = false;
+static BeepStream g_stream;
+static long g_ndraw = 0;
+
+int poisson_sample(const double lam)
+{
+	if(!g_inject) return beepref_poisson_sample(lam);
+	g_ndraw++;
+	return beep_poisson(&g_stream,lam);
+}
+
+unsigned int binomial_sample(const double p, const unsigned int n)
+{
+	if(!g_inject) return beepref_binomial_sample(p,n);
+	if(n == 0) return 0;                                               // utils.cc:176
+	g_ndraw++;
+	return (unsigned int)beep_binomial(&g_stream,p,(int)n);
+}
+
+static void inject_on(uint64_t seed, uint32_t id)
+{
+	g_inject = true;
+	beep_stream_init(&g_stream,seed,id,0,0xFFFFFFFFu);
+}
+static void inject_off(){ g_inject = false; }
+
+// ---------------------------------------------------------------------------
+// BPK1 container
+// ---------------------------------------------------------------------------
+struct Pack {
+	FILE *f; unsigned int n;
+	Pack(const char *file){ f = fopen(file,"wb"); if(!f){ perror(file); exit(1);} n = 0; fwrite("BPK1",1,4,f); fwrite(&n,4,1,f); }
+	void head(const string &name, unsigned int dtype, const vector <long> &dims){
+		unsigned int len = name.size(); fwrite(&len,4,1,f); fwrite(name.data(),1,len,f);
+		fwrite(&dtype,4,1,f); unsigned int nd = dims.size(); fwrite(&nd,4,1,f);
+		for(auto d : dims){ long long dd = d; fwrite(&dd,8,1,f);}
+		n++;
+	}
+	void i32(const string &name, const vector <int> &v, vector <long> dims = {}){
+		if(dims.size() == 0) dims.push_back(v.size());
+		long tot = 1; for(auto d : dims) tot *= d; if(tot != (long)v.size()){ cerr << "dims " << name << endl; exit(1);}
+		head(name,0,dims); if(v.size()) fwrite(v.data(),4,v.size(),f);
+	}
+	void f64(const string &name, const vector <double> &v, vector <long> dims = {}){
+		if(dims.size() == 0) dims.push_back(v.size());
+		long tot = 1; for(auto d : dims) tot *= d; if(tot != (long)v.size()){ cerr << "dims " << name << endl; exit(1);}
+		head(name,1,dims); if(v.size()) fwrite(v.data(),8,v.size(),f);
+	}
+	void scalar_i(const string &name, int v){ i32(name,vector<int>{v},{1}); }
+	void scalar_d(const string &name, double v){ f64(name,vector<double>{v},{1}); }
+	void close(){ fseek(f,4,SEEK_SET); fwrite(&n,4,1,f); fclose(f); }
+};
+
+static int u2i(unsigned int v){ return v == UNSET ? -1 : (int)v; }
+
+static vector <double> flat4(const vector < vector < vector < vector <double> > > > &x, unsigned int n0)
+{
+	vector <double> v;
+	for(auto a = 0u; a < n0; a++) for(const auto &b : x[a]) for(const auto &c : b) for(auto d : c) v.push_back(d);
+	return v;
+}
+static vector <double> flat3(const vector < vector < vector <double> > > &x)
+{
+	vector <double> v;
+	for(const auto &a : x) for(const auto &b : a) for(auto c : b) v.push_back(c);
+	return v;
+}
+static vector <double> flat2(const vector < vector <double> > &x)
+{
+	vector <double> v;
+	for(const auto &a : x) for(auto b : a) v.push_back(b);
+	return v;
+}
+
+// ---------------------------------------------------------------------------
+// 1. adapter: Details + Data + Model -> BeepModelDesc arrays
+// ---------------------------------------------------------------------------
+static void export_desc(Pack &pk, const Details &details, const Data &data, const Model &model)
+{
+	const string P = "desc.";
+	auto T = details.ndivision, A = data.narea, D = data.ndemocatpos, G = data.nage, S = data.nstrain;
+	unsigned int C = model.comp.size(), J = model.trans.size(), Dq = data.ndemocatpos_per_strain;
+
+	pk.scalar_i(P+"T",T); pk.scalar_i(P+"period",details.period); pk.scalar_i(P+"spu",details.division_per_time);
+	pk.scalar_i(P+"A",A); pk.scalar_i(P+"C",C); pk.scalar_i(P+"J",J); pk.scalar_i(P+"D",D); pk.scalar_i(P+"G",G);
+	pk.scalar_i(P+"S",S); pk.scalar_i(P+"Dq",Dq); pk.scalar_i(P+"nparam",model.param.size());
+	pk.scalar_i(P+"nspline",model.spline.size()); pk.scalar_i(P+"nobs",data.nobs); pk.scalar_i(P+"ntable",data.datatable.size());
+	pk.scalar_i(P+"stochastic",details.stochastic ? 1 : 0);
+	pk.scalar_i(P+"siminf_simulate",details.siminf == SIMULATE ? 1 : 0);
+	pk.scalar_i(P+"infection_trans",model.infection_trans);
+	pk.scalar_i(P+"geo_spline_ref",model.geo_spline_ref);
+	pk.scalar_i(P+"pmcmc_obs_period",details.pmcmc_obs_period);
+	int nunsup = 0;
+	if(data.democat_change.size() > 0) nunsup++;                       // state.cc:339-376 (outside scope)
+	if(details.mode == PREDICTION) nunsup++;                           // modelmod multipliers (outside scope)
+	pk.scalar_i(P+"n_unsupported",nunsup);
+	pk.scalar_d(P+"popsize",data.popsize);
+
+	{ // Dirichlet groups, model.cc:2685-2695
+		vector <int> off, th; vector <double> frac; off.push_back(0);
+		for(const auto &dir : model.dirichlet){
+			for(const auto &par : dir.param){ th.push_back(par.th); frac.push_back(par.frac);}
+			off.push_back(th.size());
+		}
+		pk.i32(P+"dir_off",off); pk.i32(P+"dir_th",th); pk.f64(P+"dir_frac",frac);
+	}
+
+	{ // transitions, model.cc:1116-1140
+		vector <int> from, to, inf, meanp, probp; vector <double> shape;
+		for(auto tr = 0u; tr < J; tr++){
+			const auto &t = model.trans[tr];
+			from.push_back(t.from); to.push_back(t.to); inf.push_back(t.inf == TRANS_INFECTION ? 1 : 0);
+			const auto &co = model.comp[t.from];
+			shape.push_back(co.shape == UNSET ? 1 : co.shape);
+			for(auto dp = 0u; dp < D; dp++){
+				if(t.inf == TRANS_INFECTION){ meanp.push_back(-1); probp.push_back(-1);}
+				else{
+					meanp.push_back(co.param_mean[dp]);
+					if(co.trans.size() > 1) probp.push_back(t.param_prob[dp]); else probp.push_back(-1);
+				}
+			}
+		}
+		pk.i32(P+"trans_from",from); pk.i32(P+"trans_to",to); pk.i32(P+"trans_inf",inf); pk.f64(P+"trans_shape",shape);
+		pk.i32(P+"trans_mean_param",meanp,{(long)J,(long)D}); pk.i32(P+"trans_prob_param",probp,{(long)J,(long)D});
+		vector <int> cinf; for(const auto &co : model.comp) cinf.push_back(co.infectivity_param);
+		pk.i32(P+"comp_inf_param",cinf);
+		vector <int> is; for(auto c : model.inf_state) is.push_back(c);
+		pk.i32(P+"inf_state",is);
+	}
+
+	{ // splines
+		vector <int> fac, off, par; vector <double> t, mf; off.push_back(0);
+		for(const auto &sp : model.spline){
+			fac.push_back(sp.param_factor);
+			for(const auto &p : sp.p){ t.push_back(p.t); par.push_back(p.param); mf.push_back(p.multfac);}
+			off.push_back(t.size());
+		}
+		pk.i32(P+"spline_factor_param",fac); pk.i32(P+"spline_off",off); pk.f64(P+"spline_t",t);
+		pk.i32(P+"spline_param",par); pk.f64(P+"spline_multfac",mf);
+	}
+
+	{ // susceptibility, model.cc:1144-1164
+		vector <int> off, par; off.push_back(0);
+		for(auto dp = 0u; dp < D; dp++){
+			for(auto c = 0u; c < data.ndemocat; c++){
+				if(data.democat[c].sus_vari == true) par.push_back(data.democat[c].sus_param[data.democatpos[dp][c]]);
+			}
+			off.push_back(par.size());
+		}
+		pk.i32(P+"sus_off",off); pk.i32(P+"sus_param",par);
+	}
+
+	{ // area factor, model.cc:1182-1250
+		vector <int> re, ae, cp, lp, lm; vector <double> cv, tp;
+		if(model.region_effect.on == true){ for(auto c = 0u; c < A; c++) re.push_back(model.region_effect.area_param[c]);}
+		if(data.area_effect.on == true){ for(auto c = 0u; c < A; c++) ae.push_back(model.area_effect_param_list[c]);}
+		for(auto j = 0u; j < data.ncovar; j++){
+			cp.push_back(model.covariate_param[j]);
+			for(auto c = 0u; c < A; c++) for(auto t = 0u; t < details.period; t++) cv.push_back(data.covar[j].value[c][t]);
+		}
+		if(data.level_effect.on == true){
+			for(auto th : model.level_effect_param_list) lp.push_back(th);
+			for(auto t = 0u; t < details.period; t++) for(auto c = 0u; c < A; c++) lm.push_back(data.level_effect.param_map[t][c]);
+		}
+		for(auto c = 0u; c < A; c++) tp.push_back(data.area[c].total_pop);
+		pk.i32(P+"region_effect_param",re); pk.i32(P+"area_effect_param",ae); pk.i32(P+"covar_param",cp);
+		pk.f64(P+"covar_value",cv); pk.i32(P+"level_param",lp); pk.i32(P+"level_map",lm); pk.f64(P+"area_total_pop",tp);
+	}
+
+	{ // age mixing
+		pk.f64(P+"N0",flat2(data.genQ.N[0].ele),{(long)G,(long)G});
+		vector <int> ms, off, ag; off.push_back(0);
+		for(const auto &mm : data.genQ.matmod){
+			ms.push_back(mm.spline_ref);
+			for(auto a : mm.ages) ag.push_back(a);
+			off.push_back(ag.size());
+		}
+		pk.i32(P+"matmod_spline",ms); pk.i32(P+"matmod_age_off",off); pk.i32(P+"matmod_age",ag);
+		vector <int> da; for(auto dp = 0u; dp < Dq; dp++) da.push_back(data.democatpos[dp][0]);
+		pk.i32(P+"dp_age",da);
+	}
+
+	{ // beta from R
+		vector <int> sr, off, ar, rf; vector <double> dist; off.push_back(0);
+		for(const auto &info : model.Rspline_info){
+			sr.push_back(info.spline_ref);
+			for(auto c : info.area) ar.push_back(c);
+			off.push_back(ar.size());
+			if(info.democatpos_dist.size() != Dq){ cerr << "R_dist size" << endl; exit(1);}
+			for(auto v : info.democatpos_dist) dist.push_back(v);
+		}
+		for(auto st = 0u; st < S; st++) rf.push_back(data.strain[st].Rfactor_param);
+		pk.i32(P+"R_spline_ref",sr); pk.i32(P+"R_area_off",off); pk.i32(P+"R_area",ar);
+		pk.f64(P+"R_dist",dist,{(long)model.Rspline_info.size(),(long)Dq}); pk.i32(P+"strain_Rfactor_param",rf);
+	}
+
+	{ // efoi
+		vector <int> sr, ref; vector <double> ad;
+		for(const auto &info : model.efoispline_info){
+			sr.push_back(info.spline_ref);
+			if(info.efoi_agedist.size() != G){ cerr << "efoi_agedist size" << endl; exit(1);}
+			for(auto v : info.efoi_agedist) ad.push_back(v);
+		}
+		for(auto st = 0u; st < S; st++) for(auto c = 0u; c < A; c++) ref.push_back(model.efoi_spl_ref[st][c]);
+		pk.i32(P+"efoi_spline_ref",sr); pk.f64(P+"efoi_agedist",ad,{(long)model.efoispline_info.size(),(long)G});
+		pk.i32(P+"efoi_ref",ref,{(long)S,(long)A});
+	}
+
+	{ // geographic mixing
+		vector <int> off, to; vector <double> val, diag, fac; off.push_back(0);
+		const auto &M = data.genQ.M;
+		for(auto c = 0u; c < A; c++){
+			for(auto j = 0u; j < M.to[c].size(); j++){ to.push_back(M.to[c][j]); val.push_back(M.val[c][j]);}
+			off.push_back(to.size());
+			diag.push_back(M.diag[c]); fac.push_back(data.genQ.factor[c]);
+		}
+		pk.i32(P+"M_off",off); pk.i32(P+"M_to",to); pk.f64(P+"M_val",val); pk.f64(P+"M_diag",diag); pk.f64(P+"M_factor",fac);
+	}
+
+	{ // initial population
+		vector <double> pi;
+		for(auto c = 0u; c < A; c++) for(auto co = 0u; co < C; co++) for(auto dp = 0u; dp < D; dp++) pi.push_back(data.area[c].pop_init[co][dp]);
+		pk.f64(P+"pop_init",pi,{(long)A,(long)C,(long)D});
+	}
+
+	{ // observations
+		vector <double> val, sd, fac, shape, thr; vector <int> fs, tab, om, si, sf, aoff, ar, doff, dp, ttoff, tt, tcoff, tc;
+		aoff.push_back(0); doff.push_back(0); ttoff.push_back(0); tcoff.push_back(0);
+		for(const auto &ob : data.obs){
+			val.push_back(ob.value); sd.push_back(ob.sd); fac.push_back(ob.factor); shape.push_back(ob.shape);
+			fs.push_back(u2i(ob.factor_spline)); tab.push_back(ob.datatable); om.push_back((int)ob.obsmodel);
+			si.push_back(ob.sett_i); sf.push_back(ob.sett_f);
+			for(auto c : ob.area) ar.push_back(c);
+			aoff.push_back(ar.size());
+			for(auto d : ob.dp_sel) dp.push_back(d);
+			doff.push_back(dp.size());
+		}
+		for(const auto &dt : data.datatable){
+			for(auto tr : dt.translist) tt.push_back(tr);
+			ttoff.push_back(tt.size());
+			for(auto co : dt.complist) tc.push_back(co);
+			tcoff.push_back(tc.size());
+			thr.push_back(dt.threshold);
+		}
+		pk.f64(P+"obs_value",val); pk.f64(P+"obs_sd",sd); pk.f64(P+"obs_factor",fac); pk.f64(P+"obs_shape",shape);
+		pk.i32(P+"obs_factor_spline",fs); pk.i32(P+"obs_table",tab); pk.i32(P+"obs_model",om);
+		pk.i32(P+"obs_sett_i",si); pk.i32(P+"obs_sett_f",sf);
+		pk.i32(P+"obs_area_off",aoff); pk.i32(P+"obs_area",ar); pk.i32(P+"obs_dp_off",doff); pk.i32(P+"obs_dp",dp);
+		pk.i32(P+"table_trans_off",ttoff); pk.i32(P+"table_trans",tt); pk.i32(P+"table_comp_off",tcoff); pk.i32(P+"table_comp",tc);
+		pk.f64(P+"table_threshold",thr);
+	}
+}
+
+// ---------------------------------------------------------------------------
+// 2. golden vectors
+// ---------------------------------------------------------------------------
+static void dump_derived(Pack &pk, const string &pre, const State &st)
+{
+	pk.f64(pre+"transrate",flat2(st.transrate));
+	pk.f64(pre+"disc_spline",flat2(st.disc_spline));
+	pk.f64(pre+"susceptibility",st.susceptibility);
+	pk.f64(pre+"areafactor",flat2(st.areafactor));
+	pk.f64(pre+"beta",flat3(st.beta));
+	// Ntime is N0[a][b] g_a g_b (model.cc:1254-1285): record it at three steps only
+	auto T = st.Ntime.size();
+	vector <double> nt;
+	for(auto s : {0ul,T/2,T-1}) for(const auto &r : st.Ntime[s]) for(auto v : r) nt.push_back(v);
+	pk.f64(pre+"Ntime3",nt);
+	pk.scalar_d(pre+"genT",st.genT);
+}
+
+static void dump_traj(Pack &pk, const string &pre, const State &st, const ObservationModel &obsmodel, unsigned int T, bool with_pop)
+{
+	pk.f64(pre+"transnum",flat4(st.transnum,T));
+	pk.f64(pre+"transmean",flat4(st.transmean,T));
+	if(with_pop){
+		pk.f64(pre+"pop",flat4(st.pop,T));
+		pk.f64(pre+"Imap",flat3(st.Imap));
+		pk.f64(pre+"Idiag",flat3(st.Idiag));
+	}
+	pk.scalar_d(pre+"EF",st.EF);
+	pk.f64(pre+"obs_value",obsmodel.get_obs_value(&st));
+	pk.f64(pre+"EF_datatable",obsmodel.get_EF_datatable(&st));
+	pk.scalar_d(pre+"Li",st.likelihood());
+}
+
+int main(int argc, char **argv)
+{
+	if(argc < 5){ cerr << "usage: ref_harness out.bpk ntheta seed inputfile=... mode=... [key=value ...]" << endl; return 1;}
+	string outfile = argv[1];
+	int ntheta = atoi(argv[2]);
+	int seed = atoi(argv[3]);
+	bool big = getenv("BEEP_HARNESS_BIG") != NULL;                     // England_AS-sized: skip bulky arrays
+
+	timersinit();
+	vector <char*> av; av.push_back(argv[0]); for(int i = 4; i < argc; i++) av.push_back(argv[i]);
+
+	Inputs inputs((int)av.size(),av.data());
+	Details details(inputs);
+	Mpi mpi(details);
+	Data data(inputs,details,mpi);
+	Model model(inputs,details,data,mpi);
+	sran(seed);
+	if(details.mode != PMCMC_INF){                                      // details.cc:110-121 (same rule, any mode)
+		auto max_dt = inputs.find_maximum_timestep();
+		details.pmcmc_obs_period = details.division_per_time*max_dt*int(details.period/(max_dt*10.0));
+		if(details.pmcmc_obs_period == 0) details.pmcmc_obs_period = details.ndivision;
+	}
+	ObservationModel obsmodel(details,data,model);
+	if(details.mode != PMCMC_INF) obsmodel.split_observations();       // obsmodel.cc:326-348
+	Output output(details,data,model,inputs,obsmodel,mpi);
+
+	Pack pk(outfile.c_str());
+	export_desc(pk,details,data,model);
+
+	auto T = details.ndivision;
+	pk.scalar_i("meta.ntheta",ntheta);
+	pk.scalar_i("meta.seed",seed);
+	pk.scalar_i("meta.nsection",obsmodel.nsection);
+	{ vector <int> ti, tf; for(auto s = 0u; s < obsmodel.nsection; s++){ ti.push_back(obsmodel.section_ti[s]); tf.push_back(obsmodel.section_tf[s]);}
+		pk.i32("meta.section_ti",ti); pk.i32("meta.section_tf",tf);}
+
+	// ---- parameter vectors: the TOML 'value's when they are complete, then prior samples
+	vector < vector <double> > theta;
+	{
+		auto sv = model.simulated_values();
+		bool ok = true; for(auto v : sv) if(v == UNSET || std::isnan(v)) ok = false;
+		if(ok && model.inbounds(sv) == false && details.siminf != SIMULATE) ok = false;
+		if(ok) theta.push_back(sv);
+		auto tries = 0u;
+		while((int)theta.size() < ntheta && tries < 1000){
+			auto th = model.sample_from_prior(); tries++;
+			if(model.inbounds(th) == true || details.siminf == SIMULATE) theta.push_back(th);
+		}
+		pk.f64("theta",flat2(theta),{(long)theta.size(),(long)model.param.size()});
+		vector <double> pr; for(const auto &th : theta) pr.push_back(model.prior(th));
+		pk.f64("prior",pr);
+	}
+
+	const bool stoch0 = details.stochastic;
+	vector <Particle> stoch_part;
+
+	for(auto k = 0u; k < theta.size(); k++){
+		string pre = "th"+to_string(k)+".";
+		State st(details,data,model,obsmodel);
+
+		// (i) derived tables, State::set_param (state.cc:66-91)
+		st.set_param(theta[k]);
+		dump_derived(pk,pre,st);
+
+		// (ii) deterministic trajectory (state.cc:627 with details.stochastic == false)
+		details.stochastic = false;
+		st.simulate(theta[k]);
+		dump_traj(pk,pre+"det.",st,obsmodel,T,!big);
+		{ vector <double> Ls; for(auto s = 0u; s < obsmodel.nsection; s++) Ls.push_back(obsmodel.calculate_section(&st,s)); pk.f64(pre+"det.L_section",Ls);}
+
+		// (iii) stochastic trajectory, injected sequential stream
+		details.stochastic = true;
+		inject_on(seed,k); g_ndraw = 0;
+		st.simulate(theta[k]);
+		inject_off();
+		pk.scalar_i(pre+"sto.ndraw",(int)g_ndraw);
+		dump_traj(pk,pre+"sto.",st,obsmodel,T,false);
+		{ vector <double> Ls; for(auto s = 0u; s < obsmodel.nsection; s++) Ls.push_back(obsmodel.calculate_section(&st,s)); pk.f64(pre+"sto.L_section",Ls);}
+		stoch_part.push_back(st.create_particle(0));
+
+		// (iv) sectioned simulation as PMCMC::obs_prob does (pmcmc.cc:190-199), same stream
+		if(k == 0){
+			inject_on(seed,1000+k);
+			vector <double> Ls;
+			for(auto s = 0u; s < obsmodel.nsection; s++){
+				st.simulate(obsmodel.section_ti[s],obsmodel.section_tf[s]);
+				Ls.push_back(obsmodel.calculate_section(&st,s));
+			}
+			inject_off();
+			pk.f64(pre+"sec.transnum",flat4(st.transnum,T));
+			pk.f64(pre+"sec.L_section",Ls);
+		}
+		details.stochastic = stoch0;
+	}
+
+	// ---- model-based proposals, Mbp::mbp (mbp.cc:252-330)
+	if(theta.size() >= 2){
+		details.stochastic = true;
+		Mbp mbp(INVT,details,data,model,obsmodel,output,mpi);
+		mbp.invT = 1; mbp.EFcut = UNSET;
+
+		// (v) pure MBP from theta0's trajectory towards theta1
+		mbp.initial->initialise_from_particle(stoch_part[0]);
+		pk.f64("mbp.init.transmean",flat4(mbp.initial->transmean,T));
+		pk.scalar_d("mbp.init.Li",mbp.initial->likelihood());
+		inject_on(seed,2000); g_ndraw = 0;
+		auto ok = mbp.mbp(theta[1],INF_DIF_UPDATE);
+		inject_off();
+		pk.scalar_i("mbp.a.status",ok == SUCCESS ? 1 : 0);
+		pk.scalar_i("mbp.a.ndraw",(int)g_ndraw);
+		if(ok == SUCCESS){
+			mbp.propose->set_EF();
+			pk.f64("mbp.a.transnum",flat4(mbp.propose->transnum,T));
+			pk.f64("mbp.a.transmean",flat4(mbp.propose->transmean,T));
+			pk.scalar_d("mbp.a.EF",mbp.propose->EF);
+			pk.scalar_d("mbp.a.Li",mbp.propose->likelihood());
+		}
+
+		// (vi) mixed SIMU/MBP with the same parameters (mbp_slicetime / mbp_fixedtree pattern, mbp.cc:656-697)
+		vector <int> mask;
+		for(auto sett = 0u; sett < T; sett++){
+			for(auto c = 0u; c < data.narea; c++){
+				bool simu = (sett >= T/3 && sett < (2*T)/3 && (c%2 == 0));
+				mbp.simu_or_mbp[sett][c] = simu ? SIMU : MBP;
+				mask.push_back(simu ? 1 : 0);
+			}
+		}
+		pk.i32("mbp.b.mask",mask,{(long)T,(long)data.narea});
+		inject_on(seed,3000);
+		ok = mbp.mbp(theta[0],INF_DIF_UPDATE);
+		inject_off();
+		pk.scalar_i("mbp.b.status",ok == SUCCESS ? 1 : 0);
+		if(ok == SUCCESS){
+			mbp.propose->set_EF();
+			pk.f64("mbp.b.transnum",flat4(mbp.propose->transnum,T));
+			pk.f64("mbp.b.transmean",flat4(mbp.propose->transmean,T));
+			pk.scalar_d("mbp.b.EF",mbp.propose->EF);
+		}
+		mbp.simu_or_mbp_reset();
+
+		// (vii) parameter proposal with fixed events (mbp.cc:460-491): transmean under theta1, transnum of theta0
+		mbp.copy_initial_to_propse();
+		mbp.propose->set_param(theta[1]);
+		for(auto sett = 0u; sett < T; sett++) for(auto c = 0u; c < data.narea; c++) mbp.propose->set_transmean(sett,c);
+		pk.scalar_d("mbp.c.Li",mbp.propose->likelihood());
+		pk.f64("mbp.c.transmean",flat4(mbp.propose->transmean,T));
+		details.stochastic = stoch0;
+	}
+
+	pk.close();
+	cout << "ref_harness: wrote " << outfile << " (" << pk.n << " arrays)" << endl;
+	return 0;
+}

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_harness (built by oracle/ref/build_ref.sh from the sources
+under /root/reference) on the reference's own worked examples and converts the
+BPK1 dumps to compressed .npz fixtures.  The GPU box has no /root/reference, so
+the fixtures are committed; this script is how they were made:
+
+    ./oracle/ref/build_ref.sh && python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from beep_b200.bpk import read_bpk  # noqa: E402
+
+REF = os.environ.get("BEEP_REFERENCE", "/root/reference")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+# name -> (toml relative to the reference root, harness args, ntheta, seed)
+CASES = {
+    # BASELINE.json configs[0]: EX.toml in simulation mode
+    "EX_sim": ("examples/EX.toml", ["mode=sim"], 1, 7),
+    # the same model in inference mode (real observation values)
+    "EX_inf": ("examples/EX.toml", ["mode=mcmcmbp", "nsample=10"], 3, 7),
+    # BASELINE.json configs[1]
+    "EX_A1": ("examples/EX_A1.toml", ["mode=mcmcmbp", "nsample=10"], 3, 11),
+    # EX_B1 (marginal + population-fraction data) cannot be used: the reference itself aborts on it at this
+    # commit, in inference mode ("Cannot have zero variance", data.cc:1113) and in mode=sim (Utils error 2)
+    "EX_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 17),   # Poisson observation model
+    "EX_B6": ("examples/EX_B6.toml", ["mode=mcmcmbp", "nsample=10"], 2, 19),   # observation factor spline
+    "EX_C2": ("examples/EX_C2.toml", ["mode=mcmcmbp", "nsample=10"], 3, 23),   # 10 areas, covariates, area effects, Dirichlet
+    "EX_C4": ("examples/EX_C4.toml", ["mode=mcmcmbp", "nsample=10"], 3, 29),   # 4 age groups
+    "EX_C5": ("examples/EX_C5.toml", ["mode=mcmcmbp", "nsample=10"], 2, 31),   # geographic mixing spline
+    "EX_C6": ("examples/EX_C6.toml", ["mode=mcmcmbp", "nsample=10"], 2, 37),   # two strains
+    "EX_D3": ("examples/EX_D3.toml", ["mode=mcmcmbp", "nsample=10"], 2, 41),   # level effects / tv covariates
+    # EX_E2 has smoothed-spline priors that only mode=map can sample (model.cc:741): simulation mode
+    "EX_E2": ("examples/EX_E2.toml", ["mode=sim"], 1, 43),   # time-varying age matrix
+}
+
+
+def convert(bpk_path, out_path):
+    d = read_bpk(bpk_path)
+    out = {}
+    for k, v in d.items():
+        if k.endswith("det.transmean"):
+            # deterministic dynamics: transnum IS transmean (state.cc:627)
+            assert np.array_equal(v, d[k.replace("transmean", "transnum")])
+            continue
+        if k.endswith(".transnum") and ".det." not in k:
+            assert np.all(v == np.round(v))
+            v = v.astype(np.int32)
+        if k.endswith(".mask"):
+            v = v.astype(np.uint8)
+        out[k] = v
+    np.savez_compressed(out_path, **out)
+    return len(out)
+
+
+def main():
+    only = sys.argv[1:]
+    if not os.path.exists(HARNESS):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "ref", "build_ref.sh")])
+    work = tempfile.mkdtemp(prefix="beep_golden_")
+    # the reference resolves datadir/outputdir relative to the cwd and writes
+    # its output there: run in a scratch tree of symlinks, never in /root/reference
+    os.makedirs(os.path.join(work, "examples"))
+    for f in os.listdir(os.path.join(REF, "examples")):
+        os.symlink(os.path.join(REF, "examples", f), os.path.join(work, "examples", f))
+    for name, (toml, args, ntheta, seed) in CASES.items():
+        if only and name not in only:
+            continue
+        bpk = os.path.join(work, name + ".bpk")
+        cmd = [HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
+        r = subprocess.run(cmd, cwd=work, capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(bpk):
+            print(f"{name}: harness FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        n = convert(bpk, out)
+        print(f"{name}: {n} arrays, {os.path.getsize(out) / 1024:.0f} KiB")
+    shutil.rmtree(work, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
