@@ -1,0 +1,83 @@
+/* dev_types.h -- device-side views of the model tables and of a particle batch.
+ *
+ * DevModel is BeepModelDesc (include/beep_model_fields.def) after the engine has
+ * uploaded it and built the derived read-only indices (transposed mixing matrix,
+ * observation cell index, sections).  DevBatch is the per-batch state in HBM.
+ *
+ * HBM layout (P = particles of the batch; "tile" = one (particle, area) pair):
+ *   theta, pd            [P][nparam]           raw / Dirichlet-corrected parameters
+ *   transrate            [P][J][D]             State::transrate      (state.hh:58)
+ *   disc_spline          [P][nspline][T]       State::disc_spline    (state.hh:57)
+ *   sus                  [P][D]                State::susceptibility (state.hh:59)
+ *   areafactor           [P][period][A]        State::areafactor     (state.hh:60)
+ *   betaR                [P][S][nR][T]         State::beta per R-spline group (areas of
+ *                                              one group share the series, model.cc:1343)
+ *   infco                [P][C]                infectivity of each compartment
+ *   pop_cur              [P][A][C][D]          population at the batch's current step
+ *   dinf                 [2][P][S][A][G]       infectivity by (area, age), double buffered
+ *                                              (only the grid-synchronised kernel uses it)
+ *   tn (int32)           [P][T][A][J][D]       State::transnum, dp innermost
+ *   tm (double)          [P][T][A][J][D]       State::transmean
+ *   poptraj              [P][T][A][C][D]       State::pop (tests / outputs only)
+ *   obs_partial          [P][nslot]            per (observation, area) running sums
+ *   obs_val              [P][nobs]             ObservationModel::get_obs_value
+ * A tile's J*D (or C*D) block is contiguous, so a warp reads and writes it with
+ * unit-stride lanes.
+ */
+#ifndef BEEP_DEV_TYPES_H
+#define BEEP_DEV_TYPES_H
+
+#include <stdint.h>
+
+struct ObsEnt { int ob; int slot; };
+
+struct DevModel {
+	int T, period, spu, A, C, J, D, G, S, Dq, nparam, nspline, nobs, ntable;
+	int stochastic, siminf, itr, geo_spline, nR, nefoi, ninf, nmm, ncovar, nlevel, ndir;
+	int nslot, nsection, has_region, has_area_eff, age_fast, M_nnz;
+	double popsize, dt;
+
+	const int *dir_off, *dir_th; const double *dir_frac;
+	const int *trans_from, *trans_to, *trans_inf; const double *trans_shape;
+	const int *trans_mean_param, *trans_prob_param;
+	const int *comp_inf_param, *inf_state, *inf_ref;
+	const int *spline_factor_param, *spline_off, *spline_param; const double *spline_t, *spline_multfac;
+	const int *sus_off, *sus_param;
+	const int *region_effect_param, *area_effect_param, *covar_param; const double *covar_value;
+	const int *level_param, *level_map; const double *area_total_pop;
+	const double *N0, *N0T; const int *mm_spline, *mm_cnt; const int *dp_age;
+	const int *R_spline_ref, *area_rgrp; const double *R_dist; const int *strain_Rfactor_param;
+	const int *efoi_spline_ref, *efoi_ref; const double *efoi_agedist;
+	const int *Min_off, *Min_src; const double *Min_val; const double *M_diag, *M_factor;
+	const double *pop_init;
+	const double *obs_value, *obs_sd, *obs_factor, *obs_shape;
+	const int *obs_fs, *obs_table, *obs_model, *obs_section, *obs_slot_off;
+	const unsigned long long *obs_tmask, *obs_cmask, *obs_dmask;
+	const int *cell_off; const ObsEnt *cell_ent;
+	const double *table_threshold;
+	const int *section_ti, *section_tf;
+};
+
+struct DevBatch {
+	int P; unsigned flags;
+	double *theta, *pd, *transrate, *disc_spline, *sus, *areafactor, *betaR, *infco;
+	double *pop_cur, *dinf;
+	int *tn; double *tm; double *poptraj;
+	double *obs_partial, *obs_val, *L, *EFtab, *Li;
+	unsigned long long *stream_id;
+};
+
+enum { MODE_SIM = 0, MODE_MBP = 1, MODE_REPLAY = 2 };
+enum { SYNC_NONE = 0, SYNC_CTA = 1, SYNC_GRID = 2 };
+
+struct TrajArgs {
+	DevModel m;
+	DevBatch b;
+	int ti, tf;
+	unsigned long long seed;
+	/* MBP: the coupled initial state (same slot of the `init` batch) */
+	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
+	int nwarp;          /* warps per CTA */
+};
+
+#endif

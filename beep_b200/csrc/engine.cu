@@ -1,0 +1,913 @@
+/* engine.cu -- C-ABI of the B200-native BEEP latent-state engine (include/beep_b200.h).
+ *
+ * Host logic only: validates and uploads the flat model description, builds the
+ * derived read-only indices, owns batches of particles in HBM and launches the
+ * kernels of kernels.cuh.  There is no CPU fallback: without a CUDA device
+ * beep_engine_create fails with BEEP_ERR_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+/* ------------------------------------------------------------------------ */
+/* errors                                                                    */
+/* ------------------------------------------------------------------------ */
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	g_err = buf;
+	return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(BEEP_ERR_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *beep_last_error(void) { return g_err.c_str(); }
+extern "C" int beep_version(void) { return 100; }
+
+/* ------------------------------------------------------------------------ */
+/* engine                                                                    */
+/* ------------------------------------------------------------------------ */
+struct BeepEngine {
+	int device = 0, nsm = 0, smem_optin = 0;
+	DevModel dm;
+	std::vector<void *> dev_allocs;
+	std::vector<int> section_ti, section_tf;
+	long long launches = 0;
+	int sync_mode = SYNC_NONE, nwarp = 4;
+	size_t smem_traj = 0;
+	int coop_grid = 0;
+};
+
+struct BeepBatch {
+	BeepEngine *eng = nullptr;
+	DevBatch db;
+	std::vector<void *> dev_allocs;
+	long long bytes = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool have_params = false, have_sim_time = false;
+	int cur_t = 0;
+	double *d_scratch = nullptr;    /* [P*max(ntable,K5_CHUNKS,1)] */
+	double *h_pinned = nullptr; size_t h_pinned_n = 0;
+	unsigned *d_map = nullptr; unsigned char *d_flag = nullptr;
+	unsigned char *d_mask = nullptr; size_t d_mask_n = 0;
+	double *d_tmp = nullptr; size_t d_tmp_n = 0;
+};
+
+template <typename Tp>
+static int upload(BeepEngine *eng, const Tp *src, size_t n, const Tp **out)
+{
+	Tp *d = nullptr;
+	CU(cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(Tp)));
+	eng->dev_allocs.push_back(d);
+	if (n) CU(cudaMemcpy(d, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+	*out = d;
+	return BEEP_OK;
+}
+template <typename Tp>
+static int upload(BeepEngine *eng, const std::vector<Tp> &v, const Tp **out) { return upload(eng, v.data(), v.size(), out); }
+
+#define NEED(cond, ...) do { if (!(cond)) { beep_engine_destroy(eng); return fail(BEEP_ERR_INVALID, __VA_ARGS__); } } while (0)
+#define UP(field, src, n) do { int rc_ = upload(eng, (src), (size_t)(n), &eng->dm.field); if (rc_) { beep_engine_destroy(eng); return rc_; } } while (0)
+#define UPV(field, vec) do { int rc_ = upload(eng, (vec), &eng->dm.field); if (rc_) { beep_engine_destroy(eng); return rc_; } } while (0)
+
+static int choose_launch(BeepEngine *eng);
+
+extern "C" void beep_engine_destroy(BeepEngine *eng)
+{
+	if (!eng) return;
+	cudaSetDevice(eng->device);
+	for (void *p : eng->dev_allocs) cudaFree(p);
+	delete eng;
+}
+
+extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine **out)
+{
+	if (!d || !out) return fail(BEEP_ERR_INVALID, "null argument");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BEEP_ERR_NO_DEVICE, "no CUDA device: the BEEP engine has no CPU fallback");
+	if (device < 0 || device >= ndev) return fail(BEEP_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+	CU(cudaSetDevice(device));
+	BeepEngine *eng = new BeepEngine();
+	eng->device = device;
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	eng->nsm = prop.multiProcessorCount;
+	eng->smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+	DevModel &m = eng->dm;
+	memset(&m, 0, sizeof m);
+	m.T = d->T; m.period = d->period; m.spu = d->spu; m.A = d->A; m.C = d->C; m.J = d->J; m.D = d->D; m.G = d->G; m.S = d->S; m.Dq = d->Dq;
+	m.nparam = d->nparam; m.nspline = d->nspline; m.nobs = d->nobs; m.ntable = d->ntable;
+	m.stochastic = d->stochastic; m.siminf = d->siminf_simulate; m.itr = d->infection_trans; m.geo_spline = d->geo_spline_ref;
+	m.popsize = d->popsize; m.dt = (double)d->period / d->T;
+	m.nR = (int)d->n_R_spline_ref; m.nefoi = (int)d->n_efoi_spline_ref; m.ninf = (int)d->n_inf_state; m.nmm = (int)d->n_matmod_spline;
+	m.ncovar = (int)d->n_covar_param; m.nlevel = (int)d->n_level_param; m.ndir = (int)d->n_dir_off > 0 ? (int)d->n_dir_off - 1 : 0;
+	m.has_region = d->n_region_effect_param > 0; m.has_area_eff = d->n_area_effect_param > 0;
+
+	const int T = m.T, A = m.A, C = m.C, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
+	if (d->n_unsupported > 0) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "the analysis uses democat_change or prediction-mode model modifications, which are outside the hot-path scope"); }
+	NEED(T > 0 && A > 0 && C > 0 && J > 0 && D > 0 && G > 0 && S > 0 && Dq > 0 && m.spu > 0 && m.period > 0, "non-positive dimension");
+	NEED(D == S * Dq, "D (%d) != S*Dq (%d*%d)", D, S, Dq);
+	NEED(m.itr >= 0 && m.itr < J, "infection_trans out of range");
+	NEED(m.geo_spline >= 0 && m.geo_spline < m.nspline, "geo_spline_ref out of range");
+	if (G > 32 || D > 64 || J > 64 || C > 64 || m.ninf > K0_MAXINF) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "engine limits: G<=32 D<=64 J<=64 C<=64 ninf<=%d (got G=%d D=%d J=%d C=%d ninf=%d)", K0_MAXINF, G, D, J, C, m.ninf); }
+	NEED(d->n_trans_from == J && d->n_trans_to == J && d->n_trans_inf == J && d->n_trans_shape == J, "transition arrays must have J entries");
+	NEED(d->n_trans_mean_param == (int64_t)J * D && d->n_trans_prob_param == (int64_t)J * D, "trans_*_param must be [J][D]");
+	NEED(d->n_comp_inf_param == C, "comp_inf_param must be [C]");
+	NEED(d->n_spline_factor_param == m.nspline && d->n_spline_off == m.nspline + 1, "spline arrays inconsistent");
+	NEED(d->n_sus_off == D + 1, "sus_off must be [D+1]");
+	NEED(d->n_N0 == (int64_t)G * G && d->n_dp_age == Dq, "N0 must be [G][G], dp_age [Dq]");
+	NEED(d->n_R_area_off == m.nR + 1 && d->n_R_dist == (int64_t)m.nR * Dq && d->n_strain_Rfactor_param == S, "R-spline arrays inconsistent");
+	NEED(d->n_efoi_agedist == (int64_t)m.nefoi * G && d->n_efoi_ref == (int64_t)S * A, "efoi arrays inconsistent");
+	NEED(d->n_M_off == A + 1 && d->n_M_diag == A && d->n_M_factor == A, "mixing matrix arrays inconsistent");
+	NEED(d->n_pop_init == (int64_t)A * C * D, "pop_init must be [A][C][D]");
+	NEED(d->n_area_total_pop == A, "area_total_pop must be [A]");
+	NEED(d->n_obs_value == m.nobs && d->n_obs_area_off == m.nobs + 1 && d->n_obs_dp_off == m.nobs + 1, "observation arrays inconsistent");
+	NEED(d->n_table_trans_off == m.ntable + 1 && d->n_table_comp_off == m.ntable + 1 && d->n_table_threshold == m.ntable, "datatable arrays inconsistent");
+	NEED(m.ncovar == 0 || d->n_covar_value == (int64_t)m.ncovar * A * m.period, "covar_value must be [ncovar][A][period]");
+	NEED(m.nlevel == 0 || d->n_level_map == (int64_t)m.period * A, "level_map must be [period][A]");
+	for (int tr = 0; tr < J; tr++) NEED(d->trans_from[tr] >= 0 && d->trans_from[tr] < C && d->trans_to[tr] >= 0 && d->trans_to[tr] < C, "transition %d endpoints out of range", tr);
+	for (int i = 0; i < Dq; i++) NEED(d->dp_age[i] >= 0 && d->dp_age[i] < G, "dp_age out of range");
+
+	UP(dir_off, d->dir_off, d->n_dir_off); UP(dir_th, d->dir_th, d->n_dir_th); UP(dir_frac, d->dir_frac, d->n_dir_frac);
+	UP(trans_from, d->trans_from, J); UP(trans_to, d->trans_to, J); UP(trans_inf, d->trans_inf, J); UP(trans_shape, d->trans_shape, J);
+	UP(trans_mean_param, d->trans_mean_param, J * D); UP(trans_prob_param, d->trans_prob_param, J * D);
+	UP(comp_inf_param, d->comp_inf_param, C); UP(inf_state, d->inf_state, m.ninf);
+	{
+		std::vector<int> ir(C, -1);
+		for (int i = 0; i < m.ninf; i++) { NEED(d->inf_state[i] >= 0 && d->inf_state[i] < C, "inf_state out of range"); ir[d->inf_state[i]] = i; }
+		UPV(inf_ref, ir);
+	}
+	UP(spline_factor_param, d->spline_factor_param, m.nspline); UP(spline_off, d->spline_off, m.nspline + 1);
+	UP(spline_param, d->spline_param, d->n_spline_param); UP(spline_t, d->spline_t, d->n_spline_t); UP(spline_multfac, d->spline_multfac, d->n_spline_multfac);
+	UP(sus_off, d->sus_off, D + 1); UP(sus_param, d->sus_param, d->n_sus_param);
+	UP(region_effect_param, d->region_effect_param, d->n_region_effect_param); UP(area_effect_param, d->area_effect_param, d->n_area_effect_param);
+	UP(covar_param, d->covar_param, m.ncovar); UP(covar_value, d->covar_value, d->n_covar_value);
+	UP(level_param, d->level_param, m.nlevel); UP(level_map, d->level_map, d->n_level_map); UP(area_total_pop, d->area_total_pop, A);
+	UP(N0, d->N0, G * G);
+	{
+		std::vector<double> nt((size_t)G * G);
+		for (int a = 0; a < G; a++) for (int b = 0; b < G; b++) nt[(size_t)b * G + a] = d->N0[a * G + b];
+		UPV(N0T, nt);
+		std::vector<int> cnt((size_t)std::max(m.nmm, 1) * G, 0);
+		NEED(d->n_matmod_age_off == m.nmm + 1 || m.nmm == 0, "matmod_age_off must be [nmatmod+1]");
+		for (int mm = 0; mm < m.nmm; mm++)
+			for (int k = d->matmod_age_off[mm]; k < d->matmod_age_off[mm + 1]; k++) { NEED(d->matmod_age[k] >= 0 && d->matmod_age[k] < G, "matmod age out of range"); cnt[(size_t)mm * G + d->matmod_age[k]]++; }
+		UPV(mm_cnt, cnt);
+	}
+	UP(mm_spline, d->matmod_spline, m.nmm); UP(dp_age, d->dp_age, Dq);
+	m.age_fast = 1;
+	for (int i = 0; i < Dq; i++) if (d->dp_age[i] != i % G) m.age_fast = 0;
+	UP(R_spline_ref, d->R_spline_ref, m.nR); UP(R_dist, d->R_dist, d->n_R_dist); UP(strain_Rfactor_param, d->strain_Rfactor_param, S);
+	{
+		std::vector<int> rg(A, -1);
+		for (int i = 0; i < m.nR; i++) for (int k = d->R_area_off[i]; k < d->R_area_off[i + 1]; k++) { NEED(d->R_area[k] >= 0 && d->R_area[k] < A, "R_area out of range"); rg[d->R_area[k]] = i; }
+		for (int c = 0; c < A; c++) NEED(rg[c] >= 0, "area %d belongs to no R spline", c);
+		UPV(area_rgrp, rg);
+	}
+	UP(efoi_spline_ref, d->efoi_spline_ref, m.nefoi); UP(efoi_ref, d->efoi_ref, S * A); UP(efoi_agedist, d->efoi_agedist, d->n_efoi_agedist);
+	{
+		/* transpose of genQ.M (state.cc:204-216 scatters along row c; we gather into c'),
+		 * sources kept in ascending order so that the sum has the reference's order */
+		std::vector<int> off(A + 1, 0), src; std::vector<double> val;
+		const int nnz = d->M_off[A];
+		NEED(d->n_M_to >= nnz && d->n_M_val >= nnz, "M_to / M_val shorter than M_off says");
+		for (int k = 0; k < nnz; k++) { NEED(d->M_to[k] >= 0 && d->M_to[k] < A, "M_to out of range"); off[d->M_to[k] + 1]++; }
+		for (int c = 0; c < A; c++) off[c + 1] += off[c];
+		src.resize(nnz); val.resize(nnz);
+		std::vector<int> fill(off.begin(), off.end() - 1);
+		for (int c = 0; c < A; c++) for (int k = d->M_off[c]; k < d->M_off[c + 1]; k++) { int to = d->M_to[k]; src[fill[to]] = c; val[fill[to]] = d->M_val[k]; fill[to]++; }
+		UPV(Min_off, off); UPV(Min_src, src); UPV(Min_val, val);
+		m.M_nnz = nnz;
+	}
+	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
+	UP(pop_init, d->pop_init, (size_t)A * C * D);
+
+	/* observations: masks, (observation, area) slots, the (sett, area) -> entries index
+	 * (the reference's obs_trans / obs_pop inverted index, obsmodel.cc:174-217) and the
+	 * PMCMC sections (obsmodel.cc:326-348) */
+	{
+		const int O = m.nobs;
+		std::vector<unsigned long long> tmask(O, 0), cmask(O, 0), dmask(O, 0);
+		std::vector<int> slot_off(O + 1, 0), section(O, -1);
+		std::vector<int> cell_cnt((size_t)T * A + 1, 0);
+		for (int ob = 0; ob < O; ob++) {
+			int tb = d->obs_table[ob];
+			NEED(tb >= 0 && tb < m.ntable, "obs_table out of range");
+			for (int k = d->table_trans_off[tb]; k < d->table_trans_off[tb + 1]; k++) { NEED(d->table_trans[k] >= 0 && d->table_trans[k] < J, "table_trans out of range"); tmask[ob] |= 1ull << d->table_trans[k]; }
+			for (int k = d->table_comp_off[tb]; k < d->table_comp_off[tb + 1]; k++) { NEED(d->table_comp[k] >= 0 && d->table_comp[k] < C, "table_comp out of range"); cmask[ob] |= 1ull << d->table_comp[k]; }
+			for (int k = d->obs_dp_off[ob]; k < d->obs_dp_off[ob + 1]; k++) { NEED(d->obs_dp[k] >= 0 && d->obs_dp[k] < D, "obs_dp out of range"); dmask[ob] |= 1ull << d->obs_dp[k]; }
+			int na = d->obs_area_off[ob + 1] - d->obs_area_off[ob];
+			slot_off[ob + 1] = slot_off[ob] + na;
+			NEED(d->obs_sett_i[ob] >= 0 && d->obs_sett_f[ob] <= T && d->obs_sett_i[ob] <= d->obs_sett_f[ob], "observation %d window out of range", ob);
+			NEED(d->obs_factor_spline[ob] < m.nspline, "obs_factor_spline out of range");
+			for (int k = d->obs_area_off[ob]; k < d->obs_area_off[ob + 1]; k++) {
+				NEED(d->obs_area[k] >= 0 && d->obs_area[k] < A, "obs_area out of range");
+				for (int t = d->obs_sett_i[ob]; t < d->obs_sett_f[ob]; t++) cell_cnt[(size_t)t * A + d->obs_area[k] + 1]++;
+			}
+		}
+		m.nslot = slot_off[O];
+		for (size_t i = 0; i < (size_t)T * A; i++) cell_cnt[i + 1] += cell_cnt[i];
+		std::vector<ObsEnt> ent(cell_cnt[(size_t)T * A]);
+		std::vector<int> fill(cell_cnt.begin(), cell_cnt.end() - 1);
+		for (int ob = 0; ob < O; ob++)
+			for (int k = d->obs_area_off[ob]; k < d->obs_area_off[ob + 1]; k++)
+				for (int t = d->obs_sett_i[ob]; t < d->obs_sett_f[ob]; t++) {
+					size_t cell = (size_t)t * A + d->obs_area[k];
+					ent[fill[cell]++] = ObsEnt{ob, slot_off[ob] + (k - d->obs_area_off[ob])};
+				}
+		int per = d->pmcmc_obs_period > 0 ? d->pmcmc_obs_period : T;
+		m.nsection = (T + per - 1) / per;
+		for (int s = 0; s < m.nsection; s++) {
+			int ti = s * per, tf = std::min(ti + per, T);
+			eng->section_ti.push_back(ti); eng->section_tf.push_back(tf);
+			for (int ob = 0; ob < O; ob++)
+				if (section[ob] < 0 && d->obs_sett_i[ob] < tf && d->obs_sett_f[ob] >= ti && d->obs_sett_i[ob] >= ti && d->obs_sett_f[ob] <= tf) section[ob] = s;
+		}
+		UP(obs_value, d->obs_value, O); UP(obs_sd, d->obs_sd, O); UP(obs_factor, d->obs_factor, O); UP(obs_shape, d->obs_shape, O);
+		UP(obs_fs, d->obs_factor_spline, O); UP(obs_table, d->obs_table, O); UP(obs_model, d->obs_model, O);
+		UPV(obs_section, section); UPV(obs_slot_off, slot_off); UPV(obs_tmask, tmask); UPV(obs_cmask, cmask); UPV(obs_dmask, dmask);
+		UPV(cell_off, cell_cnt); UPV(cell_ent, ent);
+		UP(table_threshold, d->table_threshold, m.ntable);
+		UPV(section_ti, eng->section_ti); UPV(section_tf, eng->section_tf);
+	}
+	int rc = choose_launch(eng);
+	if (rc) { beep_engine_destroy(eng); return rc; }
+	*out = eng;
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* launch configuration of the trajectory kernel                             */
+/* ------------------------------------------------------------------------ */
+template <int SYNC>
+static const void *traj_fn(int mode)
+{
+	switch (mode) {
+	case MODE_SIM: return (const void *)k_traj<MODE_SIM, SYNC>;
+	case MODE_MBP: return (const void *)k_traj<MODE_MBP, SYNC>;
+	default: return (const void *)k_traj<MODE_REPLAY, SYNC>;
+	}
+}
+static const void *traj_fn(int mode, int sync)
+{
+	if (sync == SYNC_NONE) return traj_fn<SYNC_NONE>(mode);
+	if (sync == SYNC_CTA) return traj_fn<SYNC_CTA>(mode);
+	return traj_fn<SYNC_GRID>(mode);
+}
+
+static int choose_launch(BeepEngine *eng)
+{
+	const DevModel &m = eng->dm;
+	const size_t CD = (size_t)m.C * m.D, JD = (size_t)m.J * m.D;
+	const char *force = getenv("BEEP_FORCE_SYNC");      /* tests: exercise every flavour on small models */
+	if (m.M_nnz == 0 && m.A >= 1) {
+		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
+		eng->smem_traj = eng->nwarp * (CD + JD + m.D + m.G + 2 * (size_t)m.S * m.G) * sizeof(double);
+	} else {
+		eng->nwarp = std::min(8, m.A);
+		size_t cta = ((size_t)m.A * CD + 2 * (size_t)m.S * m.A * m.G + eng->nwarp * (JD + m.D + m.G)) * sizeof(double);
+		if (cta <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta; }
+		else eng->sync_mode = SYNC_GRID;
+	}
+	if (force) {
+		int f = atoi(force);
+		if (f == SYNC_GRID) eng->sync_mode = SYNC_GRID;
+		else if (f == SYNC_CTA && m.M_nnz == 0) {
+			eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(8, m.A);
+			eng->smem_traj = ((size_t)m.A * CD + 2 * (size_t)m.S * m.A * m.G + eng->nwarp * (JD + m.D + m.G)) * sizeof(double);
+		}
+	}
+	if (eng->sync_mode == SYNC_GRID) {
+		eng->nwarp = 8;
+		eng->smem_traj = eng->nwarp * (CD + JD + m.D + m.G) * sizeof(double);
+	}
+	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
+	for (int mode = 0; mode < 3; mode++) {
+		const void *fn = traj_fn(mode, eng->sync_mode);
+		CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eng->smem_traj));
+	}
+	if (eng->sync_mode == SYNC_GRID) {
+		int coop = 0;
+		CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, eng->device));
+		if (!coop) return fail(BEEP_ERR_UNSUPPORTED, "device lacks cooperative launch");
+		int nb = 0, nbmin = 1 << 30;
+		for (int mode = 0; mode < 3; mode++) {
+			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, traj_fn(mode, SYNC_GRID), eng->nwarp * 32, eng->smem_traj));
+			nbmin = std::min(nbmin, nb);
+		}
+		if (nbmin < 1) return fail(BEEP_ERR_UNSUPPORTED, "trajectory kernel does not fit an SM");
+		eng->coop_grid = nbmin * eng->nsm;
+	}
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* batches                                                                   */
+/* ------------------------------------------------------------------------ */
+template <typename Tp>
+static int balloc(BeepBatch *bt, Tp **out, size_t n)
+{
+	Tp *d = nullptr;
+	size_t bytes = std::max<size_t>(n, 1) * sizeof(Tp);
+	cudaError_t e = cudaMalloc((void **)&d, bytes);
+	if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+	bt->dev_allocs.push_back(d);
+	bt->bytes += (long long)bytes;
+	*out = d;
+	return BEEP_OK;
+}
+#define BA(ptr, n) do { int rc_ = balloc(bt, &(ptr), (size_t)(n)); if (rc_) { beep_batch_destroy(bt); return rc_; } } while (0)
+
+extern "C" void beep_batch_destroy(BeepBatch *bt)
+{
+	if (!bt) return;
+	cudaSetDevice(bt->eng->device);
+	if (bt->stream) cudaStreamSynchronize(bt->stream);
+	for (void *p : bt->dev_allocs) cudaFree(p);
+	if (bt->h_pinned) cudaFreeHost(bt->h_pinned);
+	if (bt->ev0) cudaEventDestroy(bt->ev0);
+	if (bt->ev1) cudaEventDestroy(bt->ev1);
+	if (bt->stream) cudaStreamDestroy(bt->stream);
+	delete bt;
+}
+
+extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBatch **out)
+{
+	if (!eng || !out || P <= 0) return fail(BEEP_ERR_INVALID, "bad argument to beep_batch_create");
+	*out = nullptr;
+	CU(cudaSetDevice(eng->device));
+	BeepBatch *bt = new BeepBatch();
+	bt->eng = eng;
+	const DevModel &m = eng->dm;
+	DevBatch &b = bt->db;
+	memset(&b, 0, sizeof b);
+	b.P = P; b.flags = flags;
+	cudaError_t e = cudaStreamCreateWithFlags(&bt->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { delete bt; return fail(BEEP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+	cudaEventCreate(&bt->ev0); cudaEventCreate(&bt->ev1);
+	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
+	BA(b.theta, (size_t)P * m.nparam); BA(b.pd, (size_t)P * m.nparam);
+	BA(b.transrate, (size_t)P * m.J * m.D); BA(b.disc_spline, (size_t)P * m.nspline * m.T); BA(b.sus, (size_t)P * m.D);
+	BA(b.areafactor, (size_t)P * m.period * m.A); BA(b.betaR, (size_t)P * m.S * m.nR * m.T); BA(b.infco, (size_t)P * m.C);
+	BA(b.pop_cur, (size_t)P * m.A * m.C * m.D);
+	if (eng->sync_mode == SYNC_GRID) BA(b.dinf, 2 * (size_t)P * m.S * m.A * m.G);
+	if ((flags & BEEP_KEEP_TRANSNUM) && m.stochastic) BA(b.tn, (size_t)P * TAJD);
+	if ((flags & BEEP_KEEP_TRANSMEAN) || ((flags & BEEP_KEEP_TRANSNUM) && !m.stochastic)) { BA(b.tm, (size_t)P * TAJD); b.flags |= BEEP_KEEP_TRANSMEAN; }
+	if (flags & BEEP_KEEP_POP) BA(b.poptraj, (size_t)P * m.T * m.A * m.C * m.D);
+	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
+	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
+	BA(b.stream_id, P);
+	BA(bt->d_scratch, (size_t)P * K5_CHUNKS);
+	BA(bt->d_map, P); BA(bt->d_flag, P);
+	{
+		std::vector<unsigned long long> ids(P);
+		for (int i = 0; i < P; i++) ids[i] = (unsigned long long)i;
+		cudaMemcpy(b.stream_id, ids.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+		cudaMemset(b.obs_partial, 0, (size_t)P * std::max(m.nslot, 1) * sizeof(double));
+		cudaMemset(b.obs_val, 0, (size_t)P * std::max(m.nobs, 1) * sizeof(double));
+	}
+	bt->h_pinned_n = (size_t)P * std::max(std::max(m.nparam, m.ntable), 1);
+	e = cudaMallocHost((void **)&bt->h_pinned, bt->h_pinned_n * sizeof(double));
+	if (e != cudaSuccess) { beep_batch_destroy(bt); return fail(BEEP_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e)); }
+	*out = bt;
+	return BEEP_OK;
+}
+
+extern "C" int beep_batch_size(const BeepBatch *bt) { return bt ? bt->db.P : 0; }
+extern "C" int64_t beep_batch_bytes(const BeepBatch *bt) { return bt ? bt->bytes : 0; }
+extern "C" void *beep_batch_stream(BeepBatch *bt) { return bt ? (void *)bt->stream : nullptr; }
+extern "C" int64_t beep_launch_count(const BeepEngine *eng) { return eng ? eng->launches : 0; }
+extern "C" int beep_sync(BeepBatch *bt)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+extern "C" double beep_last_simulate_ms(const BeepBatch *bt)
+{
+	if (!bt || !bt->have_sim_time) return -1;
+	cudaSetDevice(bt->eng->device);
+	if (cudaEventSynchronize(bt->ev1) != cudaSuccess) return -1;
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, bt->ev0, bt->ev1) != cudaSuccess) return -1;
+	return ms;
+}
+
+/* ------------------------------------------------------------------------ */
+/* K0                                                                        */
+/* ------------------------------------------------------------------------ */
+static int launch_set_param(BeepBatch *bt)
+{
+	BeepEngine *eng = bt->eng;
+	const DevModel &m = eng->dm;
+	size_t smem = (32 + m.Dq + (K0_THREADS / 32) * ((size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq)) * sizeof(double);
+	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_set_param, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_set_param<<<bt->db.P, K0_THREADS, smem, bt->stream>>>(m, bt->db);
+	eng->launches++;
+	CU(cudaGetLastError());
+	bt->have_params = true;
+	return BEEP_OK;
+}
+
+extern "C" int beep_set_params_dev(BeepBatch *bt, const double *theta_dev)
+{
+	if (!bt || !theta_dev) return fail(BEEP_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaMemcpyAsync(bt->db.theta, theta_dev, (size_t)bt->db.P * bt->eng->dm.nparam * sizeof(double), cudaMemcpyDeviceToDevice, bt->stream));
+	return launch_set_param(bt);
+}
+
+extern "C" int beep_set_params(BeepBatch *bt, const double *theta_host)
+{
+	if (!bt || !theta_host) return fail(BEEP_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(bt->eng->device));
+	size_t n = (size_t)bt->db.P * bt->eng->dm.nparam;
+	/* stage through the batch's pinned buffer so the copy is asynchronous and the caller's array is free on return */
+	CU(cudaStreamSynchronize(bt->stream));
+	memcpy(bt->h_pinned, theta_host, n * sizeof(double));
+	CU(cudaMemcpyAsync(bt->db.theta, bt->h_pinned, n * sizeof(double), cudaMemcpyHostToDevice, bt->stream));
+	return launch_set_param(bt);
+}
+
+/* ------------------------------------------------------------------------ */
+/* K1-K3                                                                     */
+/* ------------------------------------------------------------------------ */
+static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, const BeepBatch *init, const unsigned char *d_mask)
+{
+	BeepEngine *eng = bt->eng;
+	const DevModel &m = eng->dm;
+	TrajArgs a;
+	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
+	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
+	a.nwarp = eng->nwarp;
+	const int P = bt->db.P;
+	if (ti == 0) {
+		size_t n = (size_t)P * m.A * m.C * m.D;
+		int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)eng->nsm * 8);
+		k_pop_reset<<<nb, 256, 0, bt->stream>>>(m, bt->db);
+		size_t ns = (size_t)P * std::max(m.nslot, 1);
+		k_zero<<<(int)std::min<size_t>((ns + 255) / 256, (size_t)eng->nsm * 8), 256, 0, bt->stream>>>(bt->db.obs_partial, ns);
+		eng->launches += 2;
+	}
+	CU(cudaEventRecord(bt->ev0, bt->stream));
+	const void *fn = traj_fn(mode, eng->sync_mode);
+	void *args[] = {(void *)&a};
+	if (eng->sync_mode == SYNC_NONE) {
+		long long ntile = (long long)P * m.A;
+		int grid = (int)((ntile + eng->nwarp - 1) / eng->nwarp);
+		CU(cudaLaunchKernel(fn, dim3(grid), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
+	} else if (eng->sync_mode == SYNC_CTA) {
+		CU(cudaLaunchKernel(fn, dim3(P), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
+	} else {
+		long long ntile = (long long)P * m.A;
+		int grid = (int)std::min<long long>(eng->coop_grid, (ntile + eng->nwarp - 1) / eng->nwarp);
+		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
+	}
+	eng->launches++;
+	CU(cudaEventRecord(bt->ev1, bt->stream));
+	bt->have_sim_time = true;
+	bt->cur_t = tf;
+	return BEEP_OK;
+}
+
+static int set_stream_ids(BeepBatch *bt, const uint64_t *ids)
+{
+	if (!ids) return BEEP_OK;
+	CU(cudaStreamSynchronize(bt->stream));
+	CU(cudaMemcpyAsync(bt->db.stream_id, ids, (size_t)bt->db.P * sizeof(uint64_t), cudaMemcpyHostToDevice, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+extern "C" int beep_simulate(BeepBatch *bt, int ti, int tf, uint64_t seed, const uint64_t *stream_id_host)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	const DevModel &m = bt->eng->dm;
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "beep_simulate before beep_set_params");
+	if (ti < 0 || tf > m.T || ti >= tf) return fail(BEEP_ERR_INVALID, "bad step range [%d,%d)", ti, tf);
+	if (ti != 0 && ti != bt->cur_t) return fail(BEEP_ERR_STATE, "simulate(%d,..) but the batch stands at step %d", ti, bt->cur_t);
+	CU(cudaSetDevice(bt->eng->device));
+	int rc = set_stream_ids(bt, stream_id_host);
+	if (rc) return rc;
+	return launch_traj(bt, MODE_SIM, ti, tf, seed, nullptr, nullptr);
+}
+
+extern "C" int beep_mbp(BeepBatch *init, BeepBatch *prop, const uint8_t *simu_mask_host, int inf_update, uint64_t seed, const uint64_t *stream_id_host)
+{
+	(void)inf_update;
+	if (!init || !prop || init == prop) return fail(BEEP_ERR_INVALID, "beep_mbp needs two distinct batches");
+	if (init->eng != prop->eng || init->db.P != prop->db.P) return fail(BEEP_ERR_INVALID, "init and prop batches differ in engine or size");
+	const DevModel &m = prop->eng->dm;
+	if (!m.stochastic) return fail(BEEP_ERR_UNSUPPORTED, "model-based proposals need stochastic dynamics");
+	if (!init->db.tn || !init->db.tm) return fail(BEEP_ERR_STATE, "init batch must keep transnum and transmean");
+	if (!prop->have_params) return fail(BEEP_ERR_STATE, "beep_mbp before beep_set_params on the proposal batch");
+	CU(cudaSetDevice(prop->eng->device));
+	int rc = set_stream_ids(prop, stream_id_host);
+	if (rc) return rc;
+	unsigned char *d_mask = nullptr;
+	if (simu_mask_host) {
+		size_t n = (size_t)prop->db.P * m.T * m.A;
+		if (prop->d_mask_n < n) {
+			rc = balloc(prop, &prop->d_mask, n);
+			if (rc) return rc;
+			prop->d_mask_n = n;
+		}
+		CU(cudaStreamSynchronize(prop->stream));
+		CU(cudaMemcpyAsync(prop->d_mask, simu_mask_host, n, cudaMemcpyHostToDevice, prop->stream));
+		d_mask = prop->d_mask;
+	}
+	/* order after everything queued on the init batch */
+	CU(cudaStreamSynchronize(init->stream));
+	return launch_traj(prop, MODE_MBP, 0, m.T, seed, init, d_mask);
+}
+
+extern "C" int beep_replay(BeepBatch *bt)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	const DevModel &m = bt->eng->dm;
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "beep_replay before parameters were set");
+	if (m.stochastic ? !bt->db.tn : !bt->db.tm) return fail(BEEP_ERR_STATE, "beep_replay needs a batch that keeps transnum");
+	CU(cudaSetDevice(bt->eng->device));
+	return launch_traj(bt, MODE_REPLAY, 0, m.T, 0, nullptr, nullptr);
+}
+
+/* ------------------------------------------------------------------------ */
+/* K4 / K5                                                                   */
+/* ------------------------------------------------------------------------ */
+extern "C" int beep_obs_loglik_dev(BeepBatch *bt, int section, double *L_dev, double *EF_dev)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	BeepEngine *eng = bt->eng;
+	if (section >= eng->dm.nsection) return fail(BEEP_ERR_INVALID, "section %d out of range", section);
+	CU(cudaSetDevice(eng->device));
+	k_obs_final<<<bt->db.P, RED_THREADS, 0, bt->stream>>>(eng->dm, bt->db, section, L_dev ? L_dev : bt->db.L, EF_dev);
+	eng->launches++;
+	CU(cudaGetLastError());
+	return BEEP_OK;
+}
+
+extern "C" int beep_obs_loglik(BeepBatch *bt, int section, double *L_host, double *EF_table_host)
+{
+	if (!bt || !L_host) return fail(BEEP_ERR_INVALID, "null argument");
+	int rc = beep_obs_loglik_dev(bt, section, bt->db.L, EF_table_host ? bt->db.EFtab : nullptr);
+	if (rc) return rc;
+	const int P = bt->db.P, nt = bt->eng->dm.ntable;
+	CU(cudaMemcpyAsync(L_host, bt->db.L, P * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	if (EF_table_host) CU(cudaMemcpyAsync(EF_table_host, bt->db.EFtab, (size_t)P * nt * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	for (int p = 0; p < P; p++) if (std::isnan(L_host[p])) return fail(BEEP_ERR_NUMERIC, "observation log-likelihood of particle %d is NaN (obsmodel.cc:30)", p);
+	return BEEP_OK;
+}
+
+extern "C" int beep_obs_values(BeepBatch *bt, double *out)
+{
+	if (!bt || !out) return fail(BEEP_ERR_INVALID, "null argument");
+	int rc = beep_obs_loglik_dev(bt, -1, bt->db.L, nullptr);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(out, bt->db.obs_val, (size_t)bt->db.P * bt->eng->dm.nobs * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+extern "C" int beep_num_sections(const BeepEngine *eng) { return eng ? eng->dm.nsection : 0; }
+extern "C" int beep_section_range(const BeepEngine *eng, int s, int *ti, int *tf)
+{
+	if (!eng || s < 0 || s >= eng->dm.nsection) return fail(BEEP_ERR_INVALID, "section out of range");
+	if (ti) *ti = eng->section_ti[s];
+	if (tf) *tf = eng->section_tf[s];
+	return BEEP_OK;
+}
+
+extern "C" int beep_latent_loglik(BeepBatch *bt, double *Li_host)
+{
+	if (!bt || !Li_host) return fail(BEEP_ERR_INVALID, "null argument");
+	BeepEngine *eng = bt->eng;
+	const DevModel &m = eng->dm;
+	if (!bt->db.tm || (m.stochastic && !bt->db.tn)) return fail(BEEP_ERR_STATE, "beep_latent_loglik needs a batch that keeps transnum and transmean");
+	CU(cudaSetDevice(eng->device));
+	const int P = bt->db.P;
+	k_latent_partial<<<dim3(K5_CHUNKS, P), RED_THREADS, 0, bt->stream>>>(m, bt->db, bt->d_scratch);
+	k_latent_final<<<(P + 127) / 128, 128, 0, bt->stream>>>(P, bt->d_scratch, bt->db.Li);
+	eng->launches += 2;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(Li_host, bt->db.Li, P * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* K6                                                                        */
+/* ------------------------------------------------------------------------ */
+template <typename Tp>
+static int gather_inplace(BeepBatch *bt, Tp *arr, size_t n, const unsigned *d_map)
+{
+	if (!arr || n == 0) return BEEP_OK;
+	const int P = bt->db.P;
+	size_t need = (size_t)P * n * sizeof(Tp);
+	if (bt->d_tmp_n < need) {
+		/* scratch grows to the largest slab ever permuted; freed with the batch */
+		double *t = nullptr;
+		cudaError_t e = cudaMalloc((void **)&t, need);
+		if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for permute scratch: %s", need, cudaGetErrorString(e));
+		bt->dev_allocs.push_back(t);
+		bt->d_tmp = t; bt->d_tmp_n = need;
+	}
+	Tp *tmp = (Tp *)bt->d_tmp;
+	CU(cudaMemcpyAsync(tmp, arr, need, cudaMemcpyDeviceToDevice, bt->stream));
+	int gx = (int)std::min<size_t>((n + 255) / 256, 1024);
+	k_gather_slab<Tp><<<dim3(gx, P), 256, 0, bt->stream>>>(arr, tmp, d_map, n, P);
+	bt->eng->launches++;
+	CU(cudaGetLastError());
+	return BEEP_OK;
+}
+
+extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what)
+{
+	if (!bt || !src_of_host) return fail(BEEP_ERR_INVALID, "null argument");
+	const DevModel &m = bt->eng->dm;
+	const int P = bt->db.P;
+	for (int p = 0; p < P; p++) if (src_of_host[p] != 0xFFFFFFFFu && src_of_host[p] >= (unsigned)P) return fail(BEEP_ERR_INVALID, "src_of[%d] = %u out of range", p, src_of_host[p]);
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaStreamSynchronize(bt->stream));
+	CU(cudaMemcpyAsync(bt->d_map, src_of_host, P * sizeof(unsigned), cudaMemcpyHostToDevice, bt->stream));
+	int rc;
+	const DevBatch &b = bt->db;
+	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.C * m.D, bt->d_map))) return rc;
+	if (what == BEEP_PERMUTE_SECTION_STATE) return BEEP_OK;      /* mpi.cc:286-288: pop (Imap/Idiag are re-derived from it) */
+	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
+	if ((rc = gather_inplace(bt, b.theta, m.nparam, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.pd, m.nparam, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.transrate, (size_t)m.J * m.D, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.disc_spline, (size_t)m.nspline * m.T, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.sus, m.D, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.areafactor, (size_t)m.period * m.A, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.betaR, (size_t)m.S * m.nR * m.T, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.infco, m.C, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.poptraj, (size_t)m.T * m.A * m.C * m.D, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.obs_partial, m.nslot, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.obs_val, m.nobs, bt->d_map))) return rc;
+	return BEEP_OK;
+}
+
+template <typename Tp>
+static int copy_flagged(BeepBatch *dst, Tp *d, const Tp *s, size_t n)
+{
+	if (!d || !s || n == 0) return BEEP_OK;
+	int gx = (int)std::min<size_t>((n + 255) / 256, 1024);
+	k_copy_flagged<Tp><<<dim3(gx, dst->db.P), 256, 0, dst->stream>>>(d, s, dst->d_flag, n, dst->db.P);
+	dst->eng->launches++;
+	CU(cudaGetLastError());
+	return BEEP_OK;
+}
+
+extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *accept_host)
+{
+	if (!init || !prop || !accept_host || init == prop) return fail(BEEP_ERR_INVALID, "bad argument to beep_accept");
+	if (init->eng != prop->eng || init->db.P != prop->db.P) return fail(BEEP_ERR_INVALID, "init and prop batches differ in engine or size");
+	const DevModel &m = init->eng->dm;
+	CU(cudaSetDevice(init->eng->device));
+	CU(cudaStreamSynchronize(prop->stream));
+	CU(cudaStreamSynchronize(init->stream));
+	CU(cudaMemcpyAsync(init->d_flag, accept_host, init->db.P, cudaMemcpyHostToDevice, init->stream));
+	const DevBatch &a = init->db, &b = prop->db;
+	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
+	int rc;
+	if ((rc = copy_flagged(init, a.theta, b.theta, m.nparam))) return rc;
+	if ((rc = copy_flagged(init, a.pd, b.pd, m.nparam))) return rc;
+	if ((rc = copy_flagged(init, a.transrate, b.transrate, (size_t)m.J * m.D))) return rc;
+	if ((rc = copy_flagged(init, a.disc_spline, b.disc_spline, (size_t)m.nspline * m.T))) return rc;
+	if ((rc = copy_flagged(init, a.sus, b.sus, m.D))) return rc;
+	if ((rc = copy_flagged(init, a.areafactor, b.areafactor, (size_t)m.period * m.A))) return rc;
+	if ((rc = copy_flagged(init, a.betaR, b.betaR, (size_t)m.S * m.nR * m.T))) return rc;
+	if ((rc = copy_flagged(init, a.infco, b.infco, m.C))) return rc;
+	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.C * m.D))) return rc;
+	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;
+	if ((rc = copy_flagged(init, a.tm, b.tm, TAJD))) return rc;
+	if ((rc = copy_flagged(init, a.poptraj, b.poptraj, (size_t)m.T * m.A * m.C * m.D))) return rc;
+	if ((rc = copy_flagged(init, a.obs_partial, b.obs_partial, m.nslot))) return rc;
+	if ((rc = copy_flagged(init, a.obs_val, b.obs_val, m.nobs))) return rc;
+	CU(cudaStreamSynchronize(init->stream));
+	init->have_params = true;
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* particle import / export, read-back                                       */
+/* ------------------------------------------------------------------------ */
+static int slot_ok(const BeepBatch *bt, int slot)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	if (slot < 0 || slot >= bt->db.P) return fail(BEEP_ERR_INVALID, "slot %d out of range", slot);
+	return BEEP_OK;
+}
+
+extern "C" int beep_get_trajectory(BeepBatch *bt, int slot, int which, double *out, int64_t n)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	if (!out) return fail(BEEP_ERR_INVALID, "null output");
+	const DevModel &m = bt->eng->dm;
+	CU(cudaSetDevice(bt->eng->device));
+	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D, TACD = (size_t)m.T * m.A * m.C * m.D;
+	if (which == BEEP_TRAJ_TRANSNUM && m.stochastic) {
+		if (!bt->db.tn) return fail(BEEP_ERR_STATE, "batch does not keep transnum");
+		if ((size_t)n != TAJD) return fail(BEEP_ERR_INVALID, "transnum has %zu elements, not %lld", TAJD, (long long)n);
+		std::vector<int> tmp(TAJD);
+		CU(cudaMemcpyAsync(tmp.data(), bt->db.tn + (size_t)slot * TAJD, TAJD * sizeof(int), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaStreamSynchronize(bt->stream));
+		for (size_t i = 0; i < TAJD; i++) out[i] = (double)tmp[i];
+		return BEEP_OK;
+	}
+	if (which == BEEP_TRAJ_TRANSMEAN || which == BEEP_TRAJ_TRANSNUM) {
+		/* deterministic dynamics: transnum IS transmean (state.cc:627) */
+		if (!bt->db.tm) return fail(BEEP_ERR_STATE, "batch does not keep transmean");
+		if ((size_t)n != TAJD) return fail(BEEP_ERR_INVALID, "transmean has %zu elements, not %lld", TAJD, (long long)n);
+		CU(cudaMemcpyAsync(out, bt->db.tm + (size_t)slot * TAJD, TAJD * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaStreamSynchronize(bt->stream));
+		return BEEP_OK;
+	}
+	if (which == BEEP_TRAJ_POP) {
+		if (!bt->db.poptraj) return fail(BEEP_ERR_STATE, "batch does not keep pop");
+		if ((size_t)n != TACD) return fail(BEEP_ERR_INVALID, "pop has %zu elements, not %lld", TACD, (long long)n);
+		CU(cudaMemcpyAsync(out, bt->db.poptraj + (size_t)slot * TACD, TACD * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaStreamSynchronize(bt->stream));
+		return BEEP_OK;
+	}
+	return fail(BEEP_ERR_INVALID, "unknown trajectory selector %d", which);
+}
+
+extern "C" int beep_get_pop(BeepBatch *bt, int slot, double *out, int64_t n)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	const DevModel &m = bt->eng->dm;
+	size_t ACD = (size_t)m.A * m.C * m.D;
+	if (!out || (size_t)n != ACD) return fail(BEEP_ERR_INVALID, "pop has %zu elements", ACD);
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaMemcpyAsync(out, bt->db.pop_cur + (size_t)slot * ACD, ACD * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+extern "C" int beep_get_derived(BeepBatch *bt, int slot, int which, double *out, int64_t n)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	if (!out) return fail(BEEP_ERR_INVALID, "null output");
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "no parameters set");
+	const DevModel &m = bt->eng->dm;
+	const DevBatch &b = bt->db;
+	CU(cudaSetDevice(bt->eng->device));
+	const double *src = nullptr; size_t cnt = 0;
+	switch (which) {
+	case BEEP_DERIVED_TRANSRATE: cnt = (size_t)m.J * m.D; src = b.transrate + slot * cnt; break;
+	case BEEP_DERIVED_DISC_SPLINE: cnt = (size_t)m.nspline * m.T; src = b.disc_spline + slot * cnt; break;
+	case BEEP_DERIVED_SUSCEPTIBILITY: cnt = m.D; src = b.sus + slot * cnt; break;
+	case BEEP_DERIVED_AREAFACTOR: cnt = (size_t)m.period * m.A; src = b.areafactor + slot * cnt; break;
+	case BEEP_DERIVED_BETA: {
+		/* expand the per-R-group series to the reference's [S][A][T] */
+		cnt = (size_t)m.S * m.A * m.T;
+		if ((size_t)n != cnt) return fail(BEEP_ERR_INVALID, "beta has %zu elements, not %lld", cnt, (long long)n);
+		size_t gcnt = (size_t)m.S * m.nR * m.T;
+		std::vector<double> g(gcnt);
+		std::vector<int> rg(m.A);
+		CU(cudaMemcpyAsync(g.data(), b.betaR + slot * gcnt, gcnt * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaMemcpyAsync(rg.data(), m.area_rgrp, m.A * sizeof(int), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaStreamSynchronize(bt->stream));
+		for (int st = 0; st < m.S; st++) for (int c = 0; c < m.A; c++)
+			memcpy(out + ((size_t)st * m.A + c) * m.T, g.data() + ((size_t)st * m.nR + rg[c]) * m.T, m.T * sizeof(double));
+		return BEEP_OK;
+	}
+	case BEEP_DERIVED_AGEFACTOR: {
+		/* g[t][a] = prod_mm spline_mm(t)^cnt_mm[a]; Ntime[t][a][b] = N0[a][b] g[t][a] g[t][b] up to rounding order */
+		cnt = (size_t)m.T * m.G;
+		if ((size_t)n != cnt) return fail(BEEP_ERR_INVALID, "agefactor has %zu elements, not %lld", cnt, (long long)n);
+		size_t scnt = (size_t)m.nspline * m.T;
+		std::vector<double> ds(scnt);
+		std::vector<int> mmc((size_t)std::max(m.nmm, 1) * m.G), mms(std::max(m.nmm, 1));
+		CU(cudaMemcpyAsync(ds.data(), b.disc_spline + slot * scnt, scnt * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+		if (m.nmm) {
+			CU(cudaMemcpyAsync(mmc.data(), m.mm_cnt, (size_t)m.nmm * m.G * sizeof(int), cudaMemcpyDeviceToHost, bt->stream));
+			CU(cudaMemcpyAsync(mms.data(), m.mm_spline, m.nmm * sizeof(int), cudaMemcpyDeviceToHost, bt->stream));
+		}
+		CU(cudaStreamSynchronize(bt->stream));
+		for (int t = 0; t < m.T; t++) for (int a = 0; a < m.G; a++) {
+			double x = 1;
+			for (int mm = 0; mm < m.nmm; mm++) for (int k = 0; k < mmc[(size_t)mm * m.G + a]; k++) x *= ds[(size_t)mms[mm] * m.T + t];
+			out[(size_t)t * m.G + a] = x;
+		}
+		return BEEP_OK;
+	}
+	default: return fail(BEEP_ERR_INVALID, "unknown derived selector %d", which);
+	}
+	if ((size_t)n != cnt) return fail(BEEP_ERR_INVALID, "selector %d has %zu elements, not %lld", which, cnt, (long long)n);
+	CU(cudaMemcpyAsync(out, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+extern "C" int beep_export_particle(BeepBatch *bt, int slot, double *theta_host, double *transnum_host)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	const DevModel &m = bt->eng->dm;
+	CU(cudaSetDevice(bt->eng->device));
+	if (theta_host) {
+		CU(cudaMemcpyAsync(theta_host, bt->db.theta + (size_t)slot * m.nparam, m.nparam * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+		CU(cudaStreamSynchronize(bt->stream));
+	}
+	if (transnum_host) return beep_get_trajectory(bt, slot, BEEP_TRAJ_TRANSNUM, transnum_host, (int64_t)m.T * m.A * m.J * m.D);
+	return BEEP_OK;
+}
+
+extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta_host, const double *transnum_host)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	const DevModel &m = bt->eng->dm;
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaStreamSynchronize(bt->stream));
+	if (theta_host) CU(cudaMemcpy(bt->db.theta + (size_t)slot * m.nparam, theta_host, m.nparam * sizeof(double), cudaMemcpyHostToDevice));
+	if (transnum_host) {
+		const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
+		if (m.stochastic) {
+			if (!bt->db.tn) return fail(BEEP_ERR_STATE, "batch does not keep transnum");
+			std::vector<int> tmp(TAJD);
+			for (size_t i = 0; i < TAJD; i++) tmp[i] = (int)transnum_host[i];
+			CU(cudaMemcpy(bt->db.tn + (size_t)slot * TAJD, tmp.data(), TAJD * sizeof(int), cudaMemcpyHostToDevice));
+		} else {
+			if (!bt->db.tm) return fail(BEEP_ERR_STATE, "batch does not keep transmean");
+			CU(cudaMemcpy(bt->db.tm + (size_t)slot * TAJD, transnum_host, TAJD * sizeof(double), cudaMemcpyHostToDevice));
+		}
+	}
+	/* derived tables of every slot are refreshed from the stored parameters */
+	return launch_set_param(bt);
+}
+
+/* ------------------------------------------------------------------------ */
+/* PMCMC bootstrap, pmcmc.cc:211-268 (host, O(Ntot))                          */
+/* ------------------------------------------------------------------------ */
+extern "C" int beep_bootstrap(const double *L, int ntot, double invT, uint64_t seed, int section, double *loglik_inc, uint32_t *backpart)
+{
+	if (!L || ntot <= 0 || !loglik_inc || !backpart) return fail(BEEP_ERR_INVALID, "bad argument to beep_bootstrap");
+	double Lmax = -1e300;
+	for (int i = 0; i < ntot; i++) if (L[i] > Lmax) Lmax = L[i];
+	std::vector<double> wsum(ntot);
+	double sum = 0;
+	for (int i = 0; i < ntot; i++) { sum += exp(invT * (L[i] - Lmax)); wsum[i] = sum; }
+	*loglik_inc = invT * Lmax + log(sum / ntot);
+	BeepStream rs;
+	beep_stream_init(&rs, seed, (uint32_t)section, 0xB0075u, 0xFFFFFFFEu);
+	std::vector<unsigned char> flag(ntot, 0);
+	std::vector<uint32_t> extra;
+	for (int i = 0; i < ntot; i++) backpart[i] = 0xFFFFFFFFu;
+	for (int i = 0; i < ntot; i++) {
+		double z = beep_next_uniform(&rs) * sum;
+		int lo = 0, hi = ntot - 1;
+		while (lo < hi) { int mid = (lo + hi) / 2; if (z <= wsum[mid]) hi = mid; else lo = mid + 1; }
+		if (!flag[lo]) { flag[lo] = 1; backpart[lo] = (uint32_t)lo; }      /* stay in place if chosen, pmcmc.cc:250-258 */
+		else extra.push_back((uint32_t)lo);
+	}
+	size_t k = 0;
+	for (int i = 0; i < ntot; i++) if (backpart[i] == 0xFFFFFFFFu) backpart[i] = extra[k++];
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* sampler parity entry points (used by tests only; device samplers)          */
+/* ------------------------------------------------------------------------ */
+extern "C" int beep_test_poisson(uint64_t seed, uint64_t stream_id, const double *lam_host, int n, int32_t *out_host)
+{
+	double *dl = nullptr; int *dout = nullptr;
+	CU(cudaMalloc((void **)&dl, n * sizeof(double))); CU(cudaMalloc((void **)&dout, n * sizeof(int)));
+	CU(cudaMemcpy(dl, lam_host, n * sizeof(double), cudaMemcpyHostToDevice));
+	k_poisson_many<<<(n + 127) / 128, 128>>>(seed, stream_id, dl, n, dout);
+	CU(cudaMemcpy(out_host, dout, n * sizeof(int), cudaMemcpyDeviceToHost));
+	cudaFree(dl); cudaFree(dout);
+	return BEEP_OK;
+}
+extern "C" int beep_test_binomial(uint64_t seed, uint64_t stream_id, const double *p_host, const int32_t *n_host, int n, int32_t *out_host)
+{
+	double *dp = nullptr; int *dn = nullptr, *dout = nullptr;
+	CU(cudaMalloc((void **)&dp, n * sizeof(double))); CU(cudaMalloc((void **)&dn, n * sizeof(int))); CU(cudaMalloc((void **)&dout, n * sizeof(int)));
+	CU(cudaMemcpy(dp, p_host, n * sizeof(double), cudaMemcpyHostToDevice)); CU(cudaMemcpy(dn, n_host, n * sizeof(int), cudaMemcpyHostToDevice));
+	k_binomial_many<<<(n + 127) / 128, 128>>>(seed, stream_id, dp, dn, n, dout);
+	CU(cudaMemcpy(out_host, dout, n * sizeof(int), cudaMemcpyDeviceToHost));
+	cudaFree(dp); cudaFree(dn); cudaFree(dout);
+	return BEEP_OK;
+}

@@ -1,0 +1,729 @@
+/* kernels.cuh -- hand-written sm_100a kernels of the BEEP latent-state engine.
+ *
+ *   k_set_param   K0   State::set_param                    reference src/state.cc:66-91
+ *   k_traj<M,S>   K1-3 State::simulate / Mbp::mbp /        src/state.cc:596-638,
+ *                      State::initialise_from_particle     src/mbp.cc:252-330, src/state.cc:294-322
+ *                      (+ obs accumulation, obsmodel.cc:74-109)
+ *   k_obs_final   K4   ObservationModel::calculate*        src/obsmodel.cc:22-58,245-322
+ *   k_latent      K5   State::likelihood                   src/state.cc:812-826
+ *   k_permute..   K6   Mpi::copy_particles / end_sec_swap  src/mpi.cc:81-165,215-327
+ *
+ * Mapping of the trajectory kernel: ONE WARP PER (particle, area) TILE.  The
+ * tile's population pop[C][D] lives in shared memory for the whole time loop
+ * (SYNC_NONE / SYNC_CTA) or is streamed through shared memory once per step
+ * (SYNC_GRID); lanes run over the J*D cells of the tile for the draws (one
+ * Philox stream per cell) and over dp / age for the population update and the
+ * force of infection.  The per-step coupling between areas (Imap needs dinf of
+ * every source area, state.cc:204-216) is a barrier whose scope is chosen by
+ * the launcher: none (uncoupled areas), __syncthreads (a CTA owns a particle)
+ * or a cooperative grid sync (a particle spans the grid).
+ *
+ * The translation unit is compiled with --fmad=false: every double operation
+ * below is the same IEEE operation, in the same order, as in the CPU oracle
+ * (oracle/beep_oracle.c, built -ffp-contract=off), so that transition means --
+ * and hence the integer draws -- are bit-identical.
+ */
+#ifndef BEEP_KERNELS_CUH
+#define BEEP_KERNELS_CUH
+
+#include <cooperative_groups.h>
+#include "dev_types.h"
+#include "beep_b200.h"
+#include "beep_rng.h"
+
+namespace cg = cooperative_groups;
+
+#define FULLMASK 0xffffffffu
+#define BEEP_LARGE 1000000000.0
+
+/* ------------------------------------------------------------------------ */
+/* K0  set_param                                                             */
+/* ------------------------------------------------------------------------ */
+
+/* Ntime[t][a][b] = N0[a][b] * prod_mm f_mm^(cnt_mm[a]+cnt_mm[b])   (model.cc:1254-1285):
+ * every matmod multiplies row a and column a of each listed age by its spline value. */
+__device__ __forceinline__ double ntime_elem(const DevModel &m, const double *ds, int t, int a, int b, double n0)
+{
+	double x = n0;
+	for (int mm = 0; mm < m.nmm; mm++) {
+		int k = m.mm_cnt[mm * m.G + a] + m.mm_cnt[mm * m.G + b];
+		if (k > 0) {
+			double f = ds[m.mm_spline[mm] * m.T + t];
+			for (; k > 0; k--) x *= f;
+		}
+	}
+	return x;
+}
+
+#define K0_THREADS 128
+#define K0_MAXINF 8
+
+/* dynamic smem: nwarp * (Dq*(Dq+1) + 3*Dq) doubles + 32 doubles */
+__global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b)
+{
+	extern __shared__ double sm[];
+	const int p = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
+	const double *theta = b.theta + (size_t)p * m.nparam;
+	double *pd = b.pd + (size_t)p * m.nparam;
+	double *transrate = b.transrate + (size_t)p * J * D;
+	double *ds = b.disc_spline + (size_t)p * m.nspline * T;
+	double *sus = b.sus + (size_t)p * D;
+	double *af = b.areafactor + (size_t)p * m.period * A;
+	double *betaR = b.betaR + (size_t)p * S * m.nR * T;
+	double *infco = b.infco + (size_t)p * m.C;
+
+	/* model.cc:2685-2695 dirichlet_correct */
+	for (int i = tid; i < m.nparam; i += nth) pd[i] = theta[i];
+	__syncthreads();
+	for (int g = tid; g < m.ndir; g += nth) {
+		double sum = 0;
+		for (int k = m.dir_off[g]; k < m.dir_off[g + 1]; k++) sum += theta[m.dir_th[k]];
+		for (int k = m.dir_off[g]; k < m.dir_off[g + 1]; k++) pd[m.dir_th[k]] = theta[m.dir_th[k]] / (m.dir_frac[k] * sum);
+	}
+	__syncthreads();
+
+	/* model.cc:1116-1140 create_transrate */
+	for (int e = tid; e < J * D; e += nth) {
+		int tr = e / D;
+		double rate = 0;
+		if (!m.trans_inf[tr]) {
+			double mean = pd[m.trans_mean_param[e]] / m.trans_shape[tr];
+			rate = 1.0 / mean;
+			if (m.trans_prob_param[e] >= 0) rate *= pd[m.trans_prob_param[e]];
+		}
+		transrate[e] = rate;
+	}
+	/* model.cc:1144-1164 create_susceptibility */
+	for (int dp = tid; dp < D; dp += nth) {
+		double val = 1.0;
+		for (int k = m.sus_off[dp]; k < m.sus_off[dp + 1]; k++) val *= pd[m.sus_param[k]];
+		sus[dp] = val;
+	}
+	for (int co = tid; co < m.C; co += nth) infco[co] = pd[m.comp_inf_param[co]];
+	/* model.cc:1020-1043 create_disc_spline: one thread walks one spline */
+	for (int sp = tid; sp < m.nspline; sp += nth) {
+		double factor = pd[m.spline_factor_param[sp]];
+		int o = m.spline_off[sp], np = m.spline_off[sp + 1] - o;
+		int q = 0;
+		double prev = 0;
+		for (int st = 0; st < T; st++) {
+			double t = (double)((st + 0.5) * m.period) / T;
+			while (q + 1 < np && t > m.spline_t[o + q + 1]) q++;
+			double v;
+			if (q + 1 == np) v = prev;
+			else {
+				double fac = (t - m.spline_t[o + q]) / (m.spline_t[o + q + 1] - m.spline_t[o + q]);
+				v = factor * (pd[m.spline_param[o + q]] * m.spline_multfac[o + q] * (1 - fac) +
+				              pd[m.spline_param[o + q + 1]] * m.spline_multfac[o + q + 1] * fac);
+			}
+			ds[sp * T + st] = v;
+			prev = v;
+		}
+	}
+	__syncthreads();
+
+	/* model.cc:1182-1250 create_areafactor + calculate_area_av */
+	{
+		const int period = m.period;
+		for (int i = tid; i < period * A; i += nth) {
+			int t = i / A, c = i - t * A;
+			double v = m.has_region ? exp(pd[m.region_effect_param[c]]) : 1.0;
+			if (m.has_area_eff) v *= pd[m.area_effect_param[c]];
+			for (int j = 0; j < m.ncovar; j++) v *= exp(pd[m.covar_param[j]] * m.covar_value[((size_t)j * A + c) * period + t]);
+			if (m.nlevel > 0) v *= pd[m.level_param[m.level_map[i]]];
+			af[i] = v;
+		}
+		__syncthreads();
+		double part = 0;
+		for (int c = tid; c < A; c += nth) {
+			double av = 0;
+			for (int t = 0; t < period; t++) av += af[t * A + c];
+			av /= period;
+			part += av * m.area_total_pop[c];
+		}
+		/* deterministic block reduction */
+		double *red = sm;
+		for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(FULLMASK, part, o);
+		if ((tid & 31) == 0) red[tid >> 5] = part;
+		__syncthreads();
+		if (tid == 0) { double s = 0; for (int w = 0; w < (nth >> 5); w++) s += red[w]; red[0] = s / m.popsize; }
+		__syncthreads();
+		double area_av = red[0];
+		__syncthreads();
+		for (int i = tid; i < period * A; i += nth) af[i] /= area_av;
+	}
+
+	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix
+	 * NGM = F V^-1 (model.cc:2485-2576) factorises: V is block diagonal in dp, so
+	 * NGM[q][i] = dist[q] sus[q] N_t[age q][age i] w[i],  w[i] = sum_s inf_s (V_i^-1)[s][0];
+	 * its dominant eigenvalue is found by the reference's power iteration
+	 * (matrix.cc:1139-1220), warm-started along the time axis within a warp's chunk. */
+	{
+		const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
+		double *wv = sm + 32;                               /* [Dq] shared by the CTA */
+		double *ngm = wv + Dq + (size_t)warp * (Dq * (Dq + 1) + 2 * Dq);
+		double *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
+		const int ninf = m.ninf;
+		for (int st = 0; st < S; st++) {
+			__syncthreads();
+			for (int dp = tid; dp < Dq; dp += nth) {
+				/* V for this dp (ninf x ninf), model.cc:2485-2522, then Gauss-Jordan as matrix.cc:703-765 */
+				double V[K0_MAXINF * K0_MAXINF], inv[K0_MAXINF * K0_MAXINF];
+				for (int i = 0; i < ninf * ninf; i++) { V[i] = 0; inv[i] = 0; }
+				for (int i = 0; i < ninf; i++) inv[i * ninf + i] = 1;
+				for (int tr = 0; tr < J; tr++) {
+					int from = m.inf_ref[m.trans_from[tr]], to = m.inf_ref[m.trans_to[tr]];
+					if (from >= 0) {
+						double rate = transrate[tr * D + st * Dq + dp];
+						V[from * ninf + from] += rate;
+						if (to >= 0) V[to * ninf + from] -= rate;
+					}
+				}
+				for (int ii = 0; ii < ninf; ii++) {
+					double r = V[ii * ninf + ii];
+					for (int i = ii; i < ninf; i++) V[ii * ninf + i] /= r;
+					for (int i = 0; i <= ii; i++) inv[ii * ninf + i] /= r;
+					for (int jj = ii + 1; jj < ninf; jj++) {
+						double rr = V[jj * ninf + ii];
+						if (rr != 0) {
+							for (int i = ii; i < ninf; i++) V[jj * ninf + i] -= rr * V[ii * ninf + i];
+							for (int i = 0; i <= ii; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
+						}
+					}
+				}
+				for (int ii = ninf - 1; ii > 0; ii--)
+					for (int jj = ii - 1; jj >= 0; jj--) {
+						double rr = V[jj * ninf + ii];
+						if (rr != 0) for (int i = 0; i < ninf; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
+					}
+				double w = 0;
+				for (int is = 0; is < ninf; is++) {
+					double inf = pd[m.comp_inf_param[m.inf_state[is]]];
+					if (inf != 0) w += inf * inv[is * ninf + 0];
+				}
+				wv[dp] = w;
+			}
+			__syncthreads();
+			for (int ir = 0; ir < m.nR; ir++) {
+				const int spl = m.R_spline_ref[ir];
+				const double *dist = m.R_dist + (size_t)ir * Dq;
+				const double rfac = pd[m.strain_Rfactor_param[st]];
+				double *out = betaR + ((size_t)st * m.nR + ir) * T;
+				/* time chunk of this warp */
+				int t0 = (int)(((long long)T * warp) / nwarp), t1 = (int)(((long long)T * (warp + 1)) / nwarp);
+				if (m.nmm == 0) { t0 = (warp == 0) ? 0 : T; t1 = (warp == 0) ? 1 : T; }
+				for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
+				double ratio = 0;
+				for (int t = t0; t < t1; t++) {
+					bool recompute = (t == t0);
+					if (!recompute) {
+						/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY */
+						int ch = 0;
+						for (int i = lane; i < G * G; i += 32) {
+							int a = i / G, bb = i - a * G;
+							double n0 = m.N0[i];
+							double x = ntime_elem(m, ds, t, a, bb, n0), y = ntime_elem(m, ds, t - 1, a, bb, n0);
+							if (y < x - 0.00000001 || y > x + 0.00000001) ch = 1;
+						}
+						recompute = __any_sync(FULLMASK, ch);
+					}
+					if (recompute) {
+						__syncwarp();
+						for (int i = lane; i < Dq * Dq; i += 32) {
+							int q = i / Dq, k = i - q * Dq;
+							int aq = m.dp_age[q], ak = m.dp_age[k];
+							double nt = ntime_elem(m, ds, t, aq, ak, m.N0[aq * G + ak]);
+							ngm[q * (Dq + 1) + k] = dist[q] * sus[Dq * st + q] * nt * wv[k];
+						}
+						__syncwarp();
+						double ev = 0;
+						for (unsigned loop = 0;; loop++) {
+							double sum = 0;
+							for (int q = lane; q < Dq; q += 32) {
+								double acc = 0;
+								for (int k = 0; k < Dq; k++) acc += ngm[q * (Dq + 1) + k] * vec[k];
+								vec2[q] = acc;
+								sum += acc;
+							}
+							for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
+							double ev_new = sum;
+							int bad = 0;
+							double lim = 100 * 0.000000000000001;
+							if (loop > 100) lim *= 10;
+							if (loop > 1000) lim *= 10;
+							for (int q = lane; q < Dq; q += 32) {
+								double v2 = vec2[q] / sum;
+								double dif = v2 - vec[q];
+								if (dif > lim || dif < -lim) bad = 1;
+								vec2[q] = v2;
+							}
+							bool conv = false;
+							if (loop % 10 == 0) {
+								bool evok = (ev_new - ev > -lim && ev_new - ev < lim);
+								conv = evok && !__any_sync(FULLMASK, bad);
+							}
+							__syncwarp();
+							if (conv) break;                    /* as the reference: keep the pre-update ev and vec */
+							for (int q = lane; q < Dq; q += 32) vec[q] = vec2[q];
+							__syncwarp();
+							ev = ev_new;
+							if (loop > 10000) break;
+						}
+						ratio = ev;
+					}
+					if (m.nmm == 0) {
+						/* age matrix constant in time: one eigenvalue serves every step */
+						for (int tt = lane; tt < T; tt += 32) out[tt] = rfac * ds[spl * T + tt] / ratio;
+					} else if (lane == 0) out[t] = rfac * ds[spl * T + t] / ratio;
+				}
+				__syncwarp();
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* K1-K3  trajectory kernel                                                  */
+/* ------------------------------------------------------------------------ */
+
+__global__ void k_pop_reset(DevModel m, DevBatch b)
+{
+	size_t n = (size_t)m.A * m.C * m.D, tot = n * b.P;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) b.pop_cur[i] = m.pop_init[i % n];
+}
+
+__global__ void k_zero(double *x, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = 0;
+}
+
+/* dinf[st][a] of one tile from its population (state.cc:223-264): infectivity-weighted
+ * number of individuals by strain and age, summed in the oracle's (co, dp) order */
+__device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco, const double *pop, double *out, int ostride, int lane)
+{
+	const int G = m.G, Dq = m.Dq, D = m.D, C = m.C;
+	for (int st = 0; st < m.S; st++) {
+		if (lane < G) {
+			double sum = 0;
+			for (int co = 0; co < C; co++) {
+				double inf = infco[co];
+				if (inf != 0) {
+					if (m.age_fast) {
+						for (int dp = lane; dp < Dq; dp += G) { double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
+					} else {
+						for (int dp = 0; dp < Dq; dp++) if (m.dp_age[dp] == lane) { double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
+					}
+				}
+			}
+			out[st * ostride + lane] = sum;
+		}
+	}
+}
+
+template <int MODE>
+__device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane,
+                                          double *pop, double *ns, double *foi, double *nmi,
+                                          const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
+{
+	const DevModel &m = a.m;
+	const DevBatch &b = a.b;
+	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq, C = m.C;
+	const double *rate = b.transrate + (size_t)p * J * D;
+	const double *ds = b.disc_spline + (size_t)p * m.nspline * T;
+	const double *sus = b.sus + (size_t)p * D;
+	const double *af = b.areafactor + (size_t)p * m.period * A;
+	const double *betaR = b.betaR + (size_t)p * S * m.nR * T;
+	const double *infco = b.infco + (size_t)p * C;
+	const int itr = m.itr, sfrom = m.trans_from[itr];
+
+	/* state.cc:395-404: with several strains the susceptible pool lives in strain 0 */
+	if (S > 1) {
+		for (int dp = lane; dp < Dq; dp += 32) {
+			double sum = 0;
+			for (int st = 1; st < S; st++) { sum += pop[sfrom * D + Dq * st + dp]; pop[sfrom * D + Dq * st + dp] = 0; }
+			pop[sfrom * D + dp] += sum;
+		}
+		__syncwarp();
+	}
+
+	/* state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
+	{
+		const double d = ds[m.geo_spline * T + t], omd = 1 - d, fac = m.M_factor[c];
+		const double diag = m.M_diag[c];
+		const int j0 = m.Min_off[c], j1 = m.Min_off[c + 1];
+		const double afv = af[(t / m.spu) * A + c];
+		const int rg = m.area_rgrp[c];
+		for (int st = 0; st < S; st++) {
+			double Iv = 0;
+			if (lane < G) {
+				double own = dinf_cur[(st * Ad + ci) * G + lane];
+				double Idiag = own * diag;
+				double Imap = 0;
+				for (int j = j0; j < j1; j++) {
+					double di = dinf_cur[(st * Ad + m.Min_src[j]) * G + lane];
+					if (di != 0) Imap += di * m.Min_val[j];
+				}
+				if (G == 1) {
+					double val = Idiag * (d + fac * omd) + Imap * d;
+					if (val < 0) val = 0;
+					nmi[0] = val;
+				} else Iv = (Idiag + Imap) * d + fac * Idiag * omd;
+			}
+			if (G > 1) {
+				double sum = 0;
+				for (int aa = 0; aa < G; aa++) {
+					double Ia = __shfl_sync(FULLMASK, Iv, aa);
+					if (lane < G) sum += ntime_elem(m, ds, t, lane, aa, m.N0T[aa * G + lane]) * Ia;
+				}
+				if (sum < 0) sum = 0;
+				if (lane < G) nmi[lane] = sum;
+			}
+			__syncwarp();
+			double be = betaR[(st * m.nR + rg) * T + t];
+			be *= afv;
+			const int ie = m.efoi_ref[st * A + c];
+			const double et = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize;
+			for (int dp = lane; dp < Dq; dp += 32) {
+				int ag = m.dp_age[dp];
+				foi[st * Dq + dp] = be * nmi[ag] + et * m.efoi_agedist[ie * G + ag];
+			}
+			__syncwarp();
+		}
+	}
+
+	/* the J*D cells of the tile: transition mean (state.cc:434-444) and event count */
+	const size_t tbase = (((size_t)p * T + t) * A + c) * (size_t)(J * D);
+	const bool keep_tn = (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
+	int simu = 0;
+	if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
+	for (int e = lane; e < J * D; e += 32) {
+		const int tr = e / D, dp = e - tr * D;
+		double mean;
+		if (tr == itr) {
+			double popu = pop[sfrom * D + (dp % Dq)];
+			mean = (popu <= 0) ? 0.0 : m.dt * popu * sus[dp] * foi[dp];
+		} else if (m.trans_inf[tr]) mean = 0;
+		else {
+			double popu = pop[m.trans_from[tr] * D + dp];
+			mean = (popu <= 0) ? 0.0 : m.dt * popu * rate[e];
+		}
+		double num;
+		if (MODE == MODE_REPLAY) {
+			num = m.stochastic ? (double)b.tn[tbase + e] : b.tm[tbase + e];
+		} else if (!m.stochastic) {
+			num = mean;                                      /* state.cc:627 */
+		} else if (MODE == MODE_SIM) {
+			if (mean == 0) num = 0;
+			else {
+				BeepStream rs;
+				beep_stream_init_cell(&rs, a.seed, b.stream_id[p], (((unsigned long long)t * A + c) * J + tr) * D + dp);
+				num = (double)beep_poisson(&rs, mean);          /* state.cc:624-626 */
+			}
+		} else {
+			/* mbp.cc:286-311 */
+			const int num_i = a.init_tn[tbase + e];
+			int num_p;
+			if (mean == 0) num_p = 0;
+			else {
+				BeepStream rs;
+				beep_stream_init_cell(&rs, a.seed, b.stream_id[p], (((unsigned long long)t * A + c) * J + tr) * D + dp);
+				if (simu) num_p = beep_poisson(&rs, mean);
+				else {
+					const double rate_i = a.init_tm[tbase + e];
+					if (mean > rate_i) num_p = num_i + beep_poisson(&rs, mean - rate_i);
+					else if (mean == rate_i) num_p = num_i;
+					else if (num_i == 0) num_p = 0;
+					else num_p = beep_binomial(&rs, mean / rate_i, num_i);
+				}
+			}
+			num = (double)num_p;
+		}
+		ns[e] = num;
+		if (keep_tm) b.tm[tbase + e] = mean;
+		if (keep_tn && MODE != MODE_REPLAY && m.stochastic) b.tn[tbase + e] = (int)num;
+	}
+	__syncwarp();
+
+	/* obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
+	{
+		const int k0 = m.cell_off[t * A + c], k1 = m.cell_off[t * A + c + 1];
+		for (int k = k0 + lane; k < k1; k += 32) {
+			const ObsEnt en = m.cell_ent[k];
+			const int ob = en.ob;
+			const double factor = m.obs_factor[ob];
+			const int fs = m.obs_fs[ob];
+			const unsigned long long dmask = m.obs_dmask[ob];
+			double val = 0;
+			unsigned long long tmask = m.obs_tmask[ob];
+			const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
+			while (tmask) {
+				int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
+				unsigned long long dm = dmask;
+				while (dm) {
+					int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+					double num = ns[tr * D + dp];
+					if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+				}
+			}
+			unsigned long long cmask = m.obs_cmask[ob];
+			while (cmask) {
+				int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
+				unsigned long long dm = dmask;
+				while (dm) {
+					int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+					val += factor * pop[co * D + dp];
+				}
+			}
+			/* the slot has a single owner (this tile) and steps are ordered: a plain RED */
+			atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
+		}
+	}
+
+	if (b.flags & BEEP_KEEP_POP) {
+		double *pt = b.poptraj + (((size_t)p * T + t) * A + c) * (size_t)(C * D);
+		for (int i = lane; i < C * D; i += 32) pt[i] = pop[i];
+	}
+
+	/* state.cc:460-485 update_pop (the last step's events are never applied) */
+	if (t < T - 1) {
+		__syncwarp();
+		for (int dp = lane; dp < D; dp += 32)
+			for (int tr = 0; tr < J; tr++) {
+				double num = ns[tr * D + dp];
+				if (num != 0) { pop[m.trans_from[tr] * D + dp] -= num; pop[m.trans_to[tr] * D + dp] += num; }
+			}
+		__syncwarp();
+		tile_dinf(m, infco, pop, dinf_nxt + ci * G, Ad * G, lane);
+	}
+	__syncwarp();
+}
+
+/* Shared memory (doubles):
+ *   SYNC_NONE / SYNC_GRID, per warp: pop[C*D] ns[J*D] foi[D] nmi[G] (+ dinf[2][S*G] for NONE)
+ *   SYNC_CTA, per CTA: pop[A][C*D] dinf[2][S*A*G]; per warp: ns[J*D] foi[D] nmi[G]          */
+template <int MODE, int SYNC>
+__global__ void __launch_bounds__(256) k_traj(const __grid_constant__ TrajArgs a)
+{
+	extern __shared__ double sm[];
+	const DevModel &m = a.m;
+	const DevBatch &b = a.b;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = a.nwarp;
+	const int A = m.A, C = m.C, D = m.D, J = m.J, G = m.G, S = m.S;
+	const int CD = C * D, JD = J * D;
+
+	if (SYNC == SYNC_NONE) {
+		const int per = CD + JD + D + G + 2 * S * G;
+		double *pop = sm + (size_t)warp * per, *ns = pop + CD, *foi = ns + JD, *nmi = foi + D, *dinf = nmi + G;
+		const long long tile = (long long)blockIdx.x * nwarp + warp;
+		if (tile >= (long long)b.P * A) return;
+		const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
+		double *gp = b.pop_cur + ((size_t)p * A + c) * CD;
+		for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+		__syncwarp();
+		tile_dinf(m, b.infco + (size_t)p * C, pop, dinf + (a.ti & 1) * S * G, G, lane);
+		__syncwarp();
+		for (int t = a.ti; t < a.tf; t++)
+			tile_step<MODE>(a, p, c, t, lane, pop, ns, foi, nmi, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+		for (int i = lane; i < CD; i += 32) gp[i] = pop[i];
+	} else if (SYNC == SYNC_CTA) {
+		const int p = blockIdx.x;
+		double *popA = sm, *dinf = popA + (size_t)A * CD;
+		const int perw = JD + D + G;
+		double *ns = dinf + 2 * S * A * G + (size_t)warp * perw, *foi = ns + JD, *nmi = foi + D;
+		double *gp = b.pop_cur + (size_t)p * A * CD;
+		for (int i = threadIdx.x; i < A * CD; i += blockDim.x) popA[i] = gp[i];
+		__syncthreads();
+		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * C, popA + (size_t)c * CD, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
+		__syncthreads();
+		for (int t = a.ti; t < a.tf; t++) {
+			for (int c = warp; c < A; c += nwarp)
+				tile_step<MODE>(a, p, c, t, lane, popA + (size_t)c * CD, ns, foi, nmi, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+			__syncthreads();
+		}
+		for (int i = threadIdx.x; i < A * CD; i += blockDim.x) gp[i] = popA[i];
+	} else {
+		cg::grid_group grid = cg::this_grid();
+		const int per = CD + JD + D + G;
+		double *pop = sm + (size_t)warp * per, *ns = pop + CD, *foi = ns + JD, *nmi = foi + D;
+		const long long ntile = (long long)b.P * A, nw = (long long)gridDim.x * nwarp, gw = (long long)blockIdx.x * nwarp + warp;
+		const size_t dsz = (size_t)b.P * S * A * G;
+		for (long long tile = gw; tile < ntile; tile += nw) {
+			const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
+			const double *gp = b.pop_cur + (size_t)tile * CD;
+			for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+			__syncwarp();
+			tile_dinf(m, b.infco + (size_t)p * C, pop, b.dinf + (a.ti & 1) * dsz + (size_t)p * S * A * G + c * G, A * G, lane);
+			__syncwarp();
+		}
+		grid.sync();
+		for (int t = a.ti; t < a.tf; t++) {
+			for (long long tile = gw; tile < ntile; tile += nw) {
+				const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
+				double *gp = b.pop_cur + (size_t)tile * CD;
+				for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+				__syncwarp();
+				tile_step<MODE>(a, p, c, t, lane, pop, ns, foi, nmi, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
+				                b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
+				for (int i = lane; i < CD; i += 32) gp[i] = pop[i];
+				__syncwarp();
+			}
+			grid.sync();
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* K4  observation model                                                     */
+/* ------------------------------------------------------------------------ */
+__device__ __forceinline__ double d_normal_probability(double x, double mean, double var)
+{
+	return -0.5 * log(2 * 3.14159265358979323846 * var) - (x - mean) * (x - mean) / (2 * var);   /* utils.cc:107-111 */
+}
+__device__ __forceinline__ double d_poisson_probability(int i, double lam)                       /* utils.cc:157-170 */
+{
+	if (lam == 0) return (i == 0) ? 0.0 : -BEEP_LARGE;
+	if (i < 0) return -BEEP_LARGE;
+	return i * log(lam) - lam - lgamma((double)(i + 1));
+}
+__device__ __forceinline__ double d_negbin_probability(unsigned val, double mm, double shape)    /* utils.cc:124-127 */
+{
+	return lgamma(shape + val) - lgamma((double)(val + 1)) - lgamma(shape) + shape * log(shape / (shape + mm)) + val * log(mm / (shape + mm));
+}
+
+/* obsmodel.cc:245-305 obs_prob */
+__device__ double d_obs_prob(const DevModel &m, double value, int ob)
+{
+	if (value < 0) value = 0;
+	const double val = m.obs_value[ob], sd = m.obs_sd[ob];
+	if (val == BEEP_UNKNOWN) return 0;
+	const int om = m.obs_model[ob];
+	if (val == BEEP_THRESH) {
+		const double thresh = m.table_threshold[m.obs_table[ob]];
+		if (om == BEEP_OBS_NORMAL || om == BEEP_OBS_NORMAL_PERCENT) {
+			if (value < thresh) return d_normal_probability(thresh, thresh, sd * sd);
+			return d_normal_probability(thresh, value, sd * sd);
+		}
+		if (om == BEEP_OBS_POISSON) {
+			double lam = value; if (lam < 1) lam = 1;
+			double sum = 0; for (double v = 0; v <= thresh; v++) sum += exp(d_poisson_probability((int)v, lam));
+			return log(sum);
+		}
+		double mm = value; if (mm < 1) mm = 1;
+		double sum = 0; for (double v = 0; v <= thresh; v++) sum += exp(d_negbin_probability((unsigned)v, mm, m.obs_shape[ob]));
+		return log(sum);
+	}
+	if (om == BEEP_OBS_NORMAL || om == BEEP_OBS_NORMAL_PERCENT) return d_normal_probability(val, value, sd * sd);
+	if (om == BEEP_OBS_POISSON) { double lam = value; if (lam < 1) lam = 1; return d_poisson_probability((int)(val + 0.5), lam); }
+	double mm = value; if (mm < 1) mm = 1;
+	return d_negbin_probability((unsigned)(int)(val + 0.5), mm, m.obs_shape[ob]);
+}
+
+#define RED_THREADS 256
+/* deterministic block sum (fixed tree), result valid in thread 0 */
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0;
+	if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+	return s;
+}
+
+/* one CTA per particle: obs_value, log-probability, L and the per-table split.
+ * section < 0: every observation (obsmodel.cc:22-35); else that section only (:39-58) */
+__global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch b, int section, double *L_out, double *EF_out)
+{
+	__shared__ double red[RED_THREADS / 32];
+	const int p = blockIdx.x;
+	const double *part = b.obs_partial + (size_t)p * m.nslot;
+	double *oval = b.obs_val + (size_t)p * m.nobs;
+	double acc = 0;
+	for (int ob = threadIdx.x; ob < m.nobs; ob += blockDim.x) {
+		if (section >= 0 && m.obs_section[ob] != section) continue;
+		double v = 0;
+		for (int k = m.obs_slot_off[ob]; k < m.obs_slot_off[ob + 1]; k++) v += part[k];
+		oval[ob] = v;
+		acc += d_obs_prob(m, v, ob);
+	}
+	double L = block_sum(acc, red);
+	if (threadIdx.x == 0) L_out[p] = L;
+	if (EF_out) {
+		for (int tb = 0; tb < m.ntable; tb++) {
+			double a2 = 0;
+			for (int ob = threadIdx.x; ob < m.nobs; ob += blockDim.x)
+				if (m.obs_table[ob] == tb && (section < 0 || m.obs_section[ob] == section)) a2 += -2 * d_obs_prob(m, oval[ob], ob);
+			double s = block_sum(a2, red);
+			if (threadIdx.x == 0) EF_out[(size_t)p * m.ntable + tb] = s;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* K5  latent-process likelihood, state.cc:812-826                           */
+/* ------------------------------------------------------------------------ */
+#define K5_CHUNKS 64
+__global__ void __launch_bounds__(RED_THREADS) k_latent_partial(DevModel m, DevBatch b, double *partial)
+{
+	__shared__ double red[RED_THREADS / 32];
+	const int p = blockIdx.y, ch = blockIdx.x;
+	const size_t n = (size_t)m.T * m.A * m.J * m.D;
+	const size_t lo = n * ch / K5_CHUNKS, hi = n * (ch + 1) / K5_CHUNKS;
+	const int *tn = b.tn + (size_t)p * n;
+	const double *tm = b.tm + (size_t)p * n;
+	double acc = 0;
+	for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		double lam = tm[i];
+		int k = m.stochastic ? tn[i] : (int)lam;
+		acc += d_poisson_probability(k, lam);
+	}
+	double s = block_sum(acc, red);
+	if (threadIdx.x == 0) partial[(size_t)p * K5_CHUNKS + ch] = s;
+}
+__global__ void k_latent_final(int P, const double *partial, double *Li)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < P) { double s = 0; for (int i = 0; i < K5_CHUNKS; i++) s += partial[(size_t)p * K5_CHUNKS + i]; Li[p] = s; }
+}
+
+/* ------------------------------------------------------------------------ */
+/* K6  particle movement                                                     */
+/* ------------------------------------------------------------------------ */
+/* dst[p] <- src[map[p]] for slabs of `n` elements; map[p] == 0xFFFFFFFF keeps.  Out-of-place
+ * (src != dst) so that chains of copies are well defined, as in mpi.cc:81-165. */
+template <typename Tp>
+__global__ void k_gather_slab(Tp *dst, const Tp *src, const unsigned *map, size_t n, int P)
+{
+	const int p = blockIdx.y;
+	unsigned s = map ? map[p] : (unsigned)p;
+	if (s == 0xFFFFFFFFu) s = (unsigned)p;
+	const Tp *sp = src + (size_t)s * n;
+	Tp *dp = dst + (size_t)p * n;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp[i] = sp[i];
+}
+/* dst[p] <- src[p] where flag[p] != 0 */
+template <typename Tp>
+__global__ void k_copy_flagged(Tp *dst, const Tp *src, const unsigned char *flag, size_t n, int P)
+{
+	const int p = blockIdx.y;
+	if (!flag[p]) return;
+	const Tp *sp = src + (size_t)p * n;
+	Tp *dp = dst + (size_t)p * n;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp[i] = sp[i];
+}
+
+/* sampler parity helpers (tests/test_rng_parity.py) */
+__global__ void k_poisson_many(unsigned long long seed, unsigned long long stream_id, const double *lam, int n, int *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { BeepStream rs; beep_stream_init(&rs, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), (uint32_t)i); out[i] = beep_poisson(&rs, lam[i]); }
+}
+__global__ void k_binomial_many(unsigned long long seed, unsigned long long stream_id, const double *pr, const int *nn, int n, int *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { BeepStream rs; beep_stream_init(&rs, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), (uint32_t)i); out[i] = beep_binomial(&rs, pr[i], nn[i]); }
+}
+
+#endif

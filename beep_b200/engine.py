@@ -1,0 +1,289 @@
+"""ctypes binding of the C-ABI engine (``include/beep_b200.h``).
+
+This is plumbing: every call goes straight to ``beep_b200/lib/libbeep_b200.so``
+(hand-written sm_100a kernels).  There is no CPU fallback -- if the library is
+missing or no CUDA device is present the constructors raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbeep_b200.so")
+
+KEEP_TRANSNUM, KEEP_TRANSMEAN, KEEP_POP = 1, 2, 4
+DERIVED_TRANSRATE, DERIVED_DISC_SPLINE, DERIVED_SUSCEPTIBILITY, DERIVED_AREAFACTOR, DERIVED_BETA, DERIVED_AGEFACTOR = range(6)
+TRAJ_TRANSNUM, TRAJ_TRANSMEAN, TRAJ_POP = range(3)
+PERMUTE_FULL, PERMUTE_SECTION_STATE = 0, 1
+INF_UPDATE, INF_DIF_UPDATE = 0, 1
+KEEP = 0xFFFFFFFF
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+_SIGNATURES = {
+    "beep_last_error": (ctypes.c_char_p, []),
+    "beep_version": (ctypes.c_int, []),
+    "beep_engine_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "beep_engine_destroy": (None, [_vp]),
+    "beep_batch_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint, ctypes.POINTER(_vp)]),
+    "beep_batch_destroy": (None, [_vp]),
+    "beep_batch_size": (ctypes.c_int, [_vp]),
+    "beep_batch_bytes": (ctypes.c_int64, [_vp]),
+    "beep_set_params": (ctypes.c_int, [_vp, _vp]),
+    "beep_set_params_dev": (ctypes.c_int, [_vp, _vp]),
+    "beep_simulate": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, _vp]),
+    "beep_mbp": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint64, _vp]),
+    "beep_replay": (ctypes.c_int, [_vp]),
+    "beep_obs_loglik": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "beep_obs_loglik_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "beep_obs_values": (ctypes.c_int, [_vp, _vp]),
+    "beep_num_sections": (ctypes.c_int, [_vp]),
+    "beep_section_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "beep_latent_loglik": (ctypes.c_int, [_vp, _vp]),
+    "beep_permute": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "beep_accept": (ctypes.c_int, [_vp, _vp, _vp]),
+    "beep_export_particle": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "beep_import_particle": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "beep_get_derived": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int64]),
+    "beep_get_trajectory": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int64]),
+    "beep_get_pop": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64]),
+    "beep_sync": (ctypes.c_int, [_vp]),
+    "beep_batch_stream": (_vp, [_vp]),
+    "beep_launch_count": (ctypes.c_int64, [_vp]),
+    "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
+    "beep_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _c_dp, _vp]),
+    "beep_test_poisson": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_int, _vp]),
+    "beep_test_binomial": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, ctypes.c_int, _vp]),
+}
+
+_LIB = None
+
+
+class BeepError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"beep_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load the engine library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C beep_b200/csrc).  The BEEP engine has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise BeepError(rc, lib().beep_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One model on one GPU (read-only tables uploaded once)."""
+
+    def __init__(self, model, device=0):
+        self.model = model
+        self.L = lib()
+        h = _vp()
+        _check(self.L.beep_engine_create(ctypes.addressof(model.c), device, ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.beep_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def batch(self, nparticle, flags=0):
+        return Batch(self, nparticle, flags)
+
+    @property
+    def nsection(self):
+        return self.L.beep_num_sections(self.h)
+
+    def section_range(self, s):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _check(self.L.beep_section_range(self.h, s, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launch_count(self):
+        return self.L.beep_launch_count(self.h)
+
+
+class Batch:
+    """P particles resident in HBM: the batched counterpart of the reference's
+    ``State`` (src/state.hh:11-133)."""
+
+    def __init__(self, engine, nparticle, flags=0):
+        self.engine = engine
+        self.model = engine.model
+        self.L = engine.L
+        self.P = int(nparticle)
+        h = _vp()
+        _check(self.L.beep_batch_create(engine.h, self.P, flags, ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.engine, "h", None):
+            self.L.beep_batch_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def nbytes(self):
+        return self.L.beep_batch_bytes(self.h)
+
+    # -- K0 ---------------------------------------------------------------
+    def set_params(self, theta):
+        th = _f64(theta)
+        if th.ndim == 1:
+            th = np.ascontiguousarray(np.broadcast_to(th, (self.P, th.size)))
+        assert th.shape == (self.P, self.model.nparam), th.shape
+        _check(self.L.beep_set_params(self.h, th.ctypes.data))
+
+    def set_params_dev(self, ptr):
+        _check(self.L.beep_set_params_dev(self.h, ptr))
+
+    # -- K1/K2 ------------------------------------------------------------
+    def simulate(self, ti=0, tf=None, seed=0, stream_ids=None):
+        tf = self.model.T if tf is None else tf
+        sp = None
+        if stream_ids is not None:
+            ids = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+            assert ids.size == self.P
+            sp = ids.ctypes.data
+        _check(self.L.beep_simulate(self.h, ti, tf, seed, sp))
+
+    # -- K3 ---------------------------------------------------------------
+    def mbp(self, init, mask=None, seed=0, stream_ids=None, inf_update=INF_DIF_UPDATE):
+        mp = sp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mask.ndim == 2:
+                mask = np.ascontiguousarray(np.broadcast_to(mask, (self.P,) + mask.shape))
+            assert mask.shape == (self.P, self.model.T, self.model.A)
+            mp = mask.ctypes.data
+        if stream_ids is not None:
+            ids = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+            sp = ids.ctypes.data
+        _check(self.L.beep_mbp(init.h, self.h, mp, inf_update, seed, sp))
+
+    def replay(self):
+        _check(self.L.beep_replay(self.h))
+
+    # -- K4 / K5 ----------------------------------------------------------
+    def obs_loglik(self, section=-1, with_tables=False):
+        Lh = np.zeros(self.P)
+        if with_tables:
+            tab = np.zeros((self.P, self.model.ntable))
+            _check(self.L.beep_obs_loglik(self.h, section, Lh.ctypes.data, tab.ctypes.data))
+            return Lh, tab
+        _check(self.L.beep_obs_loglik(self.h, section, Lh.ctypes.data, None))
+        return Lh
+
+    def obs_values(self):
+        out = np.zeros((self.P, self.model.nobs))
+        _check(self.L.beep_obs_values(self.h, out.ctypes.data))
+        return out
+
+    def latent_loglik(self):
+        out = np.zeros(self.P)
+        _check(self.L.beep_latent_loglik(self.h, out.ctypes.data))
+        return out
+
+    # -- K6 ---------------------------------------------------------------
+    def permute(self, src_of, what=PERMUTE_FULL):
+        m = np.ascontiguousarray(src_of, dtype=np.uint32)
+        assert m.size == self.P
+        _check(self.L.beep_permute(self.h, m.ctypes.data, what))
+
+    def accept_from(self, prop, accept):
+        a = np.ascontiguousarray(accept, dtype=np.uint8)
+        assert a.size == self.P
+        _check(self.L.beep_accept(self.h, prop.h, a.ctypes.data))
+
+    # -- particles ----------------------------------------------------------
+    def export_particle(self, slot):
+        m = self.model
+        th = np.zeros(m.nparam)
+        tn = np.zeros(m.traj_shape)
+        _check(self.L.beep_export_particle(self.h, slot, th.ctypes.data, tn.ctypes.data))
+        return th, tn
+
+    def import_particle(self, slot, theta, transnum):
+        th, tn = _f64(theta), _f64(transnum)
+        _check(self.L.beep_import_particle(self.h, slot, th.ctypes.data, tn.ctypes.data))
+
+    # -- read-back ----------------------------------------------------------
+    def derived(self, slot, which):
+        m = self.model
+        shape = {DERIVED_TRANSRATE: (m.J, m.D), DERIVED_DISC_SPLINE: (m.nspline, m.T), DERIVED_SUSCEPTIBILITY: (m.D,),
+                 DERIVED_AREAFACTOR: (m.period, m.A), DERIVED_BETA: (m.S, m.A, m.T), DERIVED_AGEFACTOR: (m.T, m.G)}[which]
+        out = np.zeros(shape)
+        _check(self.L.beep_get_derived(self.h, slot, which, out.ctypes.data, out.size))
+        return out
+
+    def trajectory(self, slot, which=TRAJ_TRANSNUM):
+        m = self.model
+        out = np.zeros(m.pop_shape if which == TRAJ_POP else m.traj_shape)
+        _check(self.L.beep_get_trajectory(self.h, slot, which, out.ctypes.data, out.size))
+        return out
+
+    def pop(self, slot):
+        m = self.model
+        out = np.zeros((m.A, m.C, m.D))
+        _check(self.L.beep_get_pop(self.h, slot, out.ctypes.data, out.size))
+        return out
+
+    def sync(self):
+        _check(self.L.beep_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.beep_batch_stream(self.h)
+
+    @property
+    def last_simulate_ms(self):
+        return self.L.beep_last_simulate_ms(self.h)
+
+
+def bootstrap(L_all, invT, seed, section):
+    """PMCMC::bootstrap (src/pmcmc.cc:211-268) on the gathered weights."""
+    Ls = _f64(L_all)
+    inc = ctypes.c_double()
+    back = np.zeros(Ls.size, dtype=np.uint32)
+    _check(lib().beep_bootstrap(Ls.ctypes.data, Ls.size, invT, seed, section, ctypes.byref(inc), back.ctypes.data))
+    return inc.value, back
+
+
+def test_poisson(seed, stream_id, lam):
+    lam = _f64(lam)
+    out = np.zeros(lam.size, dtype=np.int32)
+    _check(lib().beep_test_poisson(seed, stream_id, lam.ctypes.data, lam.size, out.ctypes.data))
+    return out
+
+
+def test_binomial(seed, stream_id, p, n):
+    p = _f64(p)
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    out = np.zeros(p.size, dtype=np.int32)
+    _check(lib().beep_test_binomial(seed, stream_id, p.ctypes.data, n.ctypes.data, p.size, out.ctypes.data))
+    return out

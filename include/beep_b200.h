@@ -196,6 +196,11 @@ double beep_last_simulate_ms(const BeepBatch *batch);
 int beep_bootstrap(const double *L_all_host, int ntot, double invT, uint64_t seed, int section,
                    double *loglik_inc, uint32_t *backpart_host);
 
+/* Test hooks: the device samplers of beep_rng.h on n independent streams
+ * (seed, stream_id, i), for the host/device bit-exactness tests.            */
+int beep_test_poisson(uint64_t seed, uint64_t stream_id, const double *lam_host, int n, int32_t *out_host);
+int beep_test_binomial(uint64_t seed, uint64_t stream_id, const double *p_host, const int32_t *n_host, int n, int32_t *out_host);
+
 #ifdef __cplusplus
 }
 #endif

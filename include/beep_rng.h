@@ -83,15 +83,25 @@ BEEP_HD void beep_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], ui
 	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* A stream is identified by (seed, id0, id1, id2).  The engine uses
- *   id0 = low 32 bits of the particle's stream id
- *   id1 = high 32 bits of the particle's stream id
- *   id2 = column index ((sett*A + c)*D + dp), or 0xFFFFFFFF for the
- *         sequential stream of the reference harness.                       */
+/* A stream is identified by a 64-bit seed (the Philox key) and the upper three
+ * counter words; ctr[0] counts the blocks consumed.  Two keyings are used:
+ *   sequential  (id0, id1, 0xFFFFFFFF): ONE stream consumed in the reference's
+ *               loop order -- reference harness and the oracle's SEQ mode;
+ *   per cell    beep_stream_init_cell(): one stream per particle stream id and
+ *               per (sett, area, transition, dp) cell -- the CUDA engine and
+ *               the oracle's KEYED mode.  cell < 2^48; a draw uses < 2^16 blocks. */
 BEEP_HD void beep_stream_init(BeepStream *s, uint64_t seed, uint32_t id0, uint32_t id1, uint32_t id2)
 {
 	s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
 	s->ctr[0] = 0; s->ctr[1] = id0; s->ctr[2] = id1; s->ctr[3] = id2;
+	s->have = 0;
+}
+
+BEEP_HD void beep_stream_init_cell(BeepStream *s, uint64_t seed, uint64_t stream_id, uint64_t cell)
+{
+	s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
+	s->ctr[0] = (uint32_t)(cell >> 32) << 16; s->ctr[1] = (uint32_t)cell;
+	s->ctr[2] = (uint32_t)stream_id; s->ctr[3] = (uint32_t)(stream_id >> 32);
 	s->have = 0;
 }
 
@@ -107,13 +117,19 @@ BEEP_HD uint32_t beep_next_u32(BeepStream *s)
 	return w;
 }
 
-/* uniform on (0,1): (x + 1/2) 2^-52 with x a 52-bit integer; exact, never 0/1 */
+/* uniform on (0,1): (x + 1/2) 2^-52 with x a 52-bit integer; exact, never 0/1.
+ * Always consumes an aligned pair of words, so a Philox block yields exactly
+ * two uniforms (static buffer indices: the stream stays in registers on the GPU) */
 BEEP_HD double beep_next_uniform(BeepStream *s)
 {
-	/* always consume an aligned pair so that a Philox block yields 2 uniforms */
-	if (s->have & 1) s->have--;
-	uint32_t a = beep_next_u32(s);
-	uint32_t b = beep_next_u32(s);
+	uint32_t a, b;
+	if (s->have < 2) {
+		beep_philox4x32_10(s->ctr, s->key, s->buf);
+		s->ctr[0]++;
+		s->have = 4;
+	}
+	if (s->have >= 4) { a = s->buf[0]; b = s->buf[1]; s->have = 2; }
+	else { a = s->buf[2]; b = s->buf[3]; s->have = 0; }
 	uint64_t x = (((uint64_t)a << 32) | (uint64_t)b) >> 12;
 	return BR_MUL(BR_ADD((double)x, 0.5), 2.220446049250313080847263336181640625e-16);
 }

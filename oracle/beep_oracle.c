@@ -15,8 +15,8 @@
  * the counter-based samplers of include/beep_rng.h, in one of two stream modes:
  *   SEQ    one sequential stream consumed in the reference's loop order
  *          (state.cc:614-631, mbp.cc:276-313) -- matches the reference harness;
- *   KEYED  one stream per (sett, area, dp) column, transitions in order --
- *          matches the CUDA engine.
+ *   KEYED  one stream per (sett, area, transition, dp) cell
+ *          (beep_stream_init_cell) -- matches the CUDA engine.
  * and the infectivity map is maintained either incrementally from transnum
  * (the reference, state.cc:164-219) or recomputed from the population each step
  * (the engine); both agree to rounding (state_check.cc:60-75 allows 1e-5).
@@ -526,7 +526,7 @@ static void pop_init(OracleState *s)
 	memcpy(s->pop, m->pop_init, (size_t)m->A * m->C * m->D * sizeof(double));
 }
 
-static uint32_t column_id(const BeepModelDesc *m, int sett, int c, int dp) { return (uint32_t)(((long)sett * m->A + c) * m->D + dp); }
+static uint64_t cell_id(const BeepModelDesc *m, int sett, int c, int tr, int dp) { return (uint64_t)((((long)sett * m->A + c) * m->J + tr) * m->D + dp); }
 
 /* ---------------------------------------------------------------------- */
 /* K1+K2  State::simulate(ti,tf), state.cc:596-638                          */
@@ -535,8 +535,7 @@ int oracle_simulate(OracleState *s, int ti, int tf, uint64_t seed, uint64_t stre
 {
 	const BeepModelDesc *m = s->m;
 	int J = m->J, D = m->D;
-	BeepStream seq;
-	BeepStream *col = (BeepStream *)malloc(D * sizeof(BeepStream));
+	BeepStream seq, cell;
 	/* the sequential stream restarts at every call, as the harness re-keys it */
 	beep_stream_init(&seq, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), 0xFFFFFFFFu);
 	if (ti == 0) pop_init(s);
@@ -545,18 +544,19 @@ int oracle_simulate(OracleState *s, int ti, int tf, uint64_t seed, uint64_t stre
 		else set_Imap_sett(s, sett);
 		for (int c = 0; c < m->A; c++) {
 			set_transmean(s, sett, c);
-			if (s->keyed) for (int dp = 0; dp < D; dp++) beep_stream_init(&col[dp], seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), column_id(m, sett, c, dp));
 			for (int tr = 0; tr < J; tr++)
 				for (int dp = 0; dp < D; dp++) {
 					double mean = TM(s, sett, c, tr, dp);
 					if (mean == 0) TN(s, sett, c, tr, dp) = 0;
-					else if (s->stochastic) { TN(s, sett, c, tr, dp) = beep_poisson(s->keyed ? &col[dp] : &seq, mean); s->ndraw++; }
+					else if (s->stochastic) {
+						if (s->keyed) beep_stream_init_cell(&cell, seed, stream_id, cell_id(m, sett, c, tr, dp));
+						TN(s, sett, c, tr, dp) = beep_poisson(s->keyed ? &cell : &seq, mean); s->ndraw++;
+					}
 					else TN(s, sett, c, tr, dp) = mean;
 				}
 		}
 		if (sett < m->T - 1) update_pop(s, sett);
 	}
-	free(col);
 	return 0;
 }
 
@@ -618,8 +618,7 @@ int oracle_mbp(const OracleState *init, OracleState *prop, const unsigned char *
 	int A = m->A, J = m->J, D = m->D, T = m->T;
 	long nI = (long)m->S * A * m->G;
 	double *dImap = dalloc(nI), *dIdiag = dalloc(nI), *dtn = dalloc((long)A * J * D);
-	BeepStream seq;
-	BeepStream *col = (BeepStream *)malloc(D * sizeof(BeepStream));
+	BeepStream seq, cell;
 	beep_stream_init(&seq, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), 0xFFFFFFFFu);
 	pop_init(s); /* mbp.cc:414-424 mbp_initialise */
 	for (int sett = 0; sett < T; sett++) {
@@ -633,10 +632,10 @@ int oracle_mbp(const OracleState *init, OracleState *prop, const unsigned char *
 		for (int c = 0; c < A; c++) {
 			set_transmean(s, sett, c);
 			int simu = simu_mask ? simu_mask[(long)sett * A + c] : 0;
-			if (s->keyed) for (int dp = 0; dp < D; dp++) beep_stream_init(&col[dp], seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), column_id(m, sett, c, dp));
 			for (int tr = 0; tr < J; tr++)
 				for (int dp = 0; dp < D; dp++) {
-					BeepStream *rs = s->keyed ? &col[dp] : &seq;
+					BeepStream *rs = &seq;
+					if (s->keyed) { rs = &cell; beep_stream_init_cell(rs, seed, stream_id, cell_id(m, sett, c, tr, dp)); }
 					int num_i = (int)TN(init, sett, c, tr, dp);
 					double rate_p = TM(s, sett, c, tr, dp);
 					int num_p;
@@ -658,7 +657,7 @@ int oracle_mbp(const OracleState *init, OracleState *prop, const unsigned char *
 			if (!s->imap_from_pop) update_I_from_transnum(s, dImap, dIdiag, dtn);
 		}
 	}
-	free(dImap); free(dIdiag); free(dtn); free(col);
+	free(dImap); free(dIdiag); free(dtn);
 	return 0;
 }
 
