@@ -13,7 +13,8 @@
  *   betaR                [P][S][nR][T]         State::beta per R-spline group (areas of
  *                                              one group share the series, model.cc:1343)
  *   infco                [P][C]                infectivity of each compartment
- *   pop_cur              [P][A][C][D]          population at the batch's current step
+ *   pop_cur              [P][A][CDp]           population [C][D] at the batch's current step,
+ *                                              tile stride padded to an even count
  *   dinf                 [2][P][S][A][G]       infectivity by (area, age), double buffered
  *                                              (only the grid-synchronised kernel uses it)
  *   tn (int32)           [P][T][A][J][D]       State::transnum, dp innermost
@@ -35,6 +36,8 @@ struct DevModel {
 	int T, period, spu, A, C, J, D, G, S, Dq, nparam, nspline, nobs, ntable;
 	int stochastic, siminf, itr, geo_spline, nR, nefoi, ninf, nmm, ncovar, nlevel, ndir;
 	int nslot, nsection, has_region, has_area_eff, age_fast, M_nnz;
+	int CDp;            /* C*D rounded up to even: tile stride of pop_cur (16-byte async copies) */
+	int obs_wide;       /* observations span many dp: reduce them warp-cooperatively */
 	double popsize, dt;
 
 	const int *dir_off, *dir_th; const double *dir_frac;
@@ -54,6 +57,7 @@ struct DevModel {
 	const int *obs_fs, *obs_table, *obs_model, *obs_section, *obs_slot_off;
 	const unsigned long long *obs_tmask, *obs_cmask, *obs_dmask;
 	const int *cell_off; const ObsEnt *cell_ent;
+	const unsigned *cell_tab;   /* [J*D] packed (pop offset | tr<<12 | dp<<18 | kind<<24) */
 	const double *table_threshold;
 	const int *section_ti, *section_tf;
 };
@@ -78,6 +82,7 @@ struct TrajArgs {
 	/* MBP: the coupled initial state (same slot of the `init` batch) */
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
 	int nwarp;          /* warps per CTA */
+	unsigned char tfrom[64], tto[64];   /* trans_from / trans_to in the constant bank */
 };
 
 #endif

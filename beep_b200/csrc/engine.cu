@@ -41,6 +41,7 @@ struct BeepEngine {
 	DevModel dm;
 	std::vector<void *> dev_allocs;
 	std::vector<int> section_ti, section_tf;
+	unsigned char h_from[64] = {0}, h_to[64] = {0};
 	long long launches = 0;
 	int sync_mode = SYNC_NONE, nwarp = 4;
 	size_t smem_traj = 0;
@@ -140,6 +141,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	for (int tr = 0; tr < J; tr++) NEED(d->trans_from[tr] >= 0 && d->trans_from[tr] < C && d->trans_to[tr] >= 0 && d->trans_to[tr] < C, "transition %d endpoints out of range", tr);
 	for (int i = 0; i < Dq; i++) NEED(d->dp_age[i] >= 0 && d->dp_age[i] < G, "dp_age out of range");
 
+	for (int tr = 0; tr < J; tr++) { eng->h_from[tr] = (unsigned char)d->trans_from[tr]; eng->h_to[tr] = (unsigned char)d->trans_to[tr]; }
 	UP(dir_off, d->dir_off, d->n_dir_off); UP(dir_th, d->dir_th, d->n_dir_th); UP(dir_frac, d->dir_frac, d->n_dir_frac);
 	UP(trans_from, d->trans_from, J); UP(trans_to, d->trans_to, J); UP(trans_inf, d->trans_inf, J); UP(trans_shape, d->trans_shape, J);
 	UP(trans_mean_param, d->trans_mean_param, J * D); UP(trans_prob_param, d->trans_prob_param, J * D);
@@ -193,6 +195,19 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	}
 	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
 	UP(pop_init, d->pop_init, (size_t)A * C * D);
+	m.CDp = (C * D + 1) & ~1;
+	{
+		/* packed per-cell table: population offset of the source compartment, transition, dp, kind
+		 * (0 = ordinary transition, 1 = the infection transition, 2 = always zero) */
+		std::vector<unsigned> tab((size_t)J * D);
+		const int sfrom = d->trans_from[m.itr];
+		for (int tr = 0; tr < J; tr++) for (int dp = 0; dp < D; dp++) {
+			unsigned kind = (tr == m.itr) ? 1u : (d->trans_inf[tr] ? 2u : 0u);
+			unsigned off = (kind == 1) ? (unsigned)(sfrom * D + dp % Dq) : (unsigned)(d->trans_from[tr] * D + dp);
+			tab[(size_t)tr * D + dp] = off | ((unsigned)tr << 12) | ((unsigned)dp << 18) | (kind << 24);
+		}
+		UPV(cell_tab, tab);
+	}
 
 	/* observations: masks, (observation, area) slots, the (sett, area) -> entries index
 	 * (the reference's obs_trans / obs_pop inverted index, obsmodel.cc:174-217) and the
@@ -218,6 +233,14 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 			}
 		}
 		m.nslot = slot_off[O];
+		{
+			/* wide observations (many dp per observation) are reduced warp-cooperatively */
+			double w = 0;
+			for (int ob = 0; ob < O; ob++) w += (double)__builtin_popcountll(dmask[ob]);
+			m.obs_wide = (O > 0 && w / O > 4.0) ? 1 : 0;
+			const char *fw = getenv("BEEP_FORCE_OBS_WIDE");
+			if (fw) m.obs_wide = atoi(fw) ? 1 : 0;
+		}
 		for (size_t i = 0; i < (size_t)T * A; i++) cell_cnt[i + 1] += cell_cnt[i];
 		std::vector<ObsEnt> ent(cell_cnt[(size_t)T * A]);
 		std::vector<int> fill(cell_cnt.begin(), cell_cnt.end() - 1);
@@ -267,31 +290,31 @@ static const void *traj_fn(int mode, int sync)
 	return traj_fn<SYNC_GRID>(mode);
 }
 
+static size_t even(size_t x) { return (x + 1) & ~(size_t)1; }
+
 static int choose_launch(BeepEngine *eng)
 {
 	const DevModel &m = eng->dm;
-	const size_t CD = (size_t)m.C * m.D, JD = (size_t)m.J * m.D;
+	const size_t CDp = (size_t)m.CDp, JD = even((size_t)m.J * m.D), De = even(m.D), Ge = even(m.G);
+	const size_t common = even((size_t)m.G * m.G) + even(((size_t)m.J * m.D + 1) / 2);
 	const char *force = getenv("BEEP_FORCE_SYNC");      /* tests: exercise every flavour on small models */
-	if (m.M_nnz == 0 && m.A >= 1) {
+	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * (JD + De + 2 * Ge)) * sizeof(double); };
+	if (m.M_nnz == 0) {
 		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
-		eng->smem_traj = eng->nwarp * (CD + JD + m.D + m.G + 2 * (size_t)m.S * m.G) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (CDp + JD + De + 2 * Ge + even(2 * (size_t)m.S * m.G))) * sizeof(double);
 	} else {
 		eng->nwarp = std::min(8, m.A);
-		size_t cta = ((size_t)m.A * CD + 2 * (size_t)m.S * m.A * m.G + eng->nwarp * (JD + m.D + m.G)) * sizeof(double);
-		if (cta <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta; }
+		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
 		else eng->sync_mode = SYNC_GRID;
 	}
 	if (force) {
 		int f = atoi(force);
 		if (f == SYNC_GRID) eng->sync_mode = SYNC_GRID;
-		else if (f == SYNC_CTA && m.M_nnz == 0) {
-			eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(8, m.A);
-			eng->smem_traj = ((size_t)m.A * CD + 2 * (size_t)m.S * m.A * m.G + eng->nwarp * (JD + m.D + m.G)) * sizeof(double);
-		}
+		else if (f == SYNC_CTA && m.M_nnz == 0) { eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(8, m.A); eng->smem_traj = cta_bytes(eng->nwarp); }
 	}
 	if (eng->sync_mode == SYNC_GRID) {
 		eng->nwarp = 8;
-		eng->smem_traj = eng->nwarp * (CD + JD + m.D + m.G) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (2 * CDp + JD + De + 2 * Ge)) * sizeof(double);
 	}
 	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
 	for (int mode = 0; mode < 3; mode++) {
@@ -361,7 +384,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.theta, (size_t)P * m.nparam); BA(b.pd, (size_t)P * m.nparam);
 	BA(b.transrate, (size_t)P * m.J * m.D); BA(b.disc_spline, (size_t)P * m.nspline * m.T); BA(b.sus, (size_t)P * m.D);
 	BA(b.areafactor, (size_t)P * m.period * m.A); BA(b.betaR, (size_t)P * m.S * m.nR * m.T); BA(b.infco, (size_t)P * m.C);
-	BA(b.pop_cur, (size_t)P * m.A * m.C * m.D);
+	BA(b.pop_cur, (size_t)P * m.A * m.CDp);
 	if (eng->sync_mode == SYNC_GRID) BA(b.dinf, 2 * (size_t)P * m.S * m.A * m.G);
 	if ((flags & BEEP_KEEP_TRANSNUM) && m.stochastic) BA(b.tn, (size_t)P * TAJD);
 	if ((flags & BEEP_KEEP_TRANSMEAN) || ((flags & BEEP_KEEP_TRANSNUM) && !m.stochastic)) { BA(b.tm, (size_t)P * TAJD); b.flags |= BEEP_KEEP_TRANSMEAN; }
@@ -453,9 +476,10 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
 	a.nwarp = eng->nwarp;
+	for (int tr = 0; tr < 64; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; }
 	const int P = bt->db.P;
 	if (ti == 0) {
-		size_t n = (size_t)P * m.A * m.C * m.D;
+		size_t n = (size_t)P * m.A * m.CDp;
 		int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)eng->nsm * 8);
 		k_pop_reset<<<nb, 256, 0, bt->stream>>>(m, bt->db);
 		size_t ns = (size_t)P * std::max(m.nslot, 1);
@@ -645,7 +669,7 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	CU(cudaMemcpyAsync(bt->d_map, src_of_host, P * sizeof(unsigned), cudaMemcpyHostToDevice, bt->stream));
 	int rc;
 	const DevBatch &b = bt->db;
-	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.C * m.D, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.CDp, bt->d_map))) return rc;
 	if (what == BEEP_PERMUTE_SECTION_STATE) return BEEP_OK;      /* mpi.cc:286-288: pop (Imap/Idiag are re-derived from it) */
 	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
 	if ((rc = gather_inplace(bt, b.theta, m.nparam, bt->d_map))) return rc;
@@ -695,7 +719,7 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if ((rc = copy_flagged(init, a.areafactor, b.areafactor, (size_t)m.period * m.A))) return rc;
 	if ((rc = copy_flagged(init, a.betaR, b.betaR, (size_t)m.S * m.nR * m.T))) return rc;
 	if ((rc = copy_flagged(init, a.infco, b.infco, m.C))) return rc;
-	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.C * m.D))) return rc;
+	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.CDp))) return rc;
 	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.tm, b.tm, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.poptraj, b.poptraj, (size_t)m.T * m.A * m.C * m.D))) return rc;
@@ -759,7 +783,9 @@ extern "C" int beep_get_pop(BeepBatch *bt, int slot, double *out, int64_t n)
 	size_t ACD = (size_t)m.A * m.C * m.D;
 	if (!out || (size_t)n != ACD) return fail(BEEP_ERR_INVALID, "pop has %zu elements", ACD);
 	CU(cudaSetDevice(bt->eng->device));
-	CU(cudaMemcpyAsync(out, bt->db.pop_cur + (size_t)slot * ACD, ACD * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	const size_t CD = (size_t)m.C * m.D;
+	CU(cudaMemcpy2DAsync(out, CD * sizeof(double), bt->db.pop_cur + (size_t)slot * m.A * m.CDp, (size_t)m.CDp * sizeof(double),
+	                     CD * sizeof(double), m.A, cudaMemcpyDeviceToHost, bt->stream));
 	CU(cudaStreamSynchronize(bt->stream));
 	return BEEP_OK;
 }

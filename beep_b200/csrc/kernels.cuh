@@ -289,14 +289,27 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 
 __global__ void k_pop_reset(DevModel m, DevBatch b)
 {
-	size_t n = (size_t)m.A * m.C * m.D, tot = n * b.P;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) b.pop_cur[i] = m.pop_init[i % n];
+	const size_t CD = (size_t)m.C * m.D, CDp = m.CDp, n = (size_t)m.A * CDp, tot = n * b.P;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+		size_t r = i % n, c = r / CDp, k = r - c * CDp;
+		b.pop_cur[i] = (k < CD) ? m.pop_init[c * CD + k] : 0.0;
+	}
 }
 
 __global__ void k_zero(double *x, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = 0;
 }
+
+/* 16-byte asynchronous global -> shared copies (LDGSTS), committed as one group per tile */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+	unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 /* dinf[st][a] of one tile from its population (state.cc:223-264): infectivity-weighted
  * number of individuals by strain and age, summed in the oracle's (co, dp) order */
@@ -321,24 +334,34 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
 	}
 }
 
+/* per-warp scratch, all in shared memory */
+struct TileSm {
+	double *pop;      /* [C*D] population of the tile                       */
+	double *ns;       /* [J*D] event counts of this step                    */
+	double *foi;      /* [D]   force of infection per dp (state.cc:428)     */
+	double *nmi;      /* [G]   NMI per age (state.cc:547-578), then scratch  */
+	double *Iv;       /* [G]   infectivity vector before the age matvec     */
+	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)   */
+	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)            */
+};
+
+/* one time step of one (particle, area) tile; returns (warp-uniform) whether any event happened */
 template <int MODE>
-__device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane,
-                                          double *pop, double *ns, double *foi, double *nmi,
+__device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane, const TileSm &sm,
                                           const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
 {
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
 	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq, C = m.C;
-	const double *rate = b.transrate + (size_t)p * J * D;
+	const int JD = J * D;
+	double *pop = sm.pop, *ns = sm.ns, *foi = sm.foi, *nmi = sm.nmi;
+	const double *rate = b.transrate + (size_t)p * JD;
 	const double *ds = b.disc_spline + (size_t)p * m.nspline * T;
 	const double *sus = b.sus + (size_t)p * D;
-	const double *af = b.areafactor + (size_t)p * m.period * A;
-	const double *betaR = b.betaR + (size_t)p * S * m.nR * T;
-	const double *infco = b.infco + (size_t)p * C;
-	const int itr = m.itr, sfrom = m.trans_from[itr];
 
 	/* state.cc:395-404: with several strains the susceptible pool lives in strain 0 */
 	if (S > 1) {
+		const int sfrom = m.trans_from[m.itr];
 		for (int dp = lane; dp < Dq; dp += 32) {
 			double sum = 0;
 			for (int st = 1; st < S; st++) { sum += pop[sfrom * D + Dq * st + dp]; pop[sfrom * D + Dq * st + dp] = 0; }
@@ -352,40 +375,52 @@ __device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const 
 		const double d = ds[m.geo_spline * T + t], omd = 1 - d, fac = m.M_factor[c];
 		const double diag = m.M_diag[c];
 		const int j0 = m.Min_off[c], j1 = m.Min_off[c + 1];
-		const double afv = af[(t / m.spu) * A + c];
+		const double afv = b.areafactor[((size_t)p * m.period + t / m.spu) * A + c];
 		const int rg = m.area_rgrp[c];
 		for (int st = 0; st < S; st++) {
 			double Iv = 0;
+			bool live = false;
 			if (lane < G) {
-				double own = dinf_cur[(st * Ad + ci) * G + lane];
-				double Idiag = own * diag;
+				const double own = dinf_cur[(st * Ad + ci) * G + lane];
+				const double Idiag = own * diag;
 				double Imap = 0;
 				for (int j = j0; j < j1; j++) {
-					double di = dinf_cur[(st * Ad + m.Min_src[j]) * G + lane];
+					const double di = dinf_cur[(st * Ad + m.Min_src[j]) * G + lane];
 					if (di != 0) Imap += di * m.Min_val[j];
 				}
 				if (G == 1) {
 					double val = Idiag * (d + fac * omd) + Imap * d;
 					if (val < 0) val = 0;
 					nmi[0] = val;
-				} else Iv = (Idiag + Imap) * d + fac * Idiag * omd;
+				} else {
+					Iv = (Idiag + Imap) * d + fac * Idiag * omd;
+					live = (Iv != 0);
+				}
 			}
 			if (G > 1) {
-				double sum = 0;
-				for (int aa = 0; aa < G; aa++) {
-					double Ia = __shfl_sync(FULLMASK, Iv, aa);
-					if (lane < G) sum += ntime_elem(m, ds, t, lane, aa, m.N0T[aa * G + lane]) * Ia;
-				}
-				if (sum < 0) sum = 0;
-				if (lane < G) nmi[lane] = sum;
+				/* a neighbourhood without infectious individuals has I = 0, hence NMI = 0 exactly */
+				if (__any_sync(FULLMASK, live)) {
+					if (lane < G) sm.Iv[lane] = Iv;
+					__syncwarp();
+					if (lane < G) {
+						double sum = 0;
+						if (m.nmm == 0) {
+							for (int aa = 0; aa < G; aa++) sum += sm.N0T[aa * G + lane] * sm.Iv[aa];
+						} else {
+							for (int aa = 0; aa < G; aa++) sum += ntime_elem(m, ds, t, lane, aa, sm.N0T[aa * G + lane]) * sm.Iv[aa];
+						}
+						if (sum < 0) sum = 0;
+						nmi[lane] = sum;
+					}
+				} else if (lane < G) nmi[lane] = 0;
 			}
 			__syncwarp();
-			double be = betaR[(st * m.nR + rg) * T + t];
+			double be = b.betaR[(((size_t)p * S + st) * m.nR + rg) * T + t];
 			be *= afv;
 			const int ie = m.efoi_ref[st * A + c];
 			const double et = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize;
 			for (int dp = lane; dp < Dq; dp += 32) {
-				int ag = m.dp_age[dp];
+				const int ag = m.dp_age[dp];
 				foi[st * Dq + dp] = be * nmi[ag] + et * m.efoi_agedist[ie * G + ag];
 			}
 			__syncwarp();
@@ -393,41 +428,42 @@ __device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const 
 	}
 
 	/* the J*D cells of the tile: transition mean (state.cc:434-444) and event count */
-	const size_t tbase = (((size_t)p * T + t) * A + c) * (size_t)(J * D);
+	const size_t tbase = (((size_t)p * T + t) * A + c) * (size_t)JD;
+	const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
 	const bool keep_tn = (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
+	const bool stoch = m.stochastic != 0;
+	const unsigned long long sid = b.stream_id[p];
 	int simu = 0;
 	if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
-	for (int e = lane; e < J * D; e += 32) {
-		const int tr = e / D, dp = e - tr * D;
-		double mean;
-		if (tr == itr) {
-			double popu = pop[sfrom * D + (dp % Dq)];
-			mean = (popu <= 0) ? 0.0 : m.dt * popu * sus[dp] * foi[dp];
-		} else if (m.trans_inf[tr]) mean = 0;
-		else {
-			double popu = pop[m.trans_from[tr] * D + dp];
-			mean = (popu <= 0) ? 0.0 : m.dt * popu * rate[e];
+	bool ev = false;
+	for (int e = lane; e < JD; e += 32) {
+		const unsigned w = sm.ctab[e];
+		const double popu = pop[w & 0xfffu];
+		const unsigned kind = w >> 24;
+		double mean = 0.0;
+		if (popu > 0) {
+			if (kind == 0) mean = m.dt * popu * rate[e];
+			else if (kind == 1) { const int dp = (w >> 18) & 63; mean = m.dt * popu * sus[dp] * foi[dp]; }
 		}
 		double num;
 		if (MODE == MODE_REPLAY) {
-			num = m.stochastic ? (double)b.tn[tbase + e] : b.tm[tbase + e];
-		} else if (!m.stochastic) {
+			num = stoch ? (double)b.tn[tbase + e] : b.tm[tbase + e];
+		} else if (!stoch) {
 			num = mean;                                      /* state.cc:627 */
 		} else if (MODE == MODE_SIM) {
-			if (mean == 0) num = 0;
-			else {
+			num = 0;
+			if (mean != 0) {
 				BeepStream rs;
-				beep_stream_init_cell(&rs, a.seed, b.stream_id[p], (((unsigned long long)t * A + c) * J + tr) * D + dp);
+				beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
 				num = (double)beep_poisson(&rs, mean);          /* state.cc:624-626 */
 			}
 		} else {
 			/* mbp.cc:286-311 */
 			const int num_i = a.init_tn[tbase + e];
-			int num_p;
-			if (mean == 0) num_p = 0;
-			else {
+			int num_p = 0;
+			if (mean != 0) {
 				BeepStream rs;
-				beep_stream_init_cell(&rs, a.seed, b.stream_id[p], (((unsigned long long)t * A + c) * J + tr) * D + dp);
+				beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
 				if (simu) num_p = beep_poisson(&rs, mean);
 				else {
 					const double rate_i = a.init_tm[tbase + e];
@@ -440,43 +476,75 @@ __device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const 
 			num = (double)num_p;
 		}
 		ns[e] = num;
+		ev |= (num != 0);
 		if (keep_tm) b.tm[tbase + e] = mean;
-		if (keep_tn && MODE != MODE_REPLAY && m.stochastic) b.tn[tbase + e] = (int)num;
+		if (keep_tn && MODE != MODE_REPLAY && stoch) b.tn[tbase + e] = (int)num;
 	}
-	__syncwarp();
+	ev = __any_sync(FULLMASK, ev);      /* also orders the ns[] writes before the reads below */
 
 	/* obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
 	{
 		const int k0 = m.cell_off[t * A + c], k1 = m.cell_off[t * A + c + 1];
-		for (int k = k0 + lane; k < k1; k += 32) {
-			const ObsEnt en = m.cell_ent[k];
-			const int ob = en.ob;
-			const double factor = m.obs_factor[ob];
-			const int fs = m.obs_fs[ob];
-			const unsigned long long dmask = m.obs_dmask[ob];
-			double val = 0;
-			unsigned long long tmask = m.obs_tmask[ob];
-			const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
-			while (tmask) {
-				int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
-				unsigned long long dm = dmask;
-				while (dm) {
-					int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
-					double num = ns[tr * D + dp];
-					if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+		if (m.obs_wide) {
+			/* observations summing many dp: lanes over dp, one warp reduction per entry */
+			for (int k = k0; k < k1; k++) {
+				const ObsEnt en = m.cell_ent[k];
+				const int ob = en.ob;
+				const unsigned long long tmask0 = m.obs_tmask[ob], cmask0 = m.obs_cmask[ob], dmask = m.obs_dmask[ob];
+				if (!ev && cmask0 == 0) continue;              /* no events: a transition observation gains nothing */
+				const double factor = m.obs_factor[ob];
+				const int fs = m.obs_fs[ob];
+				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
+				double val = 0;
+				for (int dp = lane; dp < D; dp += 32) {
+					if (!((dmask >> dp) & 1ull)) continue;
+					unsigned long long tmask = tmask0;
+					while (tmask) {
+						const int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
+						const double num = ns[tr * D + dp];
+						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+					}
+					unsigned long long cmask = cmask0;
+					while (cmask) {
+						const int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
+						val += factor * pop[co * D + dp];
+					}
 				}
+				for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULLMASK, val, o);
+				if (lane == 0 && val != 0) atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
 			}
-			unsigned long long cmask = m.obs_cmask[ob];
-			while (cmask) {
-				int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
-				unsigned long long dm = dmask;
-				while (dm) {
-					int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
-					val += factor * pop[co * D + dp];
+		} else {
+			/* narrow observations (one or a few dp each): one lane per entry */
+			for (int k = k0 + lane; k < k1; k += 32) {
+				const ObsEnt en = m.cell_ent[k];
+				const int ob = en.ob;
+				const double factor = m.obs_factor[ob];
+				const int fs = m.obs_fs[ob];
+				const unsigned long long dmask = m.obs_dmask[ob];
+				double val = 0;
+				unsigned long long tmask = m.obs_tmask[ob];
+				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
+				while (tmask) {
+					const int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
+					unsigned long long dm = dmask;
+					while (dm) {
+						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+						const double num = ns[tr * D + dp];
+						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+					}
 				}
+				unsigned long long cmask = m.obs_cmask[ob];
+				while (cmask) {
+					const int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
+					unsigned long long dm = dmask;
+					while (dm) {
+						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+						val += factor * pop[co * D + dp];
+					}
+				}
+				/* the slot has a single owner (this tile) and steps are ordered: a plain RED */
+				if (val != 0) atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
 			}
-			/* the slot has a single owner (this tile) and steps are ordered: a plain RED */
-			atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
 		}
 	}
 
@@ -485,87 +553,138 @@ __device__ __forceinline__ void tile_step(const TrajArgs &a, const int p, const 
 		for (int i = lane; i < C * D; i += 32) pt[i] = pop[i];
 	}
 
-	/* state.cc:460-485 update_pop (the last step's events are never applied) */
+	/* state.cc:460-485 update_pop (the last step's events are never applied), then the
+	 * infectivity of the new population; without events both are unchanged */
 	if (t < T - 1) {
-		__syncwarp();
-		for (int dp = lane; dp < D; dp += 32)
-			for (int tr = 0; tr < J; tr++) {
-				double num = ns[tr * D + dp];
-				if (num != 0) { pop[m.trans_from[tr] * D + dp] -= num; pop[m.trans_to[tr] * D + dp] += num; }
-			}
-		__syncwarp();
-		tile_dinf(m, infco, pop, dinf_nxt + ci * G, Ad * G, lane);
-	}
+		if (ev) {
+			__syncwarp();
+			for (int dp = lane; dp < D; dp += 32)
+				for (int tr = 0; tr < J; tr++) {
+					const double num = ns[tr * D + dp];
+					if (num != 0) { pop[a.tfrom[tr] * D + dp] -= num; pop[a.tto[tr] * D + dp] += num; }
+				}
+			__syncwarp();
+			tile_dinf(m, b.infco + (size_t)p * C, pop, dinf_nxt + ci * G, Ad * G, lane);
+		} else if (lane < G) {
+			for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
+		}
+	} else ev = false;
 	__syncwarp();
+	return ev;
 }
 
-/* Shared memory (doubles):
- *   SYNC_NONE / SYNC_GRID, per warp: pop[C*D] ns[J*D] foi[D] nmi[G] (+ dinf[2][S*G] for NONE)
- *   SYNC_CTA, per CTA: pop[A][C*D] dinf[2][S*A*G]; per warp: ns[J*D] foi[D] nmi[G]          */
-template <int MODE, int SYNC>
-__global__ void __launch_bounds__(256) k_traj(const __grid_constant__ TrajArgs a)
+/* CTA-shared tables at the front of dynamic shared memory (doubles): N0T[G*G, even] ctab[J*D/2, even] */
+__device__ __forceinline__ int sm_common_doubles(const DevModel &m)
 {
-	extern __shared__ double sm[];
+	int n0 = (m.G * m.G + 1) & ~1, ct = (((m.J * m.D + 1) >> 1) + 1) & ~1;
+	return n0 + ct;
+}
+__device__ __forceinline__ double *sm_common_init(const DevModel &m, double *smem, TileSm &ts)
+{
+	const int n0 = (m.G * m.G + 1) & ~1;
+	double *N0T = smem;
+	unsigned *ctab = (unsigned *)(smem + n0);
+	for (int i = threadIdx.x; i < m.G * m.G; i += blockDim.x) N0T[i] = m.N0T[i];
+	for (int i = threadIdx.x; i < m.J * m.D; i += blockDim.x) ctab[i] = m.cell_tab[i];
+	ts.N0T = N0T; ts.ctab = ctab;
+	return smem + sm_common_doubles(m);
+}
+#define EVEN(x) (((x) + 1) & ~1)
+
+/* Shared memory after the common tables (doubles, every block even so that 16-byte copies stay aligned):
+ *   SYNC_NONE, per warp: pop[CDp] ns[JD] foi[D] nmi[G] Iv[G] dinf[2][S*G]
+ *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: ns[JD] foi[D] nmi[G] Iv[G]
+ *   SYNC_GRID, per warp: pop[2][CDp] ns[JD] foi[D] nmi[G] Iv[G]   (pop double-buffered by cp.async) */
+template <int MODE, int SYNC>
+__global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArgs a)
+{
+	extern __shared__ __align__(16) double smraw[];
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = a.nwarp;
 	const int A = m.A, C = m.C, D = m.D, J = m.J, G = m.G, S = m.S;
-	const int CD = C * D, JD = J * D;
+	const int CD = C * D, CDp = m.CDp, JD = EVEN(J * D), De = EVEN(D), Ge = EVEN(G);
+	TileSm ts;
+	double *sm = sm_common_init(m, smraw, ts);
+	__syncthreads();
 
 	if (SYNC == SYNC_NONE) {
-		const int per = CD + JD + D + G + 2 * S * G;
-		double *pop = sm + (size_t)warp * per, *ns = pop + CD, *foi = ns + JD, *nmi = foi + D, *dinf = nmi + G;
+		const int per = CDp + JD + De + 2 * Ge + EVEN(2 * S * G);
+		ts.pop = sm + (size_t)warp * per; ts.ns = ts.pop + CDp; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+		double *dinf = ts.Iv + Ge;
 		const long long tile = (long long)blockIdx.x * nwarp + warp;
 		if (tile >= (long long)b.P * A) return;
 		const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
-		double *gp = b.pop_cur + ((size_t)p * A + c) * CD;
-		for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+		double *gp = b.pop_cur + (size_t)tile * CDp;
+		for (int i = lane; i < CD; i += 32) ts.pop[i] = gp[i];
 		__syncwarp();
-		tile_dinf(m, b.infco + (size_t)p * C, pop, dinf + (a.ti & 1) * S * G, G, lane);
+		tile_dinf(m, b.infco + (size_t)p * C, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
 		__syncwarp();
 		for (int t = a.ti; t < a.tf; t++)
-			tile_step<MODE>(a, p, c, t, lane, pop, ns, foi, nmi, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
-		for (int i = lane; i < CD; i += 32) gp[i] = pop[i];
+			tile_step<MODE>(a, p, c, t, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+		for (int i = lane; i < CD; i += 32) gp[i] = ts.pop[i];
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
-		double *popA = sm, *dinf = popA + (size_t)A * CD;
-		const int perw = JD + D + G;
-		double *ns = dinf + 2 * S * A * G + (size_t)warp * perw, *foi = ns + JD, *nmi = foi + D;
-		double *gp = b.pop_cur + (size_t)p * A * CD;
-		for (int i = threadIdx.x; i < A * CD; i += blockDim.x) popA[i] = gp[i];
+		double *popA = sm, *dinf = popA + (size_t)A * CDp;
+		const int perw = JD + De + 2 * Ge;
+		ts.ns = dinf + EVEN(2 * S * A * G) + (size_t)warp * perw; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+		double *gp = b.pop_cur + (size_t)p * A * CDp;
+		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) popA[i] = gp[i];
 		__syncthreads();
-		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * C, popA + (size_t)c * CD, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
+		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * C, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
 		__syncthreads();
 		for (int t = a.ti; t < a.tf; t++) {
-			for (int c = warp; c < A; c += nwarp)
-				tile_step<MODE>(a, p, c, t, lane, popA + (size_t)c * CD, ns, foi, nmi, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+			for (int c = warp; c < A; c += nwarp) {
+				ts.pop = popA + (size_t)c * CDp;
+				tile_step<MODE>(a, p, c, t, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+			}
 			__syncthreads();
 		}
-		for (int i = threadIdx.x; i < A * CD; i += blockDim.x) gp[i] = popA[i];
+		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) gp[i] = popA[i];
 	} else {
 		cg::grid_group grid = cg::this_grid();
-		const int per = CD + JD + D + G;
-		double *pop = sm + (size_t)warp * per, *ns = pop + CD, *foi = ns + JD, *nmi = foi + D;
+		const int per = 2 * CDp + JD + De + 2 * Ge;
+		double *popbuf = sm + (size_t)warp * per;
+		ts.ns = popbuf + 2 * CDp; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
 		const long long ntile = (long long)b.P * A, nw = (long long)gridDim.x * nwarp, gw = (long long)blockIdx.x * nwarp + warp;
 		const size_t dsz = (size_t)b.P * S * A * G;
+		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
 		for (long long tile = gw; tile < ntile; tile += nw) {
 			const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
-			const double *gp = b.pop_cur + (size_t)tile * CD;
-			for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+			const double *gp = b.pop_cur + (size_t)tile * CDp;
+			for (int i = lane; i < CD; i += 32) popbuf[i] = gp[i];
 			__syncwarp();
-			tile_dinf(m, b.infco + (size_t)p * C, pop, b.dinf + (a.ti & 1) * dsz + (size_t)p * S * A * G + c * G, A * G, lane);
+			tile_dinf(m, b.infco + (size_t)p * C, popbuf, b.dinf + (a.ti & 1) * dsz + (size_t)p * S * A * G + c * G, A * G, lane);
 			__syncwarp();
 		}
 		grid.sync();
 		for (int t = a.ti; t < a.tf; t++) {
-			for (long long tile = gw; tile < ntile; tile += nw) {
+			/* software pipeline over this warp's tiles: tile k+1 streams into the other buffer while tile k computes */
+			if (gw < ntile) {
+				const double *gp = b.pop_cur + (size_t)gw * CDp;
+				for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gp + 2 * i);
+				cp_async_commit();
+			}
+			int kb = 0;
+			for (long long tile = gw; tile < ntile; tile += nw, kb ^= 1) {
 				const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
-				double *gp = b.pop_cur + (size_t)tile * CD;
-				for (int i = lane; i < CD; i += 32) pop[i] = gp[i];
+				double *gp = b.pop_cur + (size_t)tile * CDp;
+				if (tile + nw < ntile) {
+					const double *gn = b.pop_cur + (size_t)(tile + nw) * CDp;
+					double *dst = popbuf + (kb ^ 1) * CDp;
+					for (int i = lane; i < nchunk; i += 32) cp_async16(dst + 2 * i, gn + 2 * i);
+					cp_async_commit();
+					cp_async_wait<1>();
+				} else cp_async_wait<0>();
 				__syncwarp();
-				tile_step<MODE>(a, p, c, t, lane, pop, ns, foi, nmi, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
-				                b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
-				for (int i = lane; i < CD; i += 32) gp[i] = pop[i];
+				ts.pop = popbuf + kb * CDp;
+				const bool ev = tile_step<MODE>(a, p, c, t, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
+				                                b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
+				if (ev || S > 1) {
+					const double2 *s2 = (const double2 *)ts.pop;
+					double2 *g2 = (double2 *)gp;
+					for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
+				}
 				__syncwarp();
 			}
 			grid.sync();

@@ -256,6 +256,10 @@ BEEP_HD int beep_poisson(BeepStream *s, double lam)
 	if (!(lam > 0.0)) return 0;
 	if (lam < BEEP_POISSON_INV_MAX) {
 		double u = beep_next_uniform(s);
+		/* exp(-lam) >= 1 - lam, and beep_exp is good to ~1 ulp: a uniform below
+		 * (1 - lam) - 4.5e-16 yields k = 0 whatever beep_exp rounds to, so the
+		 * shortcut never changes a draw (it only skips the exp) */
+		if (u <= BR_SUB(BR_SUB(1.0, lam), 4.5e-16)) return 0;
 		double p = beep_exp(BR_SUB(0.0, lam));
 		double cdf = p;
 		int k = 0;
@@ -307,16 +311,20 @@ BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
 	int k;
 	if (BR_MUL(dn, q) < 10.0) {
 		/* BINV */
-		double sr = BR_DIV(q, omq);
-		double a = BR_MUL(BR_ADD(dn, 1.0), sr);
-		double r = beep_exp(BR_MUL(dn, beep_log(omq)));
 		double u = beep_next_uniform(s);
 		k = 0;
-		while (u > r && k < n) {
-			u = BR_SUB(u, r);
-			k++;
-			r = BR_MUL(r, BR_SUB(BR_DIV(a, (double)k), sr));
-			if (!(r > 0.0)) break;
+		/* (1-q)^n >= 1 - n q; the computed r = exp(n log(1-q)) is within ~n q ulps of it
+		 * (n q < 10): below (1 - n q) - 1e-14 the answer is 0 whatever r rounds to */
+		if (!(u <= BR_SUB(BR_SUB(1.0, BR_MUL(dn, q)), 1e-14))) {
+			double sr = BR_DIV(q, omq);
+			double a = BR_MUL(BR_ADD(dn, 1.0), sr);
+			double r = beep_exp(BR_MUL(dn, beep_log(omq)));
+			while (u > r && k < n) {
+				u = BR_SUB(u, r);
+				k++;
+				r = BR_MUL(r, BR_SUB(BR_DIV(a, (double)k), sr));
+				if (!(r > 0.0)) break;
+			}
 		}
 	} else {
 		/* BTRS */
