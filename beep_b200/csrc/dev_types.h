@@ -69,6 +69,7 @@ struct DevBatch {
 	int *tn; double *tm; double *poptraj;
 	double *obs_partial, *obs_val, *L, *EFtab, *Li;
 	unsigned long long *stream_id;
+	unsigned long long *infmask;   /* [P] transitions whose source or target compartment is infectious */
 };
 
 enum { MODE_SIM = 0, MODE_MBP = 1, MODE_REPLAY = 2 };

@@ -298,10 +298,11 @@ static int choose_launch(BeepEngine *eng)
 	const size_t CDp = (size_t)m.CDp, JD = even((size_t)m.J * m.D), De = even(m.D), Ge = even(m.G);
 	const size_t common = even((size_t)m.G * m.G) + even(((size_t)m.J * m.D + 1) / 2);
 	const char *force = getenv("BEEP_FORCE_SYNC");      /* tests: exercise every flavour on small models */
-	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * (JD + De + 2 * Ge)) * sizeof(double); };
+	const size_t work = 2 * JD + even((JD + 3) / 4) + De + 2 * Ge;     /* WORK_DOUBLES of kernels.cuh */
+	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * work) * sizeof(double); };
 	if (m.M_nnz == 0) {
 		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
-		eng->smem_traj = (common + eng->nwarp * (CDp + JD + De + 2 * Ge + even(2 * (size_t)m.S * m.G))) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (CDp + work + even(2 * (size_t)m.S * m.G))) * sizeof(double);
 	} else {
 		eng->nwarp = std::min(8, m.A);
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
@@ -314,7 +315,7 @@ static int choose_launch(BeepEngine *eng)
 	}
 	if (eng->sync_mode == SYNC_GRID) {
 		eng->nwarp = 8;
-		eng->smem_traj = (common + eng->nwarp * (2 * CDp + JD + De + 2 * Ge)) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (2 * CDp + work)) * sizeof(double);
 	}
 	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
 	for (int mode = 0; mode < 3; mode++) {
@@ -391,7 +392,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	if (flags & BEEP_KEEP_POP) BA(b.poptraj, (size_t)P * m.T * m.A * m.C * m.D);
 	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
 	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
-	BA(b.stream_id, P);
+	BA(b.stream_id, P); BA(b.infmask, P);
 	BA(bt->d_scratch, (size_t)P * K5_CHUNKS);
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
@@ -680,6 +681,7 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	if ((rc = gather_inplace(bt, b.areafactor, (size_t)m.period * m.A, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.betaR, (size_t)m.S * m.nR * m.T, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.infco, m.C, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.infmask, 1, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.poptraj, (size_t)m.T * m.A * m.C * m.D, bt->d_map))) return rc;
@@ -719,6 +721,7 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if ((rc = copy_flagged(init, a.areafactor, b.areafactor, (size_t)m.period * m.A))) return rc;
 	if ((rc = copy_flagged(init, a.betaR, b.betaR, (size_t)m.S * m.nR * m.T))) return rc;
 	if ((rc = copy_flagged(init, a.infco, b.infco, m.C))) return rc;
+	if ((rc = copy_flagged(init, a.infmask, b.infmask, 1))) return rc;
 	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.CDp))) return rc;
 	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.tm, b.tm, TAJD))) return rc;

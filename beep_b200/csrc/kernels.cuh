@@ -101,6 +101,12 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		sus[dp] = val;
 	}
 	for (int co = tid; co < m.C; co += nth) infco[co] = pd[m.comp_inf_param[co]];
+	if (tid == 0) {
+		/* transitions that can change the infectivity of a tile (either end infectious) */
+		unsigned long long mk = 0;
+		for (int tr = 0; tr < J; tr++) if (pd[m.comp_inf_param[m.trans_from[tr]]] != 0 || pd[m.comp_inf_param[m.trans_to[tr]]] != 0) mk |= 1ull << tr;
+		b.infmask[p] = mk;
+	}
 	/* model.cc:1020-1043 create_disc_spline: one thread walks one spline */
 	for (int sp = tid; sp < m.nspline; sp += nth) {
 		double factor = pd[m.spline_factor_param[sp]];
@@ -336,19 +342,28 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
 
 /* per-warp scratch, all in shared memory */
 struct TileSm {
-	double *pop;      /* [C*D] population of the tile                       */
-	double *ns;       /* [J*D] event counts of this step                    */
-	double *foi;      /* [D]   force of infection per dp (state.cc:428)     */
-	double *nmi;      /* [G]   NMI per age (state.cc:547-578), then scratch  */
-	double *Iv;       /* [G]   infectivity vector before the age matvec     */
-	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)   */
-	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)            */
+	double *pop;      /* [C*D] population of the tile                                  */
+	double *ns;       /* [J*D] event counts of this step; ALL ZERO between tile steps   */
+	double *foi;      /* [D]   force of infection per dp (state.cc:428)                */
+	double *nmi;      /* [G]   NMI per age (state.cc:547-578)                           */
+	double *Iv;       /* [G]   infectivity vector before the age matvec                */
+	double *am;       /* [J*D] means of the active cells, compacted                    */
+	unsigned short *ae; /* [J*D] cell index of the active cells, compacted             */
+	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)              */
+	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)                       */
 };
 
-/* one time step of one (particle, area) tile; returns (warp-uniform) whether any event happened */
+/* One time step of one (particle, area) tile.  Returns the (warp-uniform) mask of
+ * transitions that had events.
+ *   1. force of infection per dp;
+ *   2. SCAN the J*D cells: transition means; cells with a non-zero mean are compacted
+ *      into a dense list (most cells of an epidemic are empty);
+ *   3. DRAW on the dense list, 32 active cells per pass, one Philox stream per cell;
+ *   4. observations, population update and infectivity, visiting only the
+ *      transitions that had events.                                                    */
 template <int MODE>
-__device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane, const TileSm &sm,
-                                          const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
+__device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane, const TileSm &sm,
+                                                         const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
 {
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
@@ -370,7 +385,7 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 		__syncwarp();
 	}
 
-	/* state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
+	/* 1. state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
 	{
 		const double d = ds[m.geo_spline * T + t], omd = 1 - d, fac = m.M_factor[c];
 		const double diag = m.M_diag[c];
@@ -427,62 +442,81 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 		}
 	}
 
-	/* the J*D cells of the tile: transition mean (state.cc:434-444) and event count */
+	/* 2. scan: transition means (state.cc:434-444); compact the cells that can have events */
 	const size_t tbase = (((size_t)p * T + t) * A + c) * (size_t)JD;
-	const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
 	const bool keep_tn = (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
 	const bool stoch = m.stochastic != 0;
-	const unsigned long long sid = b.stream_id[p];
-	int simu = 0;
-	if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
-	bool ev = false;
-	for (int e = lane; e < JD; e += 32) {
-		const unsigned w = sm.ctab[e];
-		const double popu = pop[w & 0xfffu];
-		const unsigned kind = w >> 24;
+	const unsigned lt = (1u << lane) - 1u;
+	int nact = 0;
+	unsigned long long trbits = 0;
+	for (int e0 = 0; e0 < JD; e0 += 32) {
+		const int e = e0 + lane;
 		double mean = 0.0;
-		if (popu > 0) {
-			if (kind == 0) mean = m.dt * popu * rate[e];
-			else if (kind == 1) { const int dp = (w >> 18) & 63; mean = m.dt * popu * sus[dp] * foi[dp]; }
-		}
-		double num;
-		if (MODE == MODE_REPLAY) {
-			num = stoch ? (double)b.tn[tbase + e] : b.tm[tbase + e];
-		} else if (!stoch) {
-			num = mean;                                      /* state.cc:627 */
-		} else if (MODE == MODE_SIM) {
-			num = 0;
-			if (mean != 0) {
-				BeepStream rs;
-				beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
-				num = (double)beep_poisson(&rs, mean);          /* state.cc:624-626 */
+		bool act = false;
+		if (e < JD) {
+			const unsigned w = sm.ctab[e];
+			const double popu = pop[w & 0xfffu];
+			if (popu > 0) {
+				const unsigned kind = w >> 24;
+				if (kind == 0) mean = m.dt * popu * rate[e];
+				else if (kind == 1) { const int dp = (w >> 18) & 63; mean = m.dt * popu * sus[dp] * foi[dp]; }
 			}
-		} else {
-			/* mbp.cc:286-311 */
-			const int num_i = a.init_tn[tbase + e];
-			int num_p = 0;
-			if (mean != 0) {
-				BeepStream rs;
-				beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
-				if (simu) num_p = beep_poisson(&rs, mean);
+			if (keep_tm && MODE != MODE_REPLAY) b.tm[tbase + e] = mean;
+			if (MODE == MODE_REPLAY) {
+				/* the events are given (state.cc:294-322); only the means are recomputed */
+				const double num = stoch ? (double)b.tn[tbase + e] : b.tm[tbase + e];
+				if (keep_tm) b.tm[tbase + e] = mean;
+				if (num != 0) { ns[e] = num; trbits |= 1ull << ((w >> 12) & 63); }
+			} else if (!stoch) {
+				if (mean != 0) { ns[e] = mean; trbits |= 1ull << ((w >> 12) & 63); }   /* state.cc:627 */
+			} else {
+				act = (mean != 0);
+				if (keep_tn && !act) b.tn[tbase + e] = 0;
+			}
+		}
+		if (MODE != MODE_REPLAY && stoch) {
+			const unsigned bal = __ballot_sync(FULLMASK, act);
+			if (act) { const int pos = nact + __popc(bal & lt); sm.ae[pos] = (unsigned short)e; sm.am[pos] = mean; }
+			nact += __popc(bal);
+		}
+	}
+
+	/* 3. draws on the dense list */
+	if (MODE != MODE_REPLAY && stoch) {
+		__syncwarp();
+		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
+		const unsigned long long sid = b.stream_id[p];
+		int simu = 0;
+		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
+		for (int i = lane; i < nact; i += 32) {
+			const int e = sm.ae[i];
+			const double mean = sm.am[i];
+			BeepStream rs;
+			beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
+			int num;
+			if (MODE == MODE_SIM) num = beep_poisson(&rs, mean);             /* state.cc:624-626 */
+			else {
+				/* mbp.cc:286-311 */
+				const int num_i = a.init_tn[tbase + e];
+				if (simu) num = beep_poisson(&rs, mean);
 				else {
 					const double rate_i = a.init_tm[tbase + e];
-					if (mean > rate_i) num_p = num_i + beep_poisson(&rs, mean - rate_i);
-					else if (mean == rate_i) num_p = num_i;
-					else if (num_i == 0) num_p = 0;
-					else num_p = beep_binomial(&rs, mean / rate_i, num_i);
+					if (mean > rate_i) num = num_i + beep_poisson(&rs, mean - rate_i);
+					else if (mean == rate_i) num = num_i;
+					else if (num_i == 0) num = 0;
+					else num = beep_binomial(&rs, mean / rate_i, num_i);
 				}
 			}
-			num = (double)num_p;
+			if (num != 0) { ns[e] = (double)num; trbits |= 1ull << ((sm.ctab[e] >> 12) & 63); }
+			if (keep_tn) b.tn[tbase + e] = num;
 		}
-		ns[e] = num;
-		ev |= (num != 0);
-		if (keep_tm) b.tm[tbase + e] = mean;
-		if (keep_tn && MODE != MODE_REPLAY && stoch) b.tn[tbase + e] = (int)num;
 	}
-	ev = __any_sync(FULLMASK, ev);      /* also orders the ns[] writes before the reads below */
+	/* transitions with events, warp-wide (also orders the ns[] writes before the reads below) */
+	unsigned trlo = __reduce_or_sync(FULLMASK, (unsigned)trbits), trhi = 0;
+	if (J > 32) trhi = __reduce_or_sync(FULLMASK, (unsigned)(trbits >> 32));
+	const unsigned long long trmask = ((unsigned long long)trhi << 32) | trlo;
 
-	/* obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
+	/* 4a. obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
 	{
 		const int k0 = m.cell_off[t * A + c], k1 = m.cell_off[t * A + c + 1];
 		if (m.obs_wide) {
@@ -490,8 +524,9 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 			for (int k = k0; k < k1; k++) {
 				const ObsEnt en = m.cell_ent[k];
 				const int ob = en.ob;
-				const unsigned long long tmask0 = m.obs_tmask[ob], cmask0 = m.obs_cmask[ob], dmask = m.obs_dmask[ob];
-				if (!ev && cmask0 == 0) continue;              /* no events: a transition observation gains nothing */
+				const unsigned long long tmask0 = m.obs_tmask[ob] & trmask, cmask0 = m.obs_cmask[ob];
+				if (tmask0 == 0 && cmask0 == 0) continue;      /* no events in the observed transitions */
+				const unsigned long long dmask = m.obs_dmask[ob];
 				const double factor = m.obs_factor[ob];
 				const int fs = m.obs_fs[ob];
 				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
@@ -518,11 +553,12 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 			for (int k = k0 + lane; k < k1; k += 32) {
 				const ObsEnt en = m.cell_ent[k];
 				const int ob = en.ob;
+				unsigned long long tmask = m.obs_tmask[ob] & trmask, cmask = m.obs_cmask[ob];
+				if (tmask == 0 && cmask == 0) continue;
 				const double factor = m.obs_factor[ob];
 				const int fs = m.obs_fs[ob];
 				const unsigned long long dmask = m.obs_dmask[ob];
 				double val = 0;
-				unsigned long long tmask = m.obs_tmask[ob];
 				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
 				while (tmask) {
 					const int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
@@ -533,7 +569,6 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
 					}
 				}
-				unsigned long long cmask = m.obs_cmask[ob];
 				while (cmask) {
 					const int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
 					unsigned long long dm = dmask;
@@ -552,25 +587,33 @@ __device__ __forceinline__ bool tile_step(const TrajArgs &a, const int p, const 
 		double *pt = b.poptraj + (((size_t)p * T + t) * A + c) * (size_t)(C * D);
 		for (int i = lane; i < C * D; i += 32) pt[i] = pop[i];
 	}
-
-	/* state.cc:460-485 update_pop (the last step's events are never applied), then the
-	 * infectivity of the new population; without events both are unchanged */
-	if (t < T - 1) {
-		if (ev) {
-			__syncwarp();
-			for (int dp = lane; dp < D; dp += 32)
-				for (int tr = 0; tr < J; tr++) {
-					const double num = ns[tr * D + dp];
-					if (num != 0) { pop[a.tfrom[tr] * D + dp] -= num; pop[a.tto[tr] * D + dp] += num; }
-				}
-			__syncwarp();
-			tile_dinf(m, b.infco + (size_t)p * C, pop, dinf_nxt + ci * G, Ad * G, lane);
-		} else if (lane < G) {
-			for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
-		}
-	} else ev = false;
 	__syncwarp();
-	return ev;
+
+	/* 4b. state.cc:460-485 update_pop in transition order (the last step's events are never
+	 * applied), consuming -- and clearing -- the event counts; then the infectivity of the
+	 * new population.  Without events both are unchanged. */
+	{
+		const bool apply = (t < T - 1);
+		unsigned long long tm_ = trmask;
+		while (tm_) {
+			const int tr = __ffsll((long long)tm_) - 1; tm_ &= tm_ - 1;
+			const int fo = a.tfrom[tr] * D, to = a.tto[tr] * D;
+			for (int dp = lane; dp < D; dp += 32) {
+				const double num = ns[tr * D + dp];
+				if (num != 0) {
+					if (apply) { pop[fo + dp] -= num; pop[to + dp] += num; }
+					ns[tr * D + dp] = 0;
+				}
+			}
+		}
+		__syncwarp();
+		if (apply) {
+			if (trmask & b.infmask[p]) tile_dinf(m, b.infco + (size_t)p * C, pop, dinf_nxt + ci * G, Ad * G, lane);
+			else if (lane < G) for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
+		}
+	}
+	__syncwarp();
+	return (t < T - 1) ? trmask : 0ull;
 }
 
 /* CTA-shared tables at the front of dynamic shared memory (doubles): N0T[G*G, even] ctab[J*D/2, even] */
@@ -592,11 +635,23 @@ __device__ __forceinline__ double *sm_common_init(const DevModel &m, double *sme
 #define EVEN(x) (((x) + 1) & ~1)
 
 /* Shared memory after the common tables (doubles, every block even so that 16-byte copies stay aligned):
- *   SYNC_NONE, per warp: pop[CDp] ns[JD] foi[D] nmi[G] Iv[G] dinf[2][S*G]
- *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: ns[JD] foi[D] nmi[G] Iv[G]
- *   SYNC_GRID, per warp: pop[2][CDp] ns[JD] foi[D] nmi[G] Iv[G]   (pop double-buffered by cp.async) */
+ *   W = ns[JD] am[JD] ae[JD/4] foi[D] nmi[G] Iv[G]      (per-warp work area)
+ *   SYNC_NONE, per warp: pop[CDp] W dinf[2][S*G]
+ *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: W
+ *   SYNC_GRID, per warp: pop[2][CDp] W                  (pop double-buffered by cp.async) */
+#define WORK_DOUBLES(JD, De, Ge) (2 * (JD) + EVEN(((JD) + 3) / 4) + (De) + 2 * (Ge))
+__device__ __forceinline__ void work_init(TileSm &ts, double *w, int JD, int De, int Ge, int lane)
+{
+	ts.ns = w; ts.am = ts.ns + JD; ts.ae = (unsigned short *)(ts.am + JD);
+	ts.foi = ts.am + JD + EVEN((JD + 3) / 4); ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+	for (int i = lane; i < JD; i += 32) ts.ns[i] = 0;
+	__syncwarp();
+}
 template <int MODE, int SYNC>
-__global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArgs a)
+#ifndef BEEP_TRAJ_MINB
+#define BEEP_TRAJ_MINB 3
+#endif
+__global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
 {
 	extern __shared__ __align__(16) double smraw[];
 	const DevModel &m = a.m;
@@ -609,8 +664,9 @@ __global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArg
 	__syncthreads();
 
 	if (SYNC == SYNC_NONE) {
-		const int per = CDp + JD + De + 2 * Ge + EVEN(2 * S * G);
-		ts.pop = sm + (size_t)warp * per; ts.ns = ts.pop + CDp; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+		const int per = CDp + WORK_DOUBLES(JD, De, Ge) + EVEN(2 * S * G);
+		ts.pop = sm + (size_t)warp * per;
+		work_init(ts, ts.pop + CDp, JD, De, Ge, lane);
 		double *dinf = ts.Iv + Ge;
 		const long long tile = (long long)blockIdx.x * nwarp + warp;
 		if (tile >= (long long)b.P * A) return;
@@ -626,8 +682,8 @@ __global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArg
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
 		double *popA = sm, *dinf = popA + (size_t)A * CDp;
-		const int perw = JD + De + 2 * Ge;
-		ts.ns = dinf + EVEN(2 * S * A * G) + (size_t)warp * perw; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+		const int perw = WORK_DOUBLES(JD, De, Ge);
+		work_init(ts, dinf + EVEN(2 * S * A * G) + (size_t)warp * perw, JD, De, Ge, lane);
 		double *gp = b.pop_cur + (size_t)p * A * CDp;
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) popA[i] = gp[i];
 		__syncthreads();
@@ -643,9 +699,9 @@ __global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArg
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) gp[i] = popA[i];
 	} else {
 		cg::grid_group grid = cg::this_grid();
-		const int per = 2 * CDp + JD + De + 2 * Ge;
+		const int per = 2 * CDp + WORK_DOUBLES(JD, De, Ge);
 		double *popbuf = sm + (size_t)warp * per;
-		ts.ns = popbuf + 2 * CDp; ts.foi = ts.ns + JD; ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
+		work_init(ts, popbuf + 2 * CDp, JD, De, Ge, lane);
 		const long long ntile = (long long)b.P * A, nw = (long long)gridDim.x * nwarp, gw = (long long)blockIdx.x * nwarp + warp;
 		const size_t dsz = (size_t)b.P * S * A * G;
 		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
@@ -678,9 +734,9 @@ __global__ void __launch_bounds__(256, 2) k_traj(const __grid_constant__ TrajArg
 				} else cp_async_wait<0>();
 				__syncwarp();
 				ts.pop = popbuf + kb * CDp;
-				const bool ev = tile_step<MODE>(a, p, c, t, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
-				                                b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
-				if (ev || S > 1) {
+				const unsigned long long ev = tile_step<MODE>(a, p, c, t, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
+				                                              b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
+				if (ev != 0 || S > 1) {
 					const double2 *s2 = (const double2 *)ts.pop;
 					double2 *g2 = (double2 *)gp;
 					for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];

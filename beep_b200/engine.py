@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbeep_b200.so")
+LIB_PATH = os.environ.get("BEEP_B200_LIB") or os.path.join(_HERE, "lib", "libbeep_b200.so")   # override: kernel experiments only
 
 KEEP_TRANSNUM, KEEP_TRANSMEAN, KEEP_POP = 1, 2, 4
 DERIVED_TRANSRATE, DERIVED_DISC_SPLINE, DERIVED_SUSCEPTIBILITY, DERIVED_AREAFACTOR, DERIVED_BETA, DERIVED_AGEFACTOR = range(6)
