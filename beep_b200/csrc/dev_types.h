@@ -55,7 +55,7 @@ struct DevModel {
 	const double *pop_init;
 	const double *obs_value, *obs_sd, *obs_factor, *obs_shape;
 	const int *obs_fs, *obs_table, *obs_model, *obs_section, *obs_slot_off;
-	const unsigned long long *obs_tmask, *obs_cmask, *obs_dmask;
+	const unsigned *obs_tmask, *obs_cmask; const unsigned long long *obs_dmask;
 	const int *cell_off; const ObsEnt *cell_ent;
 	const unsigned *cell_tab;   /* [J*D] packed (pop offset | tr<<12 | dp<<18 | kind<<24) */
 	const double *table_threshold;
@@ -83,7 +83,7 @@ struct TrajArgs {
 	/* MBP: the coupled initial state (same slot of the `init` batch) */
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
 	int nwarp;          /* warps per CTA */
-	unsigned char tfrom[64], tto[64];   /* trans_from / trans_to in the constant bank */
+	unsigned char tfrom[32], tto[32], tkind[32];   /* per transition: source, target, kind (0 ordinary, 1 infection, 2 never) */
 };
 
 #endif

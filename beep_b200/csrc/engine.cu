@@ -41,7 +41,7 @@ struct BeepEngine {
 	DevModel dm;
 	std::vector<void *> dev_allocs;
 	std::vector<int> section_ti, section_tf;
-	unsigned char h_from[64] = {0}, h_to[64] = {0};
+	unsigned char h_from[32] = {0}, h_to[32] = {0}, h_kind[32] = {0};
 	long long launches = 0;
 	int sync_mode = SYNC_NONE, nwarp = 4;
 	size_t smem_traj = 0;
@@ -122,7 +122,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	NEED(D == S * Dq, "D (%d) != S*Dq (%d*%d)", D, S, Dq);
 	NEED(m.itr >= 0 && m.itr < J, "infection_trans out of range");
 	NEED(m.geo_spline >= 0 && m.geo_spline < m.nspline, "geo_spline_ref out of range");
-	if (G > 32 || D > 64 || J > 64 || C > 64 || m.ninf > K0_MAXINF) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "engine limits: G<=32 D<=64 J<=64 C<=64 ninf<=%d (got G=%d D=%d J=%d C=%d ninf=%d)", K0_MAXINF, G, D, J, C, m.ninf); }
+	if (G > 32 || D > 64 || J > 31 || C > 32 || m.ninf > K0_MAXINF) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "engine limits: G<=32 D<=64 J<=31 C<=32 ninf<=%d (got G=%d D=%d J=%d C=%d ninf=%d)", K0_MAXINF, G, D, J, C, m.ninf); }
 	NEED(d->n_trans_from == J && d->n_trans_to == J && d->n_trans_inf == J && d->n_trans_shape == J, "transition arrays must have J entries");
 	NEED(d->n_trans_mean_param == (int64_t)J * D && d->n_trans_prob_param == (int64_t)J * D, "trans_*_param must be [J][D]");
 	NEED(d->n_comp_inf_param == C, "comp_inf_param must be [C]");
@@ -141,7 +141,10 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	for (int tr = 0; tr < J; tr++) NEED(d->trans_from[tr] >= 0 && d->trans_from[tr] < C && d->trans_to[tr] >= 0 && d->trans_to[tr] < C, "transition %d endpoints out of range", tr);
 	for (int i = 0; i < Dq; i++) NEED(d->dp_age[i] >= 0 && d->dp_age[i] < G, "dp_age out of range");
 
-	for (int tr = 0; tr < J; tr++) { eng->h_from[tr] = (unsigned char)d->trans_from[tr]; eng->h_to[tr] = (unsigned char)d->trans_to[tr]; }
+	for (int tr = 0; tr < J; tr++) {
+		eng->h_from[tr] = (unsigned char)d->trans_from[tr]; eng->h_to[tr] = (unsigned char)d->trans_to[tr];
+		eng->h_kind[tr] = (tr == m.itr) ? 1 : (d->trans_inf[tr] ? 2 : 0);
+	}
 	UP(dir_off, d->dir_off, d->n_dir_off); UP(dir_th, d->dir_th, d->n_dir_th); UP(dir_frac, d->dir_frac, d->n_dir_frac);
 	UP(trans_from, d->trans_from, J); UP(trans_to, d->trans_to, J); UP(trans_inf, d->trans_inf, J); UP(trans_shape, d->trans_shape, J);
 	UP(trans_mean_param, d->trans_mean_param, J * D); UP(trans_prob_param, d->trans_prob_param, J * D);
@@ -214,14 +217,14 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	 * PMCMC sections (obsmodel.cc:326-348) */
 	{
 		const int O = m.nobs;
-		std::vector<unsigned long long> tmask(O, 0), cmask(O, 0), dmask(O, 0);
+		std::vector<unsigned> tmask(O, 0), cmask(O, 0); std::vector<unsigned long long> dmask(O, 0);
 		std::vector<int> slot_off(O + 1, 0), section(O, -1);
 		std::vector<int> cell_cnt((size_t)T * A + 1, 0);
 		for (int ob = 0; ob < O; ob++) {
 			int tb = d->obs_table[ob];
 			NEED(tb >= 0 && tb < m.ntable, "obs_table out of range");
-			for (int k = d->table_trans_off[tb]; k < d->table_trans_off[tb + 1]; k++) { NEED(d->table_trans[k] >= 0 && d->table_trans[k] < J, "table_trans out of range"); tmask[ob] |= 1ull << d->table_trans[k]; }
-			for (int k = d->table_comp_off[tb]; k < d->table_comp_off[tb + 1]; k++) { NEED(d->table_comp[k] >= 0 && d->table_comp[k] < C, "table_comp out of range"); cmask[ob] |= 1ull << d->table_comp[k]; }
+			for (int k = d->table_trans_off[tb]; k < d->table_trans_off[tb + 1]; k++) { NEED(d->table_trans[k] >= 0 && d->table_trans[k] < J, "table_trans out of range"); tmask[ob] |= 1u << d->table_trans[k]; }
+			for (int k = d->table_comp_off[tb]; k < d->table_comp_off[tb + 1]; k++) { NEED(d->table_comp[k] >= 0 && d->table_comp[k] < C, "table_comp out of range"); cmask[ob] |= 1u << d->table_comp[k]; }
 			for (int k = d->obs_dp_off[ob]; k < d->obs_dp_off[ob + 1]; k++) { NEED(d->obs_dp[k] >= 0 && d->obs_dp[k] < D, "obs_dp out of range"); dmask[ob] |= 1ull << d->obs_dp[k]; }
 			int na = d->obs_area_off[ob + 1] - d->obs_area_off[ob];
 			slot_off[ob + 1] = slot_off[ob] + na;
@@ -274,20 +277,22 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 /* ------------------------------------------------------------------------ */
 /* launch configuration of the trajectory kernel                             */
 /* ------------------------------------------------------------------------ */
-template <int SYNC>
-static const void *traj_fn(int mode)
+template <int SYNC, bool KEEP>
+static const void *traj_fn2(int mode)
 {
 	switch (mode) {
-	case MODE_SIM: return (const void *)k_traj<MODE_SIM, SYNC>;
-	case MODE_MBP: return (const void *)k_traj<MODE_MBP, SYNC>;
-	default: return (const void *)k_traj<MODE_REPLAY, SYNC>;
+	case MODE_SIM: return (const void *)k_traj<MODE_SIM, SYNC, KEEP>;
+	case MODE_MBP: return (const void *)k_traj<MODE_MBP, SYNC, true>;
+	default: return (const void *)k_traj<MODE_REPLAY, SYNC, true>;
 	}
 }
-static const void *traj_fn(int mode, int sync)
+/* keep = false: no trajectory array is stored (simulate + likelihood only); MBP and replay always keep */
+static const void *traj_fn(int mode, int sync, bool keep)
 {
-	if (sync == SYNC_NONE) return traj_fn<SYNC_NONE>(mode);
-	if (sync == SYNC_CTA) return traj_fn<SYNC_CTA>(mode);
-	return traj_fn<SYNC_GRID>(mode);
+	if (mode != MODE_SIM) keep = true;
+	if (sync == SYNC_NONE) return keep ? traj_fn2<SYNC_NONE, true>(mode) : traj_fn2<SYNC_NONE, false>(mode);
+	if (sync == SYNC_CTA) return keep ? traj_fn2<SYNC_CTA, true>(mode) : traj_fn2<SYNC_CTA, false>(mode);
+	return keep ? traj_fn2<SYNC_GRID, true>(mode) : traj_fn2<SYNC_GRID, false>(mode);
 }
 
 static size_t even(size_t x) { return (x + 1) & ~(size_t)1; }
@@ -317,9 +322,10 @@ static int choose_launch(BeepEngine *eng)
 		eng->nwarp = 8;
 		eng->smem_traj = (common + eng->nwarp * (2 * CDp + work)) * sizeof(double);
 	}
+	if ((long long)m.A * 1 > (1ll << 30)) return fail(BEEP_ERR_UNSUPPORTED, "too many areas");
 	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
-	for (int mode = 0; mode < 3; mode++) {
-		const void *fn = traj_fn(mode, eng->sync_mode);
+	for (int mode = 0; mode < 3; mode++) for (int keep = 0; keep < 2; keep++) {
+		const void *fn = traj_fn(mode, eng->sync_mode, keep != 0);
 		CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eng->smem_traj));
 	}
 	if (eng->sync_mode == SYNC_GRID) {
@@ -327,8 +333,8 @@ static int choose_launch(BeepEngine *eng)
 		CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, eng->device));
 		if (!coop) return fail(BEEP_ERR_UNSUPPORTED, "device lacks cooperative launch");
 		int nb = 0, nbmin = 1 << 30;
-		for (int mode = 0; mode < 3; mode++) {
-			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, traj_fn(mode, SYNC_GRID), eng->nwarp * 32, eng->smem_traj));
+		for (int mode = 0; mode < 3; mode++) for (int keep = 0; keep < 2; keep++) {
+			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, traj_fn(mode, SYNC_GRID, keep != 0), eng->nwarp * 32, eng->smem_traj));
 			nbmin = std::min(nbmin, nb);
 		}
 		if (nbmin < 1) return fail(BEEP_ERR_UNSUPPORTED, "trajectory kernel does not fit an SM");
@@ -370,6 +376,7 @@ extern "C" void beep_batch_destroy(BeepBatch *bt)
 extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBatch **out)
 {
 	if (!eng || !out || P <= 0) return fail(BEEP_ERR_INVALID, "bad argument to beep_batch_create");
+	if ((long long)P * eng->dm.A >= (1ll << 31)) return fail(BEEP_ERR_UNSUPPORTED, "P*A must be below 2^31 tiles");
 	*out = nullptr;
 	CU(cudaSetDevice(eng->device));
 	BeepBatch *bt = new BeepBatch();
@@ -477,7 +484,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
 	a.nwarp = eng->nwarp;
-	for (int tr = 0; tr < 64; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; }
+	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;
 	if (ti == 0) {
 		size_t n = (size_t)P * m.A * m.CDp;
@@ -488,7 +495,8 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 		eng->launches += 2;
 	}
 	CU(cudaEventRecord(bt->ev0, bt->stream));
-	const void *fn = traj_fn(mode, eng->sync_mode);
+	const bool keep = (bt->db.flags & (BEEP_KEEP_TRANSNUM | BEEP_KEEP_TRANSMEAN | BEEP_KEEP_POP)) != 0;
+	const void *fn = traj_fn(mode, eng->sync_mode, keep);
 	void *args[] = {(void *)&a};
 	if (eng->sync_mode == SYNC_NONE) {
 		long long ntile = (long long)P * m.A;

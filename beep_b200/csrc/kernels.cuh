@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 /* K1-K3  trajectory kernel                                                  */
 /* ------------------------------------------------------------------------ */
 
+/* A tile in pop_cur is [C*D] doubles padded to an even count (stride CDp). */
 __global__ void k_pop_reset(DevModel m, DevBatch b)
 {
 	const size_t CD = (size_t)m.C * m.D, CDp = m.CDp, n = (size_t)m.A * CDp, tot = n * b.P;
@@ -317,6 +318,50 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+/* per-warp scratch, all in shared memory */
+struct TileSm {
+	double *pop;      /* [CDp] population of the tile                                   */
+	double *ns;       /* [J*D] event counts of this step; ALL ZERO between tile steps   */
+	double *foi;      /* [D]   force of infection per dp (state.cc:428)                */
+	double *nmi;      /* [G]   NMI per age (state.cc:547-578)                           */
+	double *Iv;       /* [G]   infectivity vector before the age matvec                */
+	double *am;       /* [J*D] means of the active cells, compacted                    */
+	unsigned short *ae; /* [J*D] cell index of the active cells, compacted             */
+	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)             */
+	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)                      */
+	const double *infco;   /* [C] infectivity per compartment of the CTA's ... (global)  */
+};
+
+/* what a warp needs to know about the tile it works on (all warp-uniform) */
+struct TileCtx {
+	int p, c;
+	const double *rate, *ds, *sus, *infco, *af, *betaR;
+	double *partial;
+	unsigned long long sid;
+	unsigned infmask;
+	double diag, fac;
+	int j0, j1, rg;
+};
+
+__device__ __forceinline__ void tile_ctx(const TrajArgs &a, int p, int c, TileCtx &tc)
+{
+	const DevModel &m = a.m;
+	const DevBatch &b = a.b;
+	tc.p = p; tc.c = c;
+	tc.rate = b.transrate + (size_t)p * (m.J * m.D);
+	tc.ds = b.disc_spline + (size_t)p * (m.nspline * m.T);
+	tc.sus = b.sus + (size_t)p * m.D;
+	tc.infco = b.infco + (size_t)p * m.C;
+	tc.af = b.areafactor + (size_t)p * m.period * m.A + c;
+	tc.betaR = b.betaR + (size_t)p * (m.S * m.nR * m.T);
+	tc.partial = b.obs_partial + (size_t)p * m.nslot;
+	tc.sid = b.stream_id[p];
+	tc.infmask = (unsigned)b.infmask[p];
+	tc.diag = m.M_diag[c]; tc.fac = m.M_factor[c];
+	tc.j0 = m.Min_off[c]; tc.j1 = m.Min_off[c + 1];
+	tc.rg = m.area_rgrp[c];
+}
+
 /* dinf[st][a] of one tile from its population (state.cc:223-264): infectivity-weighted
  * number of individuals by strain and age, summed in the oracle's (co, dp) order */
 __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco, const double *pop, double *out, int ostride, int lane)
@@ -326,12 +371,12 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
 		if (lane < G) {
 			double sum = 0;
 			for (int co = 0; co < C; co++) {
-				double inf = infco[co];
+				const double inf = infco[co];
 				if (inf != 0) {
 					if (m.age_fast) {
-						for (int dp = lane; dp < Dq; dp += G) { double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
+						for (int dp = lane; dp < Dq; dp += G) { const double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
 					} else {
-						for (int dp = 0; dp < Dq; dp++) if (m.dp_age[dp] == lane) { double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
+						for (int dp = 0; dp < Dq; dp++) if (m.dp_age[dp] == lane) { const double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
 					}
 				}
 			}
@@ -340,43 +385,29 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
 	}
 }
 
-/* per-warp scratch, all in shared memory */
-struct TileSm {
-	double *pop;      /* [C*D] population of the tile                                  */
-	double *ns;       /* [J*D] event counts of this step; ALL ZERO between tile steps   */
-	double *foi;      /* [D]   force of infection per dp (state.cc:428)                */
-	double *nmi;      /* [G]   NMI per age (state.cc:547-578)                           */
-	double *Iv;       /* [G]   infectivity vector before the age matvec                */
-	double *am;       /* [J*D] means of the active cells, compacted                    */
-	unsigned short *ae; /* [J*D] cell index of the active cells, compacted             */
-	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)              */
-	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)                       */
-};
-
 /* One time step of one (particle, area) tile.  Returns the (warp-uniform) mask of
- * transitions that had events.
+ * transitions that had events (0 at the last step, whose events are never applied).
  *   1. force of infection per dp;
- *   2. SCAN the J*D cells: transition means; cells with a non-zero mean are compacted
- *      into a dense list (most cells of an epidemic are empty);
+ *   2. SCAN the J*D cells, 32 per pass: transition means; cells with a non-zero mean are
+ *      compacted into a dense list (most cells of an epidemic are empty);
  *   3. DRAW on the dense list, 32 active cells per pass, one Philox stream per cell;
  *   4. observations, population update and infectivity, visiting only the
- *      transitions that had events.                                                    */
-template <int MODE>
-__device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const int p, const int c, const int t, const int lane, const TileSm &sm,
-                                                         const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
+ *      transitions that had events.
+ * KEEP = false compiles out every trajectory store (ABC-SMC / particle-filter use). */
+template <int MODE, bool KEEP>
+__device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &tc, const int t, const int tday, const int lane, const TileSm &sm,
+                                              const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
 {
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
-	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq, C = m.C;
+	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
 	const int JD = J * D;
 	double *pop = sm.pop, *ns = sm.ns, *foi = sm.foi, *nmi = sm.nmi;
-	const double *rate = b.transrate + (size_t)p * JD;
-	const double *ds = b.disc_spline + (size_t)p * m.nspline * T;
-	const double *sus = b.sus + (size_t)p * D;
+	const double *ds = tc.ds;
 
 	/* state.cc:395-404: with several strains the susceptible pool lives in strain 0 */
 	if (S > 1) {
-		const int sfrom = m.trans_from[m.itr];
+		const int sfrom = a.tfrom[m.itr];
 		for (int dp = lane; dp < Dq; dp += 32) {
 			double sum = 0;
 			for (int st = 1; st < S; st++) { sum += pop[sfrom * D + Dq * st + dp]; pop[sfrom * D + Dq * st + dp] = 0; }
@@ -387,28 +418,32 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 
 	/* 1. state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
 	{
-		const double d = ds[m.geo_spline * T + t], omd = 1 - d, fac = m.M_factor[c];
-		const double diag = m.M_diag[c];
-		const int j0 = m.Min_off[c], j1 = m.Min_off[c + 1];
-		const double afv = b.areafactor[((size_t)p * m.period + t / m.spu) * A + c];
-		const int rg = m.area_rgrp[c];
+		const double d = ds[m.geo_spline * T + t], omd = 1 - d;
+		const double afv = tc.af[(size_t)tday * A];
+		const int nn = tc.j1 - tc.j0;
+		/* lanes fetch the (source, weight) pairs of up to 32 neighbours once; they are broadcast below */
+		int nsrc = 0; double nval = 0;
+		if (lane < nn) { nsrc = m.Min_src[tc.j0 + lane]; nval = m.Min_val[tc.j0 + lane]; }
 		for (int st = 0; st < S; st++) {
+			const double *dc = dinf_cur + (size_t)st * Ad * G;
+			double Imap = 0;
+			const int nn32 = nn < 32 ? nn : 32;
+			for (int j = 0; j < nn32; j++) {
+				const int src = __shfl_sync(FULLMASK, nsrc, j);
+				const double val = __shfl_sync(FULLMASK, nval, j);
+				if (lane < G) { const double di = dc[src * G + lane]; if (di != 0) Imap += di * val; }
+			}
+			if (lane < G) for (int j = tc.j0 + 32; j < tc.j1; j++) { const double di = dc[m.Min_src[j] * G + lane]; if (di != 0) Imap += di * m.Min_val[j]; }
 			double Iv = 0;
 			bool live = false;
 			if (lane < G) {
-				const double own = dinf_cur[(st * Ad + ci) * G + lane];
-				const double Idiag = own * diag;
-				double Imap = 0;
-				for (int j = j0; j < j1; j++) {
-					const double di = dinf_cur[(st * Ad + m.Min_src[j]) * G + lane];
-					if (di != 0) Imap += di * m.Min_val[j];
-				}
+				const double Idiag = dc[ci * G + lane] * tc.diag;
 				if (G == 1) {
-					double val = Idiag * (d + fac * omd) + Imap * d;
+					double val = Idiag * (d + tc.fac * omd) + Imap * d;
 					if (val < 0) val = 0;
 					nmi[0] = val;
 				} else {
-					Iv = (Idiag + Imap) * d + fac * Idiag * omd;
+					Iv = (Idiag + Imap) * d + tc.fac * Idiag * omd;
 					live = (Iv != 0);
 				}
 			}
@@ -420,6 +455,7 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 					if (lane < G) {
 						double sum = 0;
 						if (m.nmm == 0) {
+#pragma unroll 4
 							for (int aa = 0; aa < G; aa++) sum += sm.N0T[aa * G + lane] * sm.Iv[aa];
 						} else {
 							for (int aa = 0; aa < G; aa++) sum += ntime_elem(m, ds, t, lane, aa, sm.N0T[aa * G + lane]) * sm.Iv[aa];
@@ -430,9 +466,9 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 				} else if (lane < G) nmi[lane] = 0;
 			}
 			__syncwarp();
-			double be = b.betaR[(((size_t)p * S + st) * m.nR + rg) * T + t];
+			double be = tc.betaR[(st * m.nR + tc.rg) * T + t];
 			be *= afv;
-			const int ie = m.efoi_ref[st * A + c];
+			const int ie = m.efoi_ref[st * A + tc.c];
 			const double et = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize;
 			for (int dp = lane; dp < Dq; dp += 32) {
 				const int ag = m.dp_age[dp];
@@ -443,56 +479,58 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 	}
 
 	/* 2. scan: transition means (state.cc:434-444); compact the cells that can have events */
-	const size_t tbase = (((size_t)p * T + t) * A + c) * (size_t)JD;
-	const bool keep_tn = (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
+	const size_t tbase = KEEP ? (((size_t)tc.p * T + t) * A + tc.c) * (size_t)JD : 0;
+	const bool keep_tn = KEEP && (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = KEEP && (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
 	const bool stoch = m.stochastic != 0;
 	const unsigned lt = (1u << lane) - 1u;
+	const double dt = m.dt;
 	int nact = 0;
-	unsigned long long trbits = 0;
+	unsigned trbits = 0;
 	for (int e0 = 0; e0 < JD; e0 += 32) {
 		const int e = e0 + lane;
 		double mean = 0.0;
 		bool act = false;
+		unsigned w = 0;
 		if (e < JD) {
-			const unsigned w = sm.ctab[e];
+			w = sm.ctab[e];
 			const double popu = pop[w & 0xfffu];
 			if (popu > 0) {
 				const unsigned kind = w >> 24;
-				if (kind == 0) mean = m.dt * popu * rate[e];
-				else if (kind == 1) { const int dp = (w >> 18) & 63; mean = m.dt * popu * sus[dp] * foi[dp]; }
+				if (kind == 0) mean = dt * popu * tc.rate[e];
+				else if (kind == 1) { const int dp = (w >> 18) & 63; mean = dt * popu * tc.sus[dp] * foi[dp]; }
 			}
-			if (keep_tm && MODE != MODE_REPLAY) b.tm[tbase + e] = mean;
 			if (MODE == MODE_REPLAY) {
 				/* the events are given (state.cc:294-322); only the means are recomputed */
 				const double num = stoch ? (double)b.tn[tbase + e] : b.tm[tbase + e];
 				if (keep_tm) b.tm[tbase + e] = mean;
-				if (num != 0) { ns[e] = num; trbits |= 1ull << ((w >> 12) & 63); }
-			} else if (!stoch) {
-				if (mean != 0) { ns[e] = mean; trbits |= 1ull << ((w >> 12) & 63); }   /* state.cc:627 */
+				if (num != 0) { ns[e] = num; trbits |= 1u << ((w >> 12) & 63); }
 			} else {
-				act = (mean != 0);
-				if (keep_tn && !act) b.tn[tbase + e] = 0;
+				if (keep_tm) b.tm[tbase + e] = mean;
+				if (!stoch) { if (mean != 0) { ns[e] = mean; trbits |= 1u << ((w >> 12) & 63); } }   /* state.cc:627 */
+				else {
+					act = (mean != 0);
+					if (keep_tn && !act) b.tn[tbase + e] = 0;
+				}
 			}
 		}
-		if (MODE != MODE_REPLAY && stoch) {
+		if (MODE != MODE_REPLAY) {
 			const unsigned bal = __ballot_sync(FULLMASK, act);
-			if (act) { const int pos = nact + __popc(bal & lt); sm.ae[pos] = (unsigned short)e; sm.am[pos] = mean; }
+			if (act) { const int q = nact + __popc(bal & lt); sm.ae[q] = (unsigned short)e; sm.am[q] = mean; }
 			nact += __popc(bal);
 		}
 	}
 
 	/* 3. draws on the dense list */
-	if (MODE != MODE_REPLAY && stoch) {
+	if (MODE != MODE_REPLAY && nact > 0) {
 		__syncwarp();
-		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
-		const unsigned long long sid = b.stream_id[p];
+		const unsigned long long cell0 = ((unsigned long long)t * A + tc.c) * (unsigned long long)JD;
 		int simu = 0;
-		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
+		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)tc.p * T + t) * A + tc.c];
 		for (int i = lane; i < nact; i += 32) {
 			const int e = sm.ae[i];
 			const double mean = sm.am[i];
 			BeepStream rs;
-			beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
+			beep_stream_init_cell(&rs, a.seed, tc.sid, cell0 + e);
 			int num;
 			if (MODE == MODE_SIM) num = beep_poisson(&rs, mean);             /* state.cc:624-626 */
 			else {
@@ -507,25 +545,23 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 					else num = beep_binomial(&rs, mean / rate_i, num_i);
 				}
 			}
-			if (num != 0) { ns[e] = (double)num; trbits |= 1ull << ((sm.ctab[e] >> 12) & 63); }
+			if (num != 0) { ns[e] = (double)num; trbits |= 1u << ((sm.ctab[e] >> 12) & 63); }
 			if (keep_tn) b.tn[tbase + e] = num;
 		}
 	}
 	/* transitions with events, warp-wide (also orders the ns[] writes before the reads below) */
-	unsigned trlo = __reduce_or_sync(FULLMASK, (unsigned)trbits), trhi = 0;
-	if (J > 32) trhi = __reduce_or_sync(FULLMASK, (unsigned)(trbits >> 32));
-	const unsigned long long trmask = ((unsigned long long)trhi << 32) | trlo;
+	const unsigned trmask = __reduce_or_sync(FULLMASK, trbits);
 
 	/* 4a. obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
 	{
-		const int k0 = m.cell_off[t * A + c], k1 = m.cell_off[t * A + c + 1];
+		const int k0 = m.cell_off[t * A + tc.c], k1 = m.cell_off[t * A + tc.c + 1];
 		if (m.obs_wide) {
 			/* observations summing many dp: lanes over dp, one warp reduction per entry */
 			for (int k = k0; k < k1; k++) {
 				const ObsEnt en = m.cell_ent[k];
 				const int ob = en.ob;
-				const unsigned long long tmask0 = m.obs_tmask[ob] & trmask, cmask0 = m.obs_cmask[ob];
-				if (tmask0 == 0 && cmask0 == 0) continue;      /* no events in the observed transitions */
+				const unsigned tmask0 = m.obs_tmask[ob] & trmask, cm0 = m.obs_cmask[ob];
+				if (tmask0 == 0 && cm0 == 0) continue;         /* no events in the observed transitions */
 				const unsigned long long dmask = m.obs_dmask[ob];
 				const double factor = m.obs_factor[ob];
 				const int fs = m.obs_fs[ob];
@@ -533,35 +569,35 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 				double val = 0;
 				for (int dp = lane; dp < D; dp += 32) {
 					if (!((dmask >> dp) & 1ull)) continue;
-					unsigned long long tmask = tmask0;
+					unsigned tmask = tmask0;
 					while (tmask) {
-						const int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
+						const int tr = __ffs(tmask) - 1; tmask &= tmask - 1;
 						const double num = ns[tr * D + dp];
 						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
 					}
-					unsigned long long cmask = cmask0;
-					while (cmask) {
-						const int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
+					unsigned cm = cm0;
+					while (cm) {
+						const int co = __ffs(cm) - 1; cm &= cm - 1;
 						val += factor * pop[co * D + dp];
 					}
 				}
 				for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULLMASK, val, o);
-				if (lane == 0 && val != 0) atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
+				if (lane == 0 && val != 0) atomicAdd(&tc.partial[en.slot], val);
 			}
 		} else {
 			/* narrow observations (one or a few dp each): one lane per entry */
 			for (int k = k0 + lane; k < k1; k += 32) {
 				const ObsEnt en = m.cell_ent[k];
 				const int ob = en.ob;
-				unsigned long long tmask = m.obs_tmask[ob] & trmask, cmask = m.obs_cmask[ob];
-				if (tmask == 0 && cmask == 0) continue;
+				unsigned tmask = m.obs_tmask[ob] & trmask, cm = m.obs_cmask[ob];
+				if (tmask == 0 && cm == 0) continue;
 				const double factor = m.obs_factor[ob];
 				const int fs = m.obs_fs[ob];
 				const unsigned long long dmask = m.obs_dmask[ob];
 				double val = 0;
 				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
 				while (tmask) {
-					const int tr = __ffsll((long long)tmask) - 1; tmask &= tmask - 1;
+					const int tr = __ffs(tmask) - 1; tmask &= tmask - 1;
 					unsigned long long dm = dmask;
 					while (dm) {
 						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
@@ -569,8 +605,8 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
 					}
 				}
-				while (cmask) {
-					const int co = __ffsll((long long)cmask) - 1; cmask &= cmask - 1;
+				while (cm) {
+					const int co = __ffs(cm) - 1; cm &= cm - 1;
 					unsigned long long dm = dmask;
 					while (dm) {
 						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
@@ -578,25 +614,25 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 					}
 				}
 				/* the slot has a single owner (this tile) and steps are ordered: a plain RED */
-				if (val != 0) atomicAdd(&b.obs_partial[(size_t)p * m.nslot + en.slot], val);
+				if (val != 0) atomicAdd(&tc.partial[en.slot], val);
 			}
 		}
 	}
 
-	if (b.flags & BEEP_KEEP_POP) {
-		double *pt = b.poptraj + (((size_t)p * T + t) * A + c) * (size_t)(C * D);
-		for (int i = lane; i < C * D; i += 32) pt[i] = pop[i];
+	if (KEEP && (b.flags & BEEP_KEEP_POP)) {
+		double *pt = b.poptraj + (((size_t)tc.p * T + t) * A + tc.c) * (size_t)(m.C * D);
+		for (int i = lane; i < m.C * D; i += 32) pt[i] = pop[i];
 	}
 	__syncwarp();
 
 	/* 4b. state.cc:460-485 update_pop in transition order (the last step's events are never
 	 * applied), consuming -- and clearing -- the event counts; then the infectivity of the
 	 * new population.  Without events both are unchanged. */
+	const bool apply = (t < T - 1);
 	{
-		const bool apply = (t < T - 1);
-		unsigned long long tm_ = trmask;
+		unsigned tm_ = trmask;
 		while (tm_) {
-			const int tr = __ffsll((long long)tm_) - 1; tm_ &= tm_ - 1;
+			const int tr = __ffs(tm_) - 1; tm_ &= tm_ - 1;
 			const int fo = a.tfrom[tr] * D, to = a.tto[tr] * D;
 			for (int dp = lane; dp < D; dp += 32) {
 				const double num = ns[tr * D + dp];
@@ -608,29 +644,24 @@ __device__ __forceinline__ unsigned long long tile_step(const TrajArgs &a, const
 		}
 		__syncwarp();
 		if (apply) {
-			if (trmask & b.infmask[p]) tile_dinf(m, b.infco + (size_t)p * C, pop, dinf_nxt + ci * G, Ad * G, lane);
+			if (trmask & tc.infmask) tile_dinf(m, tc.infco, pop, dinf_nxt + ci * G, Ad * G, lane);
 			else if (lane < G) for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
 		}
 	}
 	__syncwarp();
-	return (t < T - 1) ? trmask : 0ull;
+	return apply ? trmask : 0u;
 }
 
 /* CTA-shared tables at the front of dynamic shared memory (doubles): N0T[G*G, even] ctab[J*D/2, even] */
-__device__ __forceinline__ int sm_common_doubles(const DevModel &m)
-{
-	int n0 = (m.G * m.G + 1) & ~1, ct = (((m.J * m.D + 1) >> 1) + 1) & ~1;
-	return n0 + ct;
-}
 __device__ __forceinline__ double *sm_common_init(const DevModel &m, double *smem, TileSm &ts)
 {
-	const int n0 = (m.G * m.G + 1) & ~1;
+	const int n0 = (m.G * m.G + 1) & ~1, ct = (((m.J * m.D + 1) >> 1) + 1) & ~1;
 	double *N0T = smem;
 	unsigned *ctab = (unsigned *)(smem + n0);
 	for (int i = threadIdx.x; i < m.G * m.G; i += blockDim.x) N0T[i] = m.N0T[i];
 	for (int i = threadIdx.x; i < m.J * m.D; i += blockDim.x) ctab[i] = m.cell_tab[i];
 	ts.N0T = N0T; ts.ctab = ctab;
-	return smem + sm_common_doubles(m);
+	return smem + n0 + ct;
 }
 #define EVEN(x) (((x) + 1) & ~1)
 
@@ -647,18 +678,19 @@ __device__ __forceinline__ void work_init(TileSm &ts, double *w, int JD, int De,
 	for (int i = lane; i < JD; i += 32) ts.ns[i] = 0;
 	__syncwarp();
 }
-template <int MODE, int SYNC>
+
 #ifndef BEEP_TRAJ_MINB
 #define BEEP_TRAJ_MINB 3
 #endif
+template <int MODE, int SYNC, bool KEEP>
 __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
 {
 	extern __shared__ __align__(16) double smraw[];
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = a.nwarp;
-	const int A = m.A, C = m.C, D = m.D, J = m.J, G = m.G, S = m.S;
-	const int CD = C * D, CDp = m.CDp, JD = EVEN(J * D), De = EVEN(D), Ge = EVEN(G);
+	const int A = m.A, D = m.D, J = m.J, G = m.G, S = m.S;
+	const int CDp = m.CDp, JD = EVEN(J * D), De = EVEN(D), Ge = EVEN(G);
 	TileSm ts;
 	double *sm = sm_common_init(m, smraw, ts);
 	__syncthreads();
@@ -670,15 +702,16 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		double *dinf = ts.Iv + Ge;
 		const long long tile = (long long)blockIdx.x * nwarp + warp;
 		if (tile >= (long long)b.P * A) return;
-		const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
+		TileCtx tc;
+		tile_ctx(a, (int)(tile / A), (int)(tile % A), tc);
 		double *gp = b.pop_cur + (size_t)tile * CDp;
-		for (int i = lane; i < CD; i += 32) ts.pop[i] = gp[i];
+		for (int i = lane; i < CDp; i += 32) ts.pop[i] = gp[i];
 		__syncwarp();
-		tile_dinf(m, b.infco + (size_t)p * C, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
+		tile_dinf(m, tc.infco, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
 		__syncwarp();
 		for (int t = a.ti; t < a.tf; t++)
-			tile_step<MODE>(a, p, c, t, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
-		for (int i = lane; i < CD; i += 32) gp[i] = ts.pop[i];
+			tile_step<MODE, KEEP>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+		for (int i = lane; i < CDp; i += 32) gp[i] = ts.pop[i];
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
 		double *popA = sm, *dinf = popA + (size_t)A * CDp;
@@ -687,12 +720,15 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		double *gp = b.pop_cur + (size_t)p * A * CDp;
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) popA[i] = gp[i];
 		__syncthreads();
-		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * C, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
+		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * m.C, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
 		__syncthreads();
 		for (int t = a.ti; t < a.tf; t++) {
+			const int tday = t / m.spu;
 			for (int c = warp; c < A; c += nwarp) {
+				TileCtx tc;
+				tile_ctx(a, p, c, tc);
 				ts.pop = popA + (size_t)c * CDp;
-				tile_step<MODE>(a, p, c, t, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+				tile_step<MODE, KEEP>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
 			}
 			__syncthreads();
 		}
@@ -702,46 +738,55 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		const int per = 2 * CDp + WORK_DOUBLES(JD, De, Ge);
 		double *popbuf = sm + (size_t)warp * per;
 		work_init(ts, popbuf + 2 * CDp, JD, De, Ge, lane);
-		const long long ntile = (long long)b.P * A, nw = (long long)gridDim.x * nwarp, gw = (long long)blockIdx.x * nwarp + warp;
-		const size_t dsz = (size_t)b.P * S * A * G;
+		/* tiles of this warp: gw, gw + nw, ... (32-bit: the launcher checks P*A < 2^31) */
+		const int ntile = b.P * A, nw = gridDim.x * nwarp, gw = blockIdx.x * nwarp + warp;
+		const int p0 = gw / A, c0 = gw - p0 * A, dpn = nw / A, dcn = nw - dpn * A;
+		const size_t dsz = (size_t)b.P * S * A * G, psz = (size_t)S * A * G;
 		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
-		for (long long tile = gw; tile < ntile; tile += nw) {
-			const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
-			const double *gp = b.pop_cur + (size_t)tile * CDp;
-			for (int i = lane; i < CD; i += 32) popbuf[i] = gp[i];
-			__syncwarp();
-			tile_dinf(m, b.infco + (size_t)p * C, popbuf, b.dinf + (a.ti & 1) * dsz + (size_t)p * S * A * G + c * G, A * G, lane);
-			__syncwarp();
+		{
+			int p = p0, c = c0;
+			for (int tile = gw; tile < ntile; tile += nw) {
+				const double *gp = b.pop_cur + (size_t)tile * CDp;
+				for (int i = lane; i < CDp; i += 32) popbuf[i] = gp[i];
+				__syncwarp();
+				tile_dinf(m, b.infco + (size_t)p * m.C, popbuf, b.dinf + (a.ti & 1) * dsz + (size_t)p * psz + c * G, A * G, lane);
+				__syncwarp();
+				p += dpn; c += dcn; if (c >= A) { c -= A; p++; }
+			}
 		}
 		grid.sync();
 		for (int t = a.ti; t < a.tf; t++) {
+			const int tday = t / m.spu;
+			const double *dcur = b.dinf + (t & 1) * dsz;
+			double *dnxt = b.dinf + ((t + 1) & 1) * dsz;
 			/* software pipeline over this warp's tiles: tile k+1 streams into the other buffer while tile k computes */
 			if (gw < ntile) {
 				const double *gp = b.pop_cur + (size_t)gw * CDp;
 				for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gp + 2 * i);
 				cp_async_commit();
 			}
-			int kb = 0;
-			for (long long tile = gw; tile < ntile; tile += nw, kb ^= 1) {
-				const int p = (int)(tile / A), c = (int)(tile - (long long)p * A);
+			int kb = 0, p = p0, c = c0;
+			for (int tile = gw; tile < ntile; tile += nw, kb ^= 1) {
 				double *gp = b.pop_cur + (size_t)tile * CDp;
 				if (tile + nw < ntile) {
-					const double *gn = b.pop_cur + (size_t)(tile + nw) * CDp;
+					const double *gn = gp + (size_t)nw * CDp;
 					double *dst = popbuf + (kb ^ 1) * CDp;
 					for (int i = lane; i < nchunk; i += 32) cp_async16(dst + 2 * i, gn + 2 * i);
 					cp_async_commit();
 					cp_async_wait<1>();
 				} else cp_async_wait<0>();
 				__syncwarp();
+				TileCtx tc;
+				tile_ctx(a, p, c, tc);
 				ts.pop = popbuf + kb * CDp;
-				const unsigned long long ev = tile_step<MODE>(a, p, c, t, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * S * A * G,
-				                                              b.dinf + ((t + 1) & 1) * dsz + (size_t)p * S * A * G, A, c);
+				const unsigned ev = tile_step<MODE, KEEP>(a, tc, t, tday, lane, ts, dcur + (size_t)p * psz, dnxt + (size_t)p * psz, A, c);
 				if (ev != 0 || S > 1) {
 					const double2 *s2 = (const double2 *)ts.pop;
 					double2 *g2 = (double2 *)gp;
 					for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
 				}
 				__syncwarp();
+				p += dpn; c += dcn; if (c >= A) { c -= A; p++; }
 			}
 			grid.sync();
 		}
