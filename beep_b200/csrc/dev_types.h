@@ -66,6 +66,7 @@ struct DevBatch {
 	int P; unsigned flags;
 	double *theta, *pd, *transrate, *disc_spline, *sus, *areafactor, *betaR, *infco;
 	double *pop_cur, *dinf;
+	double *scratchA;              /* [P][A] K0 scratch (per-area averages) */
 	int *tn; double *tm; double *poptraj;
 	double *obs_partial, *obs_val, *L, *EFtab, *Li;
 	unsigned long long *stream_id;

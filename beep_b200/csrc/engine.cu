@@ -392,7 +392,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.theta, (size_t)P * m.nparam); BA(b.pd, (size_t)P * m.nparam);
 	BA(b.transrate, (size_t)P * m.J * m.D); BA(b.disc_spline, (size_t)P * m.nspline * m.T); BA(b.sus, (size_t)P * m.D);
 	BA(b.areafactor, (size_t)P * m.period * m.A); BA(b.betaR, (size_t)P * m.S * m.nR * m.T); BA(b.infco, (size_t)P * m.C);
-	BA(b.pop_cur, (size_t)P * m.A * m.CDp);
+	BA(b.pop_cur, (size_t)P * m.A * m.CDp); BA(b.scratchA, (size_t)P * m.A);
 	if (eng->sync_mode == SYNC_GRID) BA(b.dinf, 2 * (size_t)P * m.S * m.A * m.G);
 	if ((flags & BEEP_KEEP_TRANSNUM) && m.stochastic) BA(b.tn, (size_t)P * TAJD);
 	if ((flags & BEEP_KEEP_TRANSMEAN) || ((flags & BEEP_KEEP_TRANSNUM) && !m.stochastic)) { BA(b.tm, (size_t)P * TAJD); b.flags |= BEEP_KEEP_TRANSMEAN; }
@@ -444,7 +444,7 @@ static int launch_set_param(BeepBatch *bt)
 {
 	BeepEngine *eng = bt->eng;
 	const DevModel &m = eng->dm;
-	size_t smem = (32 + m.Dq + (K0_THREADS / 32) * ((size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq)) * sizeof(double);
+	size_t smem = (32 + (size_t)K0_MAXINF * m.Dq + (size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq) * sizeof(double);
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_set_param, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	k_set_param<<<bt->db.P, K0_THREADS, smem, bt->stream>>>(m, bt->db);
 	eng->launches++;

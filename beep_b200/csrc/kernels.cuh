@@ -58,7 +58,7 @@ __device__ __forceinline__ double ntime_elem(const DevModel &m, const double *ds
 #define K0_THREADS 128
 #define K0_MAXINF 8
 
-/* dynamic smem: nwarp * (Dq*(Dq+1) + 3*Dq) doubles + 32 doubles */
+/* dynamic smem: 32 + K0_MAXINF*Dq + Dq*(Dq+1) + 2*Dq doubles */
 __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b)
 {
 	extern __shared__ double sm[];
@@ -129,52 +129,55 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 	}
 	__syncthreads();
 
-	/* model.cc:1182-1250 create_areafactor + calculate_area_av */
+	/* model.cc:1182-1250 create_areafactor + calculate_area_av.  exp() is the shared beep_exp and
+	 * every sum runs in the oracle's order, so the table is bit-identical to the CPU oracle's. */
 	{
 		const int period = m.period;
 		for (int i = tid; i < period * A; i += nth) {
 			int t = i / A, c = i - t * A;
-			double v = m.has_region ? exp(pd[m.region_effect_param[c]]) : 1.0;
+			double v = m.has_region ? beep_exp(pd[m.region_effect_param[c]]) : 1.0;
 			if (m.has_area_eff) v *= pd[m.area_effect_param[c]];
-			for (int j = 0; j < m.ncovar; j++) v *= exp(pd[m.covar_param[j]] * m.covar_value[((size_t)j * A + c) * period + t]);
+			for (int j = 0; j < m.ncovar; j++) v *= beep_exp(pd[m.covar_param[j]] * m.covar_value[((size_t)j * A + c) * period + t]);
 			if (m.nlevel > 0) v *= pd[m.level_param[m.level_map[i]]];
 			af[i] = v;
 		}
 		__syncthreads();
-		double part = 0;
+		/* per-area time average, parked in the first row of betaR's neighbour -- b.scratch[p][A] */
+		double *avs = b.scratchA + (size_t)p * A;
 		for (int c = tid; c < A; c += nth) {
 			double av = 0;
 			for (int t = 0; t < period; t++) av += af[t * A + c];
 			av /= period;
-			part += av * m.area_total_pop[c];
+			avs[c] = av * m.area_total_pop[c];
 		}
-		/* deterministic block reduction */
-		double *red = sm;
-		for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(FULLMASK, part, o);
-		if ((tid & 31) == 0) red[tid >> 5] = part;
 		__syncthreads();
-		if (tid == 0) { double s = 0; for (int w = 0; w < (nth >> 5); w++) s += red[w]; red[0] = s / m.popsize; }
+		if (tid == 0) {
+			double area_av = 0;
+			for (int c = 0; c < A; c++) area_av += avs[c];      /* the oracle's sequential order */
+			sm[0] = area_av / m.popsize;
+		}
 		__syncthreads();
-		double area_av = red[0];
+		const double area_av = sm[0];
 		__syncthreads();
 		for (int i = tid; i < period * A; i += nth) af[i] /= area_av;
 	}
 
-	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix
-	 * NGM = F V^-1 (model.cc:2485-2576) factorises: V is block diagonal in dp, so
-	 * NGM[q][i] = dist[q] sus[q] N_t[age q][age i] w[i],  w[i] = sum_s inf_s (V_i^-1)[s][0];
-	 * its dominant eigenvalue is found by the reference's power iteration
-	 * (matrix.cc:1139-1220), warm-started along the time axis within a warp's chunk. */
+	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix NGM = F V^-1
+	 * (model.cc:2485-2576): V is block diagonal in dp, so only column (state 0, dp = i) of the
+	 * dp = i block of V^-1 contributes to NGM[q][i]; the blocks are inverted by the reference's
+	 * Gauss-Jordan (matrix.cc:703-765) and the terms are accumulated in the reference's order.
+	 * The dominant eigenvalue is the reference's power iteration (matrix.cc:1139-1220), started
+	 * from the flat vector and warm-started from solve to solve as the reference does -- one warp,
+	 * every reduction in the oracle's sequential order, so beta is bit-identical to the oracle's. */
 	{
-		const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
-		double *wv = sm + 32;                               /* [Dq] shared by the CTA */
-		double *ngm = wv + Dq + (size_t)warp * (Dq * (Dq + 1) + 2 * Dq);
-		double *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
+		const int warp = tid >> 5, lane = tid & 31;
 		const int ninf = m.ninf;
+		double *vinv0 = sm + 32;                            /* [ninf][Dq] column 0 of each block inverse, per strain */
+		double *ngm = vinv0 + K0_MAXINF * Dq, *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
+		if (warp == 0) for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
 		for (int st = 0; st < S; st++) {
 			__syncthreads();
 			for (int dp = tid; dp < Dq; dp += nth) {
-				/* V for this dp (ninf x ninf), model.cc:2485-2522, then Gauss-Jordan as matrix.cc:703-765 */
 				double V[K0_MAXINF * K0_MAXINF], inv[K0_MAXINF * K0_MAXINF];
 				for (int i = 0; i < ninf * ninf; i++) { V[i] = 0; inv[i] = 0; }
 				for (int i = 0; i < ninf; i++) inv[i * ninf + i] = 1;
@@ -203,61 +206,58 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 						double rr = V[jj * ninf + ii];
 						if (rr != 0) for (int i = 0; i < ninf; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
 					}
-				double w = 0;
-				for (int is = 0; is < ninf; is++) {
-					double inf = pd[m.comp_inf_param[m.inf_state[is]]];
-					if (inf != 0) w += inf * inv[is * ninf + 0];
-				}
-				wv[dp] = w;
+				for (int is = 0; is < ninf; is++) vinv0[is * Dq + dp] = inv[is * ninf + 0];
 			}
 			__syncthreads();
-			for (int ir = 0; ir < m.nR; ir++) {
+			if (warp == 0) for (int ir = 0; ir < m.nR; ir++) {
 				const int spl = m.R_spline_ref[ir];
 				const double *dist = m.R_dist + (size_t)ir * Dq;
 				const double rfac = pd[m.strain_Rfactor_param[st]];
 				double *out = betaR + ((size_t)st * m.nR + ir) * T;
-				/* time chunk of this warp */
-				int t0 = (int)(((long long)T * warp) / nwarp), t1 = (int)(((long long)T * (warp + 1)) / nwarp);
-				if (m.nmm == 0) { t0 = (warp == 0) ? 0 : T; t1 = (warp == 0) ? 1 : T; }
-				for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
+				__syncwarp();
 				double ratio = 0;
-				for (int t = t0; t < t1; t++) {
-					bool recompute = (t == t0);
-					if (!recompute) {
+				for (int t = 0; t < T; t++) {
+					bool recompute = (t == 0);
+					if (!recompute && m.nmm > 0) {
 						/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY */
 						int ch = 0;
 						for (int i = lane; i < G * G; i += 32) {
-							int a = i / G, bb = i - a * G;
+							int aa = i / G, bb = i - aa * G;
 							double n0 = m.N0[i];
-							double x = ntime_elem(m, ds, t, a, bb, n0), y = ntime_elem(m, ds, t - 1, a, bb, n0);
+							double x = ntime_elem(m, ds, t, aa, bb, n0), y = ntime_elem(m, ds, t - 1, aa, bb, n0);
 							if (y < x - 0.00000001 || y > x + 0.00000001) ch = 1;
 						}
 						recompute = __any_sync(FULLMASK, ch);
 					}
 					if (recompute) {
-						__syncwarp();
 						for (int i = lane; i < Dq * Dq; i += 32) {
 							int q = i / Dq, k = i - q * Dq;
 							int aq = m.dp_age[q], ak = m.dp_age[k];
 							double nt = ntime_elem(m, ds, t, aq, ak, m.N0[aq * G + ak]);
-							ngm[q * (Dq + 1) + k] = dist[q] * sus[Dq * st + q] * nt * wv[k];
+							double sum = 0;
+							for (int is = 0; is < ninf; is++) {
+								double inf = pd[m.comp_inf_param[m.inf_state[is]]];
+								if (inf != 0) sum += dist[q] * sus[Dq * st + q] * inf * nt * vinv0[is * Dq + k];
+							}
+							ngm[q * (Dq + 1) + k] = sum;
 						}
 						__syncwarp();
 						double ev = 0;
 						for (unsigned loop = 0;; loop++) {
-							double sum = 0;
 							for (int q = lane; q < Dq; q += 32) {
 								double acc = 0;
 								for (int k = 0; k < Dq; k++) acc += ngm[q * (Dq + 1) + k] * vec[k];
 								vec2[q] = acc;
-								sum += acc;
 							}
-							for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
-							double ev_new = sum;
+							__syncwarp();
+							double sum = 0;
+							for (int k = 0; k < Dq; k++) sum += vec2[k];          /* every lane, the oracle's order */
+							const double ev_new = sum;
 							int bad = 0;
 							double lim = 100 * 0.000000000000001;
 							if (loop > 100) lim *= 10;
 							if (loop > 1000) lim *= 10;
+							__syncwarp();
 							for (int q = lane; q < Dq; q += 32) {
 								double v2 = vec2[q] / sum;
 								double dif = v2 - vec[q];
@@ -274,14 +274,16 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 							for (int q = lane; q < Dq; q += 32) vec[q] = vec2[q];
 							__syncwarp();
 							ev = ev_new;
-							if (loop > 10000) break;
+							if (loop + 1 > 10000) break;
 						}
 						ratio = ev;
 					}
 					if (m.nmm == 0) {
 						/* age matrix constant in time: one eigenvalue serves every step */
 						for (int tt = lane; tt < T; tt += 32) out[tt] = rfac * ds[spl * T + tt] / ratio;
-					} else if (lane == 0) out[t] = rfac * ds[spl * T + t] / ratio;
+						break;
+					}
+					if (lane == 0) out[t] = rfac * ds[spl * T + t] / ratio;
 				}
 				__syncwarp();
 			}

@@ -147,9 +147,10 @@ static void invert_matrix(double *M, double *inv, int n)
 }
 
 /* matrix.cc:1139-1220 largest_eigenvalue: power iteration, L1-normalised, warm
- * started; the reference seeds the first guess with ran() (matrix.cc:1171-1173),
- * here with a flat vector -- the converged value agrees to the 1e-13 stopping
- * tolerance. */
+ * started along the time axis.  The reference seeds its first guess with ran()
+ * and then carries it GLOBALLY across calls (matrix.cc:1136,1171-1173); here every
+ * set_param starts from the flat vector (the harness resets the reference's global
+ * to the same), so the result does not depend on the call history. */
 static double largest_eigenvalue(OracleState *s, const double *M, int n)
 {
 	if (s->eig_n != n) {
@@ -191,6 +192,7 @@ int oracle_set_param(OracleState *s, const double *theta)
 	const BeepModelDesc *m = s->m;
 	int T = m->T, A = m->A, J = m->J, D = m->D, G = m->G, S = m->S, Dq = m->Dq;
 	memcpy(s->paramval, theta, m->nparam * sizeof(double));
+	s->eig_n = 0;                                   /* flat start of the power iteration, see largest_eigenvalue */
 	double *pd = s->paramv_dir;
 	memcpy(pd, theta, m->nparam * sizeof(double));
 
@@ -240,19 +242,20 @@ int oracle_set_param(OracleState *s, const double *theta)
 		s->sus[dp] = val;
 	}
 
-	/* model.cc:1182-1250 create_areafactor + calculate_area_av */
+	/* model.cc:1182-1250 create_areafactor + calculate_area_av; exp() is the shared beep_exp
+	 * (include/beep_rng.h, ~1 ulp from libm) so that host and device agree bit for bit */
 	{
 		int period = m->period;
 		double *af = dalloc(A);
 		for (int c = 0; c < A; c++) {
-			af[c] = (m->n_region_effect_param > 0) ? exp(pd[m->region_effect_param[c]]) : 1;
+			af[c] = (m->n_region_effect_param > 0) ? beep_exp(pd[m->region_effect_param[c]]) : 1;
 			if (m->n_area_effect_param > 0) af[c] *= pd[m->area_effect_param[c]];
 		}
 		for (int t = 0; t < period; t++) for (int c = 0; c < A; c++) s->areafactor[t * A + c] = af[c];
 		for (int j = 0; j < s->ncovar; j++)
 			for (int t = 0; t < period; t++)
 				for (int c = 0; c < A; c++)
-					s->areafactor[t * A + c] *= exp(pd[m->covar_param[j]] * m->covar_value[((long)j * A + c) * period + t]);
+					s->areafactor[t * A + c] *= beep_exp(pd[m->covar_param[j]] * m->covar_value[((long)j * A + c) * period + t]);
 		if (s->nlevel > 0)
 			for (int t = 0; t < period; t++)
 				for (int c = 0; c < A; c++) s->areafactor[t * A + c] *= pd[m->level_param[m->level_map[t * A + c]]];
