@@ -57,7 +57,7 @@ struct BeepBatch {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool have_params = false, have_sim_time = false;
 	int cur_t = 0;
-	double *d_scratch = nullptr;    /* [P*max(ntable,K5_CHUNKS,1)] */
+	double *d_scratch = nullptr;    /* [P * max(K5_CHUNKS, OBS_CHUNKS*(1+ntable))] */
 	double *h_pinned = nullptr; size_t h_pinned_n = 0;
 	unsigned *d_map = nullptr; unsigned char *d_flag = nullptr;
 	unsigned char *d_mask = nullptr; size_t d_mask_n = 0;
@@ -400,7 +400,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
 	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
 	BA(b.stream_id, P); BA(b.infmask, P);
-	BA(bt->d_scratch, (size_t)P * K5_CHUNKS);
+	BA(bt->d_scratch, (size_t)P * std::max<size_t>(K5_CHUNKS, (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
 		std::vector<unsigned long long> ids(P);
@@ -446,8 +446,13 @@ static int launch_set_param(BeepBatch *bt)
 	const DevModel &m = eng->dm;
 	size_t smem = (32 + (size_t)K0_MAXINF * m.Dq + (size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq) * sizeof(double);
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_set_param, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_set_param<<<bt->db.P, K0_THREADS, smem, bt->stream>>>(m, bt->db);
-	eng->launches++;
+	const int P = bt->db.P;
+	k_set_param<<<P, K0_THREADS, smem, bt->stream>>>(m, bt->db);
+	k_areafactor_fill<<<dim3(P, (m.A + 127) / 128), 128, 0, bt->stream>>>(m, bt->db);
+	k_areafactor_sum<<<(P + 63) / 64, 64, 0, bt->stream>>>(m, bt->db);
+	size_t naf = (size_t)m.period * m.A;
+	k_areafactor_scale<<<dim3(P, (unsigned)std::min<size_t>((naf + 255) / 256, 1024)), 256, 0, bt->stream>>>(m, bt->db);
+	eng->launches += 4;
 	CU(cudaGetLastError());
 	bt->have_params = true;
 	return BEEP_OK;
@@ -586,8 +591,10 @@ extern "C" int beep_obs_loglik_dev(BeepBatch *bt, int section, double *L_dev, do
 	BeepEngine *eng = bt->eng;
 	if (section >= eng->dm.nsection) return fail(BEEP_ERR_INVALID, "section %d out of range", section);
 	CU(cudaSetDevice(eng->device));
-	k_obs_final<<<bt->db.P, RED_THREADS, 0, bt->stream>>>(eng->dm, bt->db, section, L_dev ? L_dev : bt->db.L, EF_dev);
-	eng->launches++;
+	const int P = bt->db.P, wt = EF_dev ? 1 : 0, nq = wt ? 1 + eng->dm.ntable : 1;
+	k_obs_final<<<dim3(P, OBS_CHUNKS), RED_THREADS, 0, bt->stream>>>(eng->dm, bt->db, section, wt, bt->d_scratch);
+	k_obs_reduce<<<(P * nq + 127) / 128, 128, 0, bt->stream>>>(eng->dm, P, wt, bt->d_scratch, L_dev ? L_dev : bt->db.L, EF_dev);
+	eng->launches += 2;
 	CU(cudaGetLastError());
 	return BEEP_OK;
 }
@@ -632,7 +639,7 @@ extern "C" int beep_latent_loglik(BeepBatch *bt, double *Li_host)
 	if (!bt->db.tm || (m.stochastic && !bt->db.tn)) return fail(BEEP_ERR_STATE, "beep_latent_loglik needs a batch that keeps transnum and transmean");
 	CU(cudaSetDevice(eng->device));
 	const int P = bt->db.P;
-	k_latent_partial<<<dim3(K5_CHUNKS, P), RED_THREADS, 0, bt->stream>>>(m, bt->db, bt->d_scratch);
+	k_latent_partial<<<dim3(P, K5_CHUNKS), RED_THREADS, 0, bt->stream>>>(m, bt->db, bt->d_scratch);
 	k_latent_final<<<(P + 127) / 128, 128, 0, bt->stream>>>(P, bt->d_scratch, bt->db.Li);
 	eng->launches += 2;
 	CU(cudaGetLastError());
@@ -661,7 +668,7 @@ static int gather_inplace(BeepBatch *bt, Tp *arr, size_t n, const unsigned *d_ma
 	Tp *tmp = (Tp *)bt->d_tmp;
 	CU(cudaMemcpyAsync(tmp, arr, need, cudaMemcpyDeviceToDevice, bt->stream));
 	int gx = (int)std::min<size_t>((n + 255) / 256, 1024);
-	k_gather_slab<Tp><<<dim3(gx, P), 256, 0, bt->stream>>>(arr, tmp, d_map, n, P);
+	k_gather_slab<Tp><<<dim3(P, gx), 256, 0, bt->stream>>>(arr, tmp, d_map, n, P);
 	bt->eng->launches++;
 	CU(cudaGetLastError());
 	return BEEP_OK;
@@ -703,7 +710,7 @@ static int copy_flagged(BeepBatch *dst, Tp *d, const Tp *s, size_t n)
 {
 	if (!d || !s || n == 0) return BEEP_OK;
 	int gx = (int)std::min<size_t>((n + 255) / 256, 1024);
-	k_copy_flagged<Tp><<<dim3(gx, dst->db.P), 256, 0, dst->stream>>>(d, s, dst->d_flag, n, dst->db.P);
+	k_copy_flagged<Tp><<<dim3(dst->db.P, gx), 256, 0, dst->stream>>>(d, s, dst->d_flag, n, dst->db.P);
 	dst->eng->launches++;
 	CU(cudaGetLastError());
 	return BEEP_OK;

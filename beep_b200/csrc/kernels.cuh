@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 	double *transrate = b.transrate + (size_t)p * J * D;
 	double *ds = b.disc_spline + (size_t)p * m.nspline * T;
 	double *sus = b.sus + (size_t)p * D;
-	double *af = b.areafactor + (size_t)p * m.period * A;
 	double *betaR = b.betaR + (size_t)p * S * m.nR * T;
 	double *infco = b.infco + (size_t)p * m.C;
 
@@ -128,39 +127,6 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		}
 	}
 	__syncthreads();
-
-	/* model.cc:1182-1250 create_areafactor + calculate_area_av.  exp() is the shared beep_exp and
-	 * every sum runs in the oracle's order, so the table is bit-identical to the CPU oracle's. */
-	{
-		const int period = m.period;
-		for (int i = tid; i < period * A; i += nth) {
-			int t = i / A, c = i - t * A;
-			double v = m.has_region ? beep_exp(pd[m.region_effect_param[c]]) : 1.0;
-			if (m.has_area_eff) v *= pd[m.area_effect_param[c]];
-			for (int j = 0; j < m.ncovar; j++) v *= beep_exp(pd[m.covar_param[j]] * m.covar_value[((size_t)j * A + c) * period + t]);
-			if (m.nlevel > 0) v *= pd[m.level_param[m.level_map[i]]];
-			af[i] = v;
-		}
-		__syncthreads();
-		/* per-area time average, parked in the first row of betaR's neighbour -- b.scratch[p][A] */
-		double *avs = b.scratchA + (size_t)p * A;
-		for (int c = tid; c < A; c += nth) {
-			double av = 0;
-			for (int t = 0; t < period; t++) av += af[t * A + c];
-			av /= period;
-			avs[c] = av * m.area_total_pop[c];
-		}
-		__syncthreads();
-		if (tid == 0) {
-			double area_av = 0;
-			for (int c = 0; c < A; c++) area_av += avs[c];      /* the oracle's sequential order */
-			sm[0] = area_av / m.popsize;
-		}
-		__syncthreads();
-		const double area_av = sm[0];
-		__syncthreads();
-		for (int i = tid; i < period * A; i += nth) af[i] /= area_av;
-	}
 
 	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix NGM = F V^-1
 	 * (model.cc:2485-2576): V is block diagonal in dp, so only column (state 0, dp = i) of the
@@ -289,6 +255,47 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 			}
 		}
 	}
+}
+
+/* model.cc:1182-1250 create_areafactor + calculate_area_av, three launches so that large
+ * area counts fill the machine.  exp() is the shared beep_exp and every sum runs in the
+ * oracle's order (time average per area sequential in t, population-weighted sum sequential
+ * in c), so the table is bit-identical to the CPU oracle's. */
+__global__ void k_areafactor_fill(DevModel m, DevBatch b)
+{
+	const int p = blockIdx.x, c = blockIdx.y * blockDim.x + threadIdx.x, A = m.A, period = m.period;
+	if (c >= A) return;
+	const double *pd = b.pd + (size_t)p * m.nparam;
+	double *af = b.areafactor + (size_t)p * period * A;
+	double base = m.has_region ? beep_exp(pd[m.region_effect_param[c]]) : 1.0;
+	if (m.has_area_eff) base *= pd[m.area_effect_param[c]];
+	double av = 0;
+	for (int t = 0; t < period; t++) {
+		double v = base;
+		for (int j = 0; j < m.ncovar; j++) v *= beep_exp(pd[m.covar_param[j]] * m.covar_value[((size_t)j * A + c) * period + t]);
+		if (m.nlevel > 0) v *= pd[m.level_param[m.level_map[t * A + c]]];
+		af[(size_t)t * A + c] = v;
+		av += v;
+	}
+	av /= period;
+	b.scratchA[(size_t)p * A + c] = av * m.area_total_pop[c];
+}
+__global__ void k_areafactor_sum(DevModel m, DevBatch b)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= b.P) return;
+	const double *avs = b.scratchA + (size_t)p * m.A;
+	double area_av = 0;
+	for (int c = 0; c < m.A; c++) area_av += avs[c];
+	b.Li[p] = area_av / m.popsize;          /* Li doubles as K0 scratch; it is rewritten by beep_latent_loglik */
+}
+__global__ void k_areafactor_scale(DevModel m, DevBatch b)
+{
+	const int p = blockIdx.x;
+	const size_t n = (size_t)m.period * m.A;
+	double *af = b.areafactor + (size_t)p * n;
+	const double area_av = b.Li[p];
+	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) af[i] /= area_av;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -854,33 +861,50 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 	return s;
 }
 
-/* one CTA per particle: obs_value, log-probability, L and the per-table split.
- * section < 0: every observation (obsmodel.cc:22-35); else that section only (:39-58) */
-__global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch b, int section, double *L_out, double *EF_out)
+/* obs_value, log-probability, L and the per-table split.  The observations of a particle are cut
+ * into OBS_CHUNKS fixed chunks (one CTA each, fixed reduction tree), summed in chunk order by
+ * k_obs_reduce -- deterministic, and enough CTAs for a million observations per particle.
+ * section < 0: every observation (obsmodel.cc:22-35); else that section only (:39-58).
+ * part is [P][OBS_CHUNKS][1 + ntable]. */
+#define OBS_CHUNKS 32
+__global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch b, int section, int want_tables, double *part)
 {
 	__shared__ double red[RED_THREADS / 32];
-	const int p = blockIdx.x;
-	const double *part = b.obs_partial + (size_t)p * m.nslot;
+	const int p = blockIdx.x, ch = blockIdx.y;
+	const int lo = (int)((long long)m.nobs * ch / OBS_CHUNKS), hi = (int)((long long)m.nobs * (ch + 1) / OBS_CHUNKS);
+	const double *pt = b.obs_partial + (size_t)p * m.nslot;
 	double *oval = b.obs_val + (size_t)p * m.nobs;
+	double *out = part + ((size_t)p * OBS_CHUNKS + ch) * (1 + m.ntable);
 	double acc = 0;
-	for (int ob = threadIdx.x; ob < m.nobs; ob += blockDim.x) {
+	for (int ob = lo + threadIdx.x; ob < hi; ob += blockDim.x) {
 		if (section >= 0 && m.obs_section[ob] != section) continue;
 		double v = 0;
-		for (int k = m.obs_slot_off[ob]; k < m.obs_slot_off[ob + 1]; k++) v += part[k];
+		for (int k = m.obs_slot_off[ob]; k < m.obs_slot_off[ob + 1]; k++) v += pt[k];
 		oval[ob] = v;
 		acc += d_obs_prob(m, v, ob);
 	}
 	double L = block_sum(acc, red);
-	if (threadIdx.x == 0) L_out[p] = L;
-	if (EF_out) {
+	if (threadIdx.x == 0) out[0] = L;
+	if (want_tables) {
 		for (int tb = 0; tb < m.ntable; tb++) {
 			double a2 = 0;
-			for (int ob = threadIdx.x; ob < m.nobs; ob += blockDim.x)
+			for (int ob = lo + threadIdx.x; ob < hi; ob += blockDim.x)
 				if (m.obs_table[ob] == tb && (section < 0 || m.obs_section[ob] == section)) a2 += -2 * d_obs_prob(m, oval[ob], ob);
 			double s = block_sum(a2, red);
-			if (threadIdx.x == 0) EF_out[(size_t)p * m.ntable + tb] = s;
+			if (threadIdx.x == 0) out[1 + tb] = s;
 		}
 	}
+}
+__global__ void k_obs_reduce(DevModel m, int P, int want_tables, const double *part, double *L_out, double *EF_out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int nq = want_tables ? 1 + m.ntable : 1;
+	if (i >= P * nq) return;
+	const int p = i / nq, q = i - p * nq;
+	double s = 0;
+	for (int ch = 0; ch < OBS_CHUNKS; ch++) s += part[((size_t)p * OBS_CHUNKS + ch) * (1 + m.ntable) + q];
+	if (q == 0) L_out[p] = s;
+	else EF_out[(size_t)p * m.ntable + (q - 1)] = s;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -890,7 +914,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch 
 __global__ void __launch_bounds__(RED_THREADS) k_latent_partial(DevModel m, DevBatch b, double *partial)
 {
 	__shared__ double red[RED_THREADS / 32];
-	const int p = blockIdx.y, ch = blockIdx.x;
+	const int p = blockIdx.x, ch = blockIdx.y;
 	const size_t n = (size_t)m.T * m.A * m.J * m.D;
 	const size_t lo = n * ch / K5_CHUNKS, hi = n * (ch + 1) / K5_CHUNKS;
 	const int *tn = b.tn + (size_t)p * n;
@@ -918,22 +942,22 @@ __global__ void k_latent_final(int P, const double *partial, double *Li)
 template <typename Tp>
 __global__ void k_gather_slab(Tp *dst, const Tp *src, const unsigned *map, size_t n, int P)
 {
-	const int p = blockIdx.y;
+	const int p = blockIdx.x;
 	unsigned s = map ? map[p] : (unsigned)p;
 	if (s == 0xFFFFFFFFu) s = (unsigned)p;
 	const Tp *sp = src + (size_t)s * n;
 	Tp *dp = dst + (size_t)p * n;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp[i] = sp[i];
+	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) dp[i] = sp[i];
 }
 /* dst[p] <- src[p] where flag[p] != 0 */
 template <typename Tp>
 __global__ void k_copy_flagged(Tp *dst, const Tp *src, const unsigned char *flag, size_t n, int P)
 {
-	const int p = blockIdx.y;
+	const int p = blockIdx.x;
 	if (!flag[p]) return;
 	const Tp *sp = src + (size_t)p * n;
 	Tp *dp = dst + (size_t)p * n;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dp[i] = sp[i];
+	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) dp[i] = sp[i];
 }
 
 /* sampler parity helpers (tests/test_rng_parity.py) */

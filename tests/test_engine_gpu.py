@@ -375,6 +375,32 @@ def test_permute_and_section_state():
         assert L1[k] == L0[s]
 
 
+def test_many_particles():
+    """More particles than a grid's y-dimension allows (65535): the particle index rides on grid.x."""
+    from beep_b200 import engine as E
+    m, d = load_golden("EX_A1")
+    ms = _variant(m, stochastic=1)
+    eng = _engine(ms)
+    P = 70000
+    b = eng.batch(P, E.KEEP_TRANSNUM | E.KEEP_TRANSMEAN)
+    b.set_params(d["theta"][0])
+    b.simulate(seed=17)
+    L = b.obs_loglik()
+    Li = b.latent_loglik()
+    st = OracleState(ms, stochastic=1, keyed=True, imap_from_pop=True)
+    st.set_param(d["theta"][0])
+    for k in (0, 65535, 65536, P - 1):
+        st.simulate(seed=17, stream_id=k)
+        assert np.array_equal(b.trajectory(k).astype(np.int64), st.transnum.astype(np.int64))
+        assert relerr(L[k], st.obs_loglik()) < RTOL
+        assert relerr(Li[k], st.latent_loglik()) < RTOL
+    src = np.full(P, E.KEEP, dtype=np.uint32)
+    src[P - 1] = 3
+    t3 = b.trajectory(3)
+    b.permute(src, E.PERMUTE_FULL)
+    assert np.array_equal(b.trajectory(P - 1), t3)
+
+
 def test_error_paths():
     from beep_b200 import engine as E
     m, d = load_golden("EX_sim")
