@@ -808,6 +808,30 @@ extern "C" int beep_get_pop(BeepBatch *bt, int slot, double *out, int64_t n)
 	return BEEP_OK;
 }
 
+/* whole-batch section state [P][A][C][D] (mpi.cc:286-288 ships pop; Imap/Idiag are re-derived from it) */
+extern "C" int beep_get_pop_all(BeepBatch *bt, double *out)
+{
+	if (!bt || !out) return fail(BEEP_ERR_INVALID, "null argument");
+	const DevModel &m = bt->eng->dm;
+	const size_t CD = (size_t)m.C * m.D;
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaMemcpy2DAsync(out, CD * sizeof(double), bt->db.pop_cur, (size_t)m.CDp * sizeof(double), CD * sizeof(double), (size_t)bt->db.P * m.A, cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+extern "C" int beep_set_pop_all(BeepBatch *bt, const double *in, int cur_t)
+{
+	if (!bt || !in) return fail(BEEP_ERR_INVALID, "null argument");
+	const DevModel &m = bt->eng->dm;
+	if (cur_t < 0 || cur_t > m.T) return fail(BEEP_ERR_INVALID, "step %d out of range", cur_t);
+	const size_t CD = (size_t)m.C * m.D;
+	CU(cudaSetDevice(bt->eng->device));
+	CU(cudaStreamSynchronize(bt->stream));
+	CU(cudaMemcpy2D(bt->db.pop_cur, (size_t)m.CDp * sizeof(double), in, CD * sizeof(double), CD * sizeof(double), (size_t)bt->db.P * m.A, cudaMemcpyHostToDevice));
+	bt->cur_t = cur_t;
+	return BEEP_OK;
+}
+
 extern "C" int beep_get_derived(BeepBatch *bt, int slot, int which, double *out, int64_t n)
 {
 	int rc = slot_ok(bt, slot);

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "beep_get_derived": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int64]),
     "beep_get_trajectory": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int64]),
     "beep_get_pop": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64]),
+    "beep_get_pop_all": (ctypes.c_int, [_vp, _vp]),
+    "beep_set_pop_all": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "beep_sync": (ctypes.c_int, [_vp]),
     "beep_batch_stream": (_vp, [_vp]),
     "beep_launch_count": (ctypes.c_int64, [_vp]),
@@ -252,6 +254,17 @@ class Batch:
         out = np.zeros((m.A, m.C, m.D))
         _check(self.L.beep_get_pop(self.h, slot, out.ctypes.data, out.size))
         return out
+
+    def pop_all(self):
+        m = self.model
+        out = np.zeros((self.P, m.A, m.C, m.D))
+        _check(self.L.beep_get_pop_all(self.h, out.ctypes.data))
+        return out
+
+    def set_pop_all(self, pop, cur_step):
+        p = _f64(pop)
+        assert p.size == self.P * self.model.A * self.model.C * self.model.D
+        _check(self.L.beep_set_pop_all(self.h, p.ctypes.data, int(cur_step)))
 
     def sync(self):
         _check(self.L.beep_sync(self.h))

@@ -179,6 +179,12 @@ int beep_get_trajectory(BeepBatch *batch, int slot, int which, double *out_host,
 /* population at the batch's current step, [A][C][D]                         */
 int beep_get_pop(BeepBatch *batch, int slot, double *out_host, int64_t n);
 
+/* Section state of the whole batch, [P][A][C][D]: what Mpi::end_sec_swap ships between ranks
+ * (mpi.cc:286-288; Imap/Idiag are re-derived from pop).  set also declares the step the batch
+ * now stands at, so that the next beep_simulate(ti, ...) continues from it.                    */
+int beep_get_pop_all(BeepBatch *batch, double *pop_host);
+int beep_set_pop_all(BeepBatch *batch, const double *pop_host, int cur_step);
+
 int beep_sync(BeepBatch *batch);
 /* the batch's cudaStream_t, for callers that time or enqueue on it          */
 void *beep_batch_stream(BeepBatch *batch);

@@ -1,0 +1,102 @@
+// beep_b200.hpp -- header-only C++ wrapper over the C ABI (include/beep_b200.h).
+//
+// The reference's drivers hold `State` / `vector<State> particle` / `vector<Particle> part`
+// by value and call their members directly (pmcmc.cc:60-66,180-207; abcsmc.cc:42-71;
+// mbp.cc:99-133).  These RAII classes are the batched counterparts a driver holds instead:
+//   beep::Engine      <- Details + Data + Model tables on one GPU   (main.cc:125-151)
+//   beep::BatchState  <- vector<State>                              (state.hh:11-133)
+// Errors become exceptions carrying beep_last_error() (the reference exits, utils.cc:296-316).
+#ifndef BEEP_B200_HPP
+#define BEEP_B200_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "beep_b200.h"
+
+namespace beep {
+
+struct Error : std::runtime_error {
+	int code;
+	Error(int c, const std::string &msg) : std::runtime_error(msg), code(c) {}
+};
+inline void check(int rc) { if (rc != BEEP_OK) throw Error(rc, beep_last_error()); }
+
+class Engine {
+public:
+	Engine(const BeepModelDesc &desc, int device = 0) { check(beep_engine_create(&desc, device, &h_)); }
+	~Engine() { beep_engine_destroy(h_); }
+	Engine(const Engine &) = delete;
+	Engine &operator=(const Engine &) = delete;
+	BeepEngine *handle() const { return h_; }
+	int nsection() const { return beep_num_sections(h_); }
+	void section_range(int s, int &ti, int &tf) const { check(beep_section_range(h_, s, &ti, &tf)); }
+private:
+	BeepEngine *h_ = nullptr;
+};
+
+/// P particles in HBM.  Method names follow State / ObservationModel / Mbp of the reference.
+class BatchState {
+public:
+	BatchState(Engine &eng, int nparticle, unsigned flags = 0) : eng_(eng) { check(beep_batch_create(eng.handle(), nparticle, flags, &h_)); }
+	~BatchState() { beep_batch_destroy(h_); }
+	BatchState(const BatchState &) = delete;
+	BatchState &operator=(const BatchState &) = delete;
+	BeepBatch *handle() const { return h_; }
+	int size() const { return beep_batch_size(h_); }
+
+	/// State::set_param (state.cc:66-91) for every particle; theta is [P][nparam]
+	void set_param(const std::vector<double> &theta) { check(beep_set_params(h_, theta.data())); }
+	/// State::simulate(ti,tf) (state.cc:596-638)
+	void simulate(int ti, int tf, uint64_t seed, const uint64_t *stream_ids = nullptr) { check(beep_simulate(h_, ti, tf, seed, stream_ids)); }
+	/// ObservationModel::calculate / calculate_section (obsmodel.cc:22-58); EF = -2 L (state.cc:95-98)
+	std::vector<double> obs_loglik(int section = -1)
+	{
+		std::vector<double> L(size());
+		check(beep_obs_loglik(h_, section, L.data(), nullptr));
+		return L;
+	}
+	/// State::likelihood (state.cc:812-826)
+	std::vector<double> likelihood()
+	{
+		std::vector<double> Li(size());
+		check(beep_latent_loglik(h_, Li.data()));
+		return Li;
+	}
+	/// Mbp::mbp (mbp.cc:252-330): this batch is the proposal, coupled slot by slot to `initial`
+	void mbp(BatchState &initial, uint64_t seed, const uint8_t *simu_mask = nullptr) { check(beep_mbp(initial.h_, h_, simu_mask, BEEP_INF_DIF_UPDATE, seed, nullptr)); }
+	/// Mbp::swap_initial_propose_state (mbp.cc:243-248) for the accepted slots
+	void accept_from(BatchState &proposal, const std::vector<uint8_t> &accept) { check(beep_accept(h_, proposal.h_, accept.data())); }
+	/// State::initialise_from_particle (state.cc:294-322)
+	void replay() { check(beep_replay(h_)); }
+	/// Mpi::copy_particles / end_sec_swap within one GPU (mpi.cc:81-165,215-327)
+	void permute(const std::vector<uint32_t> &src_of, int what) { check(beep_permute(h_, src_of.data(), what)); }
+private:
+	Engine &eng_;
+	BeepBatch *h_ = nullptr;
+};
+
+/// PMCMC::obs_prob (pmcmc.cc:180-207) + bootstrap (:211-268) on one GPU: log marginal likelihood
+/// estimate of the bootstrap particle filter for one parameter vector shared by all particles.
+inline double particle_filter(Engine &eng, BatchState &particles, const std::vector<double> &theta_all, uint64_t seed, double invT = 1.0)
+{
+	particles.set_param(theta_all);
+	double loglik = 0;
+	std::vector<uint32_t> back(particles.size());
+	for (int s = 0; s < eng.nsection(); s++) {
+		int ti, tf;
+		eng.section_range(s, ti, tf);
+		if (s > 0) particles.permute(back, BEEP_PERMUTE_SECTION_STATE);
+		particles.simulate(ti, tf, seed);
+		std::vector<double> L = particles.obs_loglik(s);
+		double inc;
+		check(beep_bootstrap(L.data(), (int)L.size(), invT, seed, s, &inc, back.data()));
+		loglik += inc;
+	}
+	return loglik;
+}
+
+} // namespace beep
+#endif
