@@ -420,6 +420,7 @@ extern "C" int beep_batch_size(const BeepBatch *bt) { return bt ? bt->db.P : 0; 
 extern "C" int64_t beep_batch_bytes(const BeepBatch *bt) { return bt ? bt->bytes : 0; }
 extern "C" void *beep_batch_stream(BeepBatch *bt) { return bt ? (void *)bt->stream : nullptr; }
 extern "C" int64_t beep_launch_count(const BeepEngine *eng) { return eng ? eng->launches : 0; }
+extern "C" int beep_engine_sync_scope(const BeepEngine *eng) { return eng ? eng->sync_mode : -1; }
 extern "C" int beep_sync(BeepBatch *bt)
 {
 	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "beep_sync": (ctypes.c_int, [_vp]),
     "beep_batch_stream": (_vp, [_vp]),
     "beep_launch_count": (ctypes.c_int64, [_vp]),
+    "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
     "beep_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _c_dp, _vp]),
     "beep_test_poisson": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_int, _vp]),
@@ -126,6 +127,10 @@ class Engine:
     @property
     def launch_count(self):
         return self.L.beep_launch_count(self.h)
+
+    @property
+    def sync_scope(self):
+        return {0: "NONE", 1: "CTA", 2: "GRID"}[self.L.beep_engine_sync_scope(self.h)]
 
 
 class Batch:

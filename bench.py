@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the batched simulate + observation-likelihood step.
+"""bench.py -- throughput of BEEP's batched latent-state hot path on B200.
 
-Metric (BASELINE.json): particle x area x age timesteps per second, i.e.
-P*A*D*T units per step divided by the step time, whole job over all ranks.
+Metric (BASELINE.json): particle x area x age timesteps per second, i.e. P*A*D*T units per step
+divided by the step time, whole job over all ranks.
 
-A step is State::simulate(theta) for a batch of P particles (reference
-src/state.cc:582-592): set_param (K0) + tau-leap over all T steps (K1/K2) +
-observation log-likelihood (K4), on the synthetic scale-up population of
-BASELINE.json configs[4] (A areas x 20 ages x 12 compartments x 365 days).
-  value  inputs (theta) resident in HBM, device-timed with CUDA events;
-  e2e    through the C-ABI with HOST buffers: theta copied in, L copied out.
-One process per GPU (torchrun for N > 1); particles are sharded across ranks
-with no data-path collective (weak scaling).
+Default workload (N = 1 and N > 1): the synthetic scale-up population of BASELINE.json configs[4]
+(10 000 areas x 20 ages x 12 compartments x 13 transitions x 365 steps; 16 particles per GPU, the
+(A, P) point on the memory frontier of SURVEY.md 8d).  A step is State::simulate(theta) for the
+batch (reference src/state.cc:582-592): set_param (K0) + tau-leap over all T steps (K1/K2) +
+observation log-likelihood (K4).
+  value  inputs (theta) resident in HBM, device-timed with CUDA events on the engine's stream;
+  e2e    through the C-ABI with HOST buffers: theta copied in, L copied out, every step.
+Other workloads (extra lines for DESIGN.md, not the driver's headline):
+  --workload england_as   the real model shape of configs[2]/[3] (1 area x 18 ages x 1050 steps,
+                          ~11.5k observations) from tests/golden/England_AS.npz, 16 384 particles;
+  --mode mbp              one model-based proposal sweep (Mbp::mbp, mbp.cc:252-330) + likelihood.
+One process per GPU (torchrun for N > 1); particles are sharded across ranks with no data-path
+collective (weak scaling).
 
-`--impl reference` times the CPU restatement of the reference algorithm
-(oracle/liboracle.so, kind "port": the reference itself builds its model from
-TOML/CSV files and cannot ingest the synthetic description) on all host cores.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/liboracle.so, kind
+"port") on all host cores: the reference itself builds its model from TOML/CSV files and cannot ingest
+the synthetic description, and /root/reference does not exist on the GPU box.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -31,7 +35,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_UNIT = 96.0     # simulate + likelihood, trajectory discarded: pop read + write, 2*C*4 B, C = 12
 METRIC = "particle*area*age timesteps/sec"
 UNIT = "particle*area*age*steps/s"
 
@@ -42,35 +45,96 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BEEP_BENCH_WORKLOAD", "synthetic"), choices=["synthetic", "england_as"])
+    ap.add_argument("--mode", default="simulate", choices=["simulate", "mbp"])
     ap.add_argument("--areas", type=int, default=int(os.environ.get("BEEP_BENCH_AREAS", 10000)))
-    ap.add_argument("--particles", type=int, default=int(os.environ.get("BEEP_BENCH_PARTICLES", 16)), help="particles per GPU")
+    ap.add_argument("--particles", type=int, default=int(os.environ.get("BEEP_BENCH_PARTICLES", 0)), help="particles per GPU (0 = workload default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--keep-traj", action="store_true", help="store transnum (MBP chain initialisation), 148 B/unit")
-    return ap.parse_args()
+    ap.add_argument("--keep-traj", action="store_true", help="store transnum (MBP chain initialisation)")
+    a = ap.parse_args()
+    if a.particles <= 0:
+        a.particles = 16 if a.workload == "synthetic" else 16384
+        if a.mode == "mbp" and a.workload == "synthetic":
+            a.particles = 4
+    return a
+
+
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+def load_workload(args, areas=None):
+    """(ModelDesc, theta_true, description)"""
+    from beep_b200.synth import make_model
+    if args.workload == "synthetic":
+        A = areas if areas is not None else args.areas
+        m, theta = make_model(A=A, G=20, T=365)
+        return m, theta
+    from beep_b200.model import ModelDesc
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "England_AS.npz")))
+    m = ModelDesc.from_prefixed(d)
+    return m, d["theta"][0]
+
+
+def particle_params(args, theta, P, seed):
+    from beep_b200.synth import jitter_params
+    if args.workload == "synthetic":
+        return jitter_params(theta, P, rel=0.05, seed=seed)
+    return np.repeat(theta[None, :], P, axis=0)          # prior-sampled vector of the fixture; bounds are model specific
+
+
+def bytes_per_unit(m, mode, keep):
+    """Algorithmic HBM bytes per (particle, area, dp, step) unit, SURVEY.md 8(d): counts int32, means FP64."""
+    C, J = m.C, m.J
+    if mode == "mbp":
+        return J * 4 + J * 8 + J * 4 + J * 8 + 2 * C * 4      # read n_i, lambda_i; write n_p, lambda_p; pop r/w
+    return 2 * C * 4 + (J * 4 if keep else 0)
+
+
+def workload_config(args, m, nparam):
+    if args.workload == "synthetic":
+        what = f"synthetic scale-up (BASELINE configs[4]): {m.A} areas x {m.D} ages x {m.C} compartments x {m.J} transitions x {m.T} steps"
+        l2 = "state per step (population tiles, > 300 MB at 10 000 areas x 16 particles) exceeds L2; no explicit flush"
+    else:
+        what = (f"England_AS model shape (BASELINE configs[2]/[3], obsmodel scale->normal 10%): {m.A} area x {m.D} ages x {m.C} compartments x "
+                f"{m.J} transitions x {m.T} steps, {m.nobs} observations")
+        l2 = "population tiles stay in shared memory for the whole trajectory; per-particle tables (> 1 GB over the batch) exceed L2"
+    step = "set_param + tau-leap simulate + obs log-likelihood" if args.mode == "simulate" else "set_param + model-based proposal sweep (Mbp::mbp) + obs log-likelihood"
+    return {"workload": f"{what}, {args.particles} particles per GPU, step = {step}" + (" (trajectory kept)" if args.keep_traj or args.mode == "mbp" else " (trajectory discarded)"),
+            "areas": int(m.A), "ages": int(m.D), "compartments": int(m.C), "transitions": int(m.J), "timesteps": int(m.T),
+            "particles_per_gpu": args.particles, "nparam": int(nparam), "mode": args.mode, "l2": l2}
 
 
 # ---------------------------------------------------------------------------
 # CPU arm (oracle port) -- also the cpu_baseline leg of the GPU arm
 # ---------------------------------------------------------------------------
-def cpu_run(steps, warmup, budget_s=12.0):
-    """Times set_param + simulate + obs log-likelihood of the oracle on every host
-    core, on a bounded sample: the same synthetic generator at A = 256 areas."""
+def cpu_run(args, steps, warmup, budget_s=12.0):
+    """Times the oracle's set_param + simulate (or mbp) + obs log-likelihood on every host core, on a
+    bounded sample of the workload (synthetic: the same generator at 256 areas; England_AS: as is)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from beep_b200.synth import make_model, jitter_params
     import oracle_lib
-    A_s = 256
-    m, theta = make_model(A=A_s, G=20, T=365)
+    m, theta = load_workload(args, areas=256)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nthread = max(1, min(cores, 64))
-    th = jitter_params(theta, nthread, rel=0.05, seed=3)
+    th = particle_params(args, theta, nthread, seed=3)
     states = [oracle_lib.OracleState(m, stochastic=1, keyed=True, imap_from_pop=True) for _ in range(nthread)]
+    props = None
+    if args.mode == "mbp":
+        props = [oracle_lib.OracleState(m, stochastic=1, keyed=True, imap_from_pop=True) for _ in range(nthread)]
+        for i in range(nthread):
+            states[i].set_param(th[i])
+            states[i].simulate(seed=1, stream_id=i)
     units_one = m.T * m.A * m.D
 
     def one(i, rep):
-        st = states[i]
-        st.set_param(th[i])
-        st.simulate(seed=1000 + rep, stream_id=i)
-        st.obs_loglik()
+        if args.mode == "mbp":
+            props[i].set_param(th[i] * (1 + 0.01 * (np.arange(th.shape[1]) % 7 == 3)))
+            props[i].mbp(states[i], None, seed=1000 + rep, stream_id=i)
+            props[i].obs_loglik()
+        else:
+            st = states[i]
+            st.set_param(th[i])
+            st.simulate(seed=1000 + rep, stream_id=i)
+            st.obs_loglik()
 
     def sweep(rep):
         ts = [threading.Thread(target=one, args=(i, rep)) for i in range(nthread)]
@@ -82,8 +146,7 @@ def cpu_run(steps, warmup, budget_s=12.0):
         return time.perf_counter() - t0
 
     t1 = sweep(0)
-    reps = max(1, int(budget_s / max(t1, 1e-3) / max(steps + warmup, 1)))
-    reps = min(reps, 8)
+    reps = max(1, min(8, int(budget_s / max(t1, 1e-3) / max(steps + warmup, 1))))
     for w in range(warmup):
         for r in range(reps):
             sweep(r)
@@ -93,34 +156,28 @@ def cpu_run(steps, warmup, budget_s=12.0):
             sweep(100 + s * reps + r)
     dt = time.perf_counter() - t0
     units = units_one * nthread * reps * steps
-    sample = (f"oracle/liboracle.so (C restatement of state.cc/obsmodel.cc), synthetic generator at A={A_s} areas x 20 ages x 365 steps, "
-              f"{nthread} threads x {reps} particles per step, set_param+simulate+obs_loglik")
+    what = "set_param+mbp+obs_loglik" if args.mode == "mbp" else "set_param+simulate+obs_loglik"
+    shape = f"synthetic generator at A={m.A} areas x {m.D} ages x {m.T} steps" if args.workload == "synthetic" else "England_AS shape"
+    sample = (f"oracle/liboracle.so (C restatement of state.cc/mbp.cc/obsmodel.cc), {shape}, {nthread} threads x {reps} particles per step, {what}")
     return units / dt, nthread, sample, dt / steps * 1e3
 
 
 def main_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    v, cores, sample, ms = cpu_run(args.steps, args.warmup)
+    v, cores, sample, ms = cpu_run(args, args.steps, args.warmup)
+    m, theta = load_workload(args, areas=256)
+    cfg = workload_config(args, m, theta.size)
+    cfg["areas"] = args.areas if args.workload == "synthetic" else int(m.A)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 0),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-
-
-def workload_config(args, nparam):
-    return {"workload": f"synthetic scale-up (BASELINE configs[4]): {args.areas} areas x 20 ages x 12 compartments x 13 transitions x 365 steps, "
-                        f"{args.particles} particles per GPU, step = set_param + tau-leap simulate + obs log-likelihood"
-                        + (" (trajectory kept)" if args.keep_traj else " (trajectory discarded)"),
-            "areas": args.areas, "ages": 20, "compartments": 12, "transitions": 13, "timesteps": 365,
-            "particles_per_gpu": args.particles, "nparam": nparam,
-            "l2": "working set (population state, > 300 MB) exceeds L2; no explicit flush"}
 
 
 # ---------------------------------------------------------------------------
@@ -179,29 +236,44 @@ def main_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from beep_b200 import engine as E
-    from beep_b200.synth import make_model, jitter_params
 
-    m, theta = make_model(A=args.areas, G=20, T=365)
+    m, theta = load_workload(args)
     eng = E.Engine(m, local)
     P = args.particles
-    flags = E.KEEP_TRANSNUM if args.keep_traj else 0
+    mbp = args.mode == "mbp"
+    keep = args.keep_traj or mbp
+    flags = (E.KEEP_TRANSNUM | E.KEEP_TRANSMEAN) if mbp else (E.KEEP_TRANSNUM if args.keep_traj else 0)
     b = eng.batch(P, flags)
-    th = jitter_params(theta, P, rel=0.05, seed=100 + rank)          # each rank owns its own particles
+    th = particle_params(args, theta, P, seed=100 + rank)          # each rank owns its own particles
     ids = (np.arange(P, dtype=np.uint64) + np.uint64(rank * P))
+    Lhost = np.zeros(P)
+    units = float(P) * m.A * m.D * m.T
+    init = None
+    if mbp:
+        # the chains' current states; the timed step proposes from them (Mbp::mbp) and evaluates the likelihood
+        init = b
+        init.set_params(th)
+        init.simulate(0, m.T, seed=1, stream_ids=ids)
+        b = eng.batch(P, flags)
+        th = th * (1 + 0.01 * (np.arange(th.shape[1]) % 7 == 3))
     th_dev = torch.from_numpy(th).cuda()
     th_pin = torch.from_numpy(th).pin_memory()
-    Lhost = np.zeros(P)
     stream = torch.cuda.ExternalStream(b.stream, device=torch.device("cuda", local))
-    units = float(P) * m.A * m.D * m.T
 
     def step_dev(i):
         b.set_params_dev(th_dev.data_ptr())
-        b.simulate(seed=7 + i, stream_ids=None)
+        if mbp:
+            b.mbp(init, None, seed=7 + i)
+        else:
+            b.simulate(seed=7 + i)
         E._check(b.L.beep_obs_loglik_dev(b.h, -1, None, None))
 
     def step_e2e(i):
         E._check(b.L.beep_set_params(b.h, th_pin.data_ptr()))
-        b.simulate(seed=7 + i)
+        if mbp:
+            b.mbp(init, None, seed=7 + i)
+        else:
+            b.simulate(seed=7 + i)
         E._check(b.L.beep_obs_loglik(b.h, -1, Lhost.ctypes.data, None))
 
     def barrier():
@@ -210,7 +282,10 @@ def main_gpu(args):
         torch.cuda.synchronize()
 
     b.set_params_dev(th_dev.data_ptr())
-    b.simulate(0, m.T, seed=1, stream_ids=ids)       # installs the stream ids; first warm-up
+    if mbp:
+        b.mbp(init, None, seed=1, stream_ids=ids)
+    else:
+        b.simulate(0, m.T, seed=1, stream_ids=ids)       # installs the stream ids; first warm-up
     b.sync()
 
     def timed(fn, steps, warmup):
@@ -234,7 +309,7 @@ def main_gpu(args):
 
     clocks = Clocks(local) if rank == 0 else None
     ms_dev, launches = timed(step_dev, args.steps, args.warmup)
-    # the dominant kernel's own duration (CUDA events around the k_traj launch on the batch stream)
+    # the dominant kernel's own duration (CUDA events around the k_traj launch on the batch's stream)
     traj_ms = []
     for i in range(max(args.steps, 1)):
         step_dev(1000 + i)
@@ -257,30 +332,33 @@ def main_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    bpu = 148.0 if args.keep_traj else BYTES_PER_UNIT
+    bpu = float(bytes_per_unit(m, args.mode, keep))
     kms = float(np.mean(traj_ms))
     achieved = units * bpu / (kms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload == "synthetic" and args.mode == "simulate":
         try:
-            traffic = json.load(open(tpath)).get("k_traj_dram_bytes_per_launch")
+            t = json.load(open(tpath))
+            # DRAM bytes of one k_traj launch measured by ncu --set full at P = t["particles"]; per launch it scales with P
+            traffic = t["k_traj_dram_bytes_per_launch"] * (P * m.A) / float(t["particles"] * t["areas"])
         except Exception:
             traffic = None
-
+    sync = eng.sync_scope
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, m.nparam),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, m, m.nparam),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(th.nbytes), "d2h_bytes_per_step": int(Lhost.nbytes),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_traj<SIM,GRID>", "kernel_ms": kms, "bytes_per_unit": bpu, "units_per_launch": units, "peak_source": peak_src},
+                     "kernel": f"k_traj<{'MBP' if mbp else 'SIM'},{sync}>", "kernel_ms": kms, "bytes_per_unit": bpu, "units_per_launch": units,
+                     "peak_source": peak_src},
         "clocks": clk,
     }
     if not args.no_cpu:
-        v, cores, sample, _ = cpu_run(2, 1, budget_s=10.0)
+        v, cores, sample, _ = cpu_run(args, 2, 1, budget_s=10.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
     if dist is not None:

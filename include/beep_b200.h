@@ -188,6 +188,9 @@ int beep_set_pop_all(BeepBatch *batch, const double *pop_host, int cur_step);
 int beep_sync(BeepBatch *batch);
 /* the batch's cudaStream_t, for callers that time or enqueue on it          */
 void *beep_batch_stream(BeepBatch *batch);
+/* scope of the per-step barrier the trajectory kernel uses for this model:
+ * 0 = none (areas uncoupled), 1 = CTA (a CTA owns a particle), 2 = cooperative grid */
+int beep_engine_sync_scope(const BeepEngine *eng);
 /* number of engine kernel launches since creation (bench accounting)        */
 int64_t beep_launch_count(const BeepEngine *eng);
 /* last kernel-only duration of beep_simulate in ms (CUDA events on the

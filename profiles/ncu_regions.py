@@ -23,9 +23,9 @@ def find(pat):
     for i, l in enumerate(lines):
         if pat in l: return i + 1
     return None
-marks = [("tile_dinf", "__device__ __forceinline__ bool tile_dinf"), ("(structs)", "/* per-warp scratch, all in shared"), ("pool+setup", "template <int MODE>\n"),
+marks = [("tile_dinf", "tile_dinf(const DevModel &m, const double *infco"), ("(structs)", "/* per-warp scratch, all in shared"), ("pool+setup", "template <int MODE>\n"),
          ("FOI", "/* 1. state.cc:547-578"), ("scan", "/* 2. scan:"), ("draw", "/* 3. draws on the dense"), ("trmask", "/* transitions with events, warp-wide"),
-         ("obs", "/* 4a. obsmodel"), ("keep_pop", "if (b.flags & BEEP_KEEP_POP) {"), ("update", "/* 4b. state.cc:460-485"), ("kernel", "/* CTA-shared table"), ("end", "/* K4  observation model")]
+         ("obs", "/* 4a. obsmodel"), ("keep_pop", "(b.flags & BEEP_KEEP_POP)) {"), ("update", "/* 4b. state.cc:460-485"), ("kernel", "/* CTA-shared tables at the front"), ("end", "/* K4  observation model")]
 pos = []
 for name, pat in marks:
     ln = find(pat.split("\n")[0]) if name != "pool+setup" else find("__device__ __forceinline__ unsigned tile_step")
