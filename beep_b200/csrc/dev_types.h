@@ -13,6 +13,7 @@
  *   betaR                [P][S][nR][T]         State::beta per R-spline group (areas of
  *                                              one group share the series, model.cc:1343)
  *   infco                [P][C]                infectivity of each compartment
+ *   etab                 [P][nefoi][T]         external force of infection per individual
  *   pop_cur              [P][A][CDp]           population [C][D] at the batch's current step,
  *                                              tile stride padded to an even count
  *   dinf                 [2][P][S][A][G]       infectivity by (area, age), double buffered
@@ -31,6 +32,50 @@
 #include <stdint.h>
 
 struct ObsEnt { int ob; int slot; };
+
+/* per-area constants of the mixing matrix, one 32-byte record (two 16-byte loads) */
+struct alignas(16) AreaInfo { double diag, fac; int j0, nn, rg, ie0; };   /* ie0 = efoi_ref of strain 0 */
+/* one entry of the transposed mixing matrix: weight and the source area's offset into a dinf plane */
+struct alignas(16) Nbr { double val; unsigned off; int pad; };   /* off in BYTES: source area * G * 8 */
+
+#define BEEP_EVEN(x) (((x) + 1) & ~1)
+
+/* Shared-memory layout of the trajectory kernel, in doubles (every block even so that 16-byte
+ * accesses stay aligned); computed identically by the launcher and by the kernel.
+ *   CTA common : N0R[G][Gs] age matrix rows, stride Gs even with Gs/2 odd (conflict-free 16-byte row reads)
+ *                ctab[J*D]  packed cell table (u32)
+ *   per warp   : ns[JD] ae[JD u16] foi[D] Iv[Gs] nbr[32 Nbr] nmi[G]      (work area)
+ *   SYNC_NONE, per warp: pop[CDp] W dinf[2][S*G]
+ *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: W
+ *   SYNC_GRID, per warp: pop[BEEP_TRAJ_NBUF][CDp] W     (2 = cp.async double buffer: tile k+1 streams
+ *                                                        in while tile k computes; 1 = more warps per SM) */
+#ifndef BEEP_TRAJ_NBUF
+#define BEEP_TRAJ_NBUF 1
+#endif
+#ifndef BEEP_TRAJ_MINB
+#define BEEP_TRAJ_MINB 4
+#endif
+struct TrajSm { int Gs, n0, ctab, common, JDe, ns, ae, foi, nmi, iv, nbr, work; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline TrajSm traj_sm_layout(int G, int J, int D)
+{
+	TrajSm L;
+	int gs = BEEP_EVEN(G);
+	if (((gs >> 1) & 1) == 0) gs += 2;
+	L.Gs = gs;
+	L.n0 = 0; L.ctab = BEEP_EVEN(G * gs);
+	L.common = L.ctab + BEEP_EVEN((J * D + 1) >> 1);
+	L.JDe = BEEP_EVEN(J * D);
+	L.ns = 0; L.ae = L.JDe;
+	L.foi = L.ae + BEEP_EVEN((L.JDe + 3) >> 2);
+	L.iv = L.foi + BEEP_EVEN(D);
+	L.nbr = L.iv + gs;
+	L.nmi = L.nbr + 64;
+	L.work = L.nmi + BEEP_EVEN(G);
+	return L;
+}
 
 struct DevModel {
 	int T, period, spu, A, C, J, D, G, S, Dq, nparam, nspline, nobs, ntable;
@@ -52,6 +97,8 @@ struct DevModel {
 	const int *R_spline_ref, *area_rgrp; const double *R_dist; const int *strain_Rfactor_param;
 	const int *efoi_spline_ref, *efoi_ref; const double *efoi_agedist;
 	const int *Min_off, *Min_src; const double *Min_val; const double *M_diag, *M_factor;
+	const AreaInfo *area_info;  /* [A] */
+	const Nbr *nbr;             /* [nnz] transposed mixing matrix, sources ascending per destination */
 	const double *pop_init;
 	const double *obs_value, *obs_sd, *obs_factor, *obs_shape;
 	const int *obs_fs, *obs_table, *obs_model, *obs_section, *obs_slot_off;
@@ -65,6 +112,9 @@ struct DevModel {
 struct DevBatch {
 	int P; unsigned flags;
 	double *theta, *pd, *transrate, *disc_spline, *sus, *areafactor, *betaR, *infco;
+	double *etab;                  /* [P][nefoi][T] external force of infection per individual, spline / popsize */
+	int *inflist;                  /* [P][C+1] count, then the compartments with non-zero infectivity (ascending) */
+	int *sched;                    /* [T] tile counters of the grid-synchronised kernel (dynamic tile scheduling) */
 	double *pop_cur, *dinf;
 	double *scratchA;              /* [P][A] K0 scratch (per-area averages) */
 	int *tn; double *tm; double *poptraj;
@@ -84,6 +134,9 @@ struct TrajArgs {
 	/* MBP: the coupled initial state (same slot of the `init` batch) */
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
 	int nwarp;          /* warps per CTA */
+	int chunk;          /* SYNC_GRID: tiles a warp takes per grab of the step's tile counter */
+	float invA;         /* 1/A: tile index -> (particle, area) without an integer division */
+	TrajSm L;           /* shared-memory layout (traj_sm_layout), computed once by the launcher */
 	unsigned char tfrom[32], tto[32], tkind[32];   /* per transition: source, target, kind (0 ordinary, 1 infection, 2 never) */
 };
 

@@ -40,7 +40,7 @@ struct BeepEngine {
 	int device = 0, nsm = 0, smem_optin = 0;
 	DevModel dm;
 	std::vector<void *> dev_allocs;
-	std::vector<int> section_ti, section_tf;
+	std::vector<int> section_ti, section_tf, h_rgrp;
 	unsigned char h_from[32] = {0}, h_to[32] = {0}, h_kind[32] = {0};
 	long long launches = 0;
 	int sync_mode = SYNC_NONE, nwarp = 4;
@@ -180,6 +180,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		for (int i = 0; i < m.nR; i++) for (int k = d->R_area_off[i]; k < d->R_area_off[i + 1]; k++) { NEED(d->R_area[k] >= 0 && d->R_area[k] < A, "R_area out of range"); rg[d->R_area[k]] = i; }
 		for (int c = 0; c < A; c++) NEED(rg[c] >= 0, "area %d belongs to no R spline", c);
 		UPV(area_rgrp, rg);
+		eng->h_rgrp = rg;
 	}
 	UP(efoi_spline_ref, d->efoi_spline_ref, m.nefoi); UP(efoi_ref, d->efoi_ref, S * A); UP(efoi_agedist, d->efoi_agedist, d->n_efoi_agedist);
 	{
@@ -195,6 +196,17 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		for (int c = 0; c < A; c++) for (int k = d->M_off[c]; k < d->M_off[c + 1]; k++) { int to = d->M_to[k]; src[fill[to]] = c; val[fill[to]] = d->M_val[k]; fill[to]++; }
 		UPV(Min_off, off); UPV(Min_src, src); UPV(Min_val, val);
 		m.M_nnz = nnz;
+		/* the same matrix as the kernel reads it: 16-byte (weight, source offset) entries and one
+		 * 32-byte record of per-area constants */
+		std::vector<Nbr> nb((size_t)nnz);
+		for (int k = 0; k < nnz; k++) { nb[k].val = val[k]; nb[k].off = (unsigned)src[k] * (unsigned)G * 8u; nb[k].pad = 0; }
+		std::vector<AreaInfo> ai((size_t)A);
+		for (int c = 0; c < A; c++) {
+			NEED(d->efoi_ref[c] >= 0 && d->efoi_ref[c] < m.nefoi, "efoi_ref out of range");
+			ai[c].diag = d->M_diag[c]; ai[c].fac = d->M_factor[c]; ai[c].j0 = off[c]; ai[c].nn = off[c + 1] - off[c];
+			ai[c].rg = eng->h_rgrp[c]; ai[c].ie0 = d->efoi_ref[c];
+		}
+		UPV(nbr, nb); UPV(area_info, ai);
 	}
 	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
 	UP(pop_init, d->pop_init, (size_t)A * C * D);
@@ -300,10 +312,9 @@ static size_t even(size_t x) { return (x + 1) & ~(size_t)1; }
 static int choose_launch(BeepEngine *eng)
 {
 	const DevModel &m = eng->dm;
-	const size_t CDp = (size_t)m.CDp, JD = even((size_t)m.J * m.D), De = even(m.D), Ge = even(m.G);
-	const size_t common = even((size_t)m.G * m.G) + even(((size_t)m.J * m.D + 1) / 2);
+	const TrajSm L = traj_sm_layout(m.G, m.J, m.D);      /* the kernel computes the same layout */
+	const size_t CDp = (size_t)m.CDp, common = (size_t)L.common, work = (size_t)L.work;
 	const char *force = getenv("BEEP_FORCE_SYNC");      /* tests: exercise every flavour on small models */
-	const size_t work = 2 * JD + even((JD + 3) / 4) + De + 2 * Ge;     /* WORK_DOUBLES of kernels.cuh */
 	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * work) * sizeof(double); };
 	if (m.M_nnz == 0) {
 		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
@@ -320,9 +331,9 @@ static int choose_launch(BeepEngine *eng)
 	}
 	if (eng->sync_mode == SYNC_GRID) {
 		eng->nwarp = 8;
-		eng->smem_traj = (common + eng->nwarp * (2 * CDp + work)) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (BEEP_TRAJ_NBUF * CDp + work)) * sizeof(double);
 	}
-	if ((long long)m.A * 1 > (1ll << 30)) return fail(BEEP_ERR_UNSUPPORTED, "too many areas");
+	if ((long long)m.A * m.G >= (1ll << 28)) return fail(BEEP_ERR_UNSUPPORTED, "too many areas (A*G must be below 2^28)");
 	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
 	for (int mode = 0; mode < 3; mode++) for (int keep = 0; keep < 2; keep++) {
 		const void *fn = traj_fn(mode, eng->sync_mode, keep != 0);
@@ -376,7 +387,7 @@ extern "C" void beep_batch_destroy(BeepBatch *bt)
 extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBatch **out)
 {
 	if (!eng || !out || P <= 0) return fail(BEEP_ERR_INVALID, "bad argument to beep_batch_create");
-	if ((long long)P * eng->dm.A >= (1ll << 31)) return fail(BEEP_ERR_UNSUPPORTED, "P*A must be below 2^31 tiles");
+	if ((long long)P * eng->dm.A >= (1ll << 30) || P >= (1 << 22)) return fail(BEEP_ERR_UNSUPPORTED, "P*A must be below 2^30 tiles and P below 2^22");
 	*out = nullptr;
 	CU(cudaSetDevice(eng->device));
 	BeepBatch *bt = new BeepBatch();
@@ -400,6 +411,8 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
 	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
 	BA(b.stream_id, P); BA(b.infmask, P);
+	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
+	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)m.T);
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(K5_CHUNKS, (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
@@ -489,7 +502,8 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	TrajArgs a;
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
-	a.nwarp = eng->nwarp;
+	a.nwarp = eng->nwarp; a.chunk = 1;
+	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D);
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;
 	if (ti == 0) {
@@ -513,6 +527,11 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	} else {
 		long long ntile = (long long)P * m.A;
 		int grid = (int)std::min<long long>(eng->coop_grid, (ntile + eng->nwarp - 1) / eng->nwarp);
+		/* dynamic tile scheduling: about 32 grabs per warp and step, at most 8 tiles per grab */
+		const long long nw = (long long)grid * eng->nwarp;
+		a.chunk = (int)std::max<long long>(1, std::min<long long>(8, ntile / (nw * 32)));
+		if (const char *ch = getenv("BEEP_TRAJ_CHUNK")) a.chunk = std::max(1, atoi(ch));
+		CU(cudaMemsetAsync(bt->db.sched, 0, (size_t)m.T * sizeof(int), bt->stream));
 		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
 	}
 	eng->launches++;
@@ -698,6 +717,8 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	if ((rc = gather_inplace(bt, b.betaR, (size_t)m.S * m.nR * m.T, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.infco, m.C, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.infmask, 1, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.etab, (size_t)m.nefoi * m.T, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.inflist, (size_t)m.C + 1, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.poptraj, (size_t)m.T * m.A * m.C * m.D, bt->d_map))) return rc;
@@ -738,6 +759,8 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if ((rc = copy_flagged(init, a.betaR, b.betaR, (size_t)m.S * m.nR * m.T))) return rc;
 	if ((rc = copy_flagged(init, a.infco, b.infco, m.C))) return rc;
 	if ((rc = copy_flagged(init, a.infmask, b.infmask, 1))) return rc;
+	if ((rc = copy_flagged(init, a.etab, b.etab, (size_t)m.nefoi * m.T))) return rc;
+	if ((rc = copy_flagged(init, a.inflist, b.inflist, (size_t)m.C + 1))) return rc;
 	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.CDp))) return rc;
 	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.tm, b.tm, TAJD))) return rc;

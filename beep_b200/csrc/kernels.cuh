@@ -105,6 +105,11 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		unsigned long long mk = 0;
 		for (int tr = 0; tr < J; tr++) if (pd[m.comp_inf_param[m.trans_from[tr]]] != 0 || pd[m.comp_inf_param[m.trans_to[tr]]] != 0) mk |= 1ull << tr;
 		b.infmask[p] = mk;
+		/* the infectious compartments, ascending (the order state.cc:223-264 visits them in) */
+		int *il = b.inflist + (size_t)p * (m.C + 1);
+		int n = 0;
+		for (int co = 0; co < m.C; co++) if (pd[m.comp_inf_param[co]] != 0) il[1 + n++] = co;
+		il[0] = n;
 	}
 	/* model.cc:1020-1043 create_disc_spline: one thread walks one spline */
 	for (int sp = tid; sp < m.nspline; sp += nth) {
@@ -127,6 +132,11 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		}
 	}
 	__syncthreads();
+	/* external force of infection per individual (state.cc:423): spline value / population size */
+	{
+		double *etab = b.etab + (size_t)p * m.nefoi * T;
+		for (int i = tid; i < m.nefoi * T; i += nth) { const int ie = i / T, t = i - ie * T; etab[i] = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize; }
+	}
 
 	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix NGM = F V^-1
 	 * (model.cc:2485-2576): V is block diagonal in dp, so only column (state 0, dp = i) of the
@@ -327,66 +337,77 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-/* per-warp scratch, all in shared memory */
+/* per-warp scratch, all in shared memory (layout: traj_sm_layout, dev_types.h) */
 struct TileSm {
 	double *pop;      /* [CDp] population of the tile                                   */
-	double *ns;       /* [J*D] event counts of this step; ALL ZERO between tile steps   */
+	double *ns;       /* [J*D] per cell: the mean of an active cell between scan and draw, then the
+	                     event count of this step; ALL ZERO between tile steps          */
 	double *foi;      /* [D]   force of infection per dp (state.cc:428)                */
 	double *nmi;      /* [G]   NMI per age (state.cc:547-578)                           */
-	double *Iv;       /* [G]   infectivity vector before the age matvec                */
-	double *am;       /* [J*D] means of the active cells, compacted                    */
+	double *Iv;       /* [Gs]  infectivity vector before the age matvec, zero padded   */
 	unsigned short *ae; /* [J*D] cell index of the active cells, compacted             */
-	const double *N0T;     /* [G*G] transposed base age matrix (CTA shared)             */
+	Nbr *nbr;         /* [32]  staged entries of the transposed mixing matrix          */
+	const double *N0R;     /* [G][Gs] base age matrix, padded rows (CTA shared)         */
 	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)                      */
-	const double *infco;   /* [C] infectivity per compartment of the CTA's ... (global)  */
+	int Gs;
 };
 
-/* what a warp needs to know about the tile it works on (all warp-uniform) */
+/* what a warp needs to know about the tile it works on (all warp-uniform): the particle
+ * part changes only when the warp moves to another particle, the area part per tile */
 struct TileCtx {
 	int p, c;
-	const double *rate, *ds, *sus, *infco, *af, *betaR;
+	const double *rate, *ds, *sus, *infco, *af, *betaR, *etab;
+	const int *il;
 	double *partial;
 	unsigned long long sid;
 	unsigned infmask;
 	double diag, fac;
-	int j0, j1, rg;
+	int j0, nn, rg, ie0;
 };
 
-__device__ __forceinline__ void tile_ctx(const TrajArgs &a, int p, int c, TileCtx &tc)
+__device__ __forceinline__ void tile_ctx_particle(const TrajArgs &a, int p, TileCtx &tc)
 {
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
-	tc.p = p; tc.c = c;
+	tc.p = p;
 	tc.rate = b.transrate + (size_t)p * (m.J * m.D);
 	tc.ds = b.disc_spline + (size_t)p * (m.nspline * m.T);
 	tc.sus = b.sus + (size_t)p * m.D;
 	tc.infco = b.infco + (size_t)p * m.C;
-	tc.af = b.areafactor + (size_t)p * m.period * m.A + c;
+	tc.il = b.inflist + (size_t)p * (m.C + 1);
+	tc.af = b.areafactor + (size_t)p * m.period * m.A;
 	tc.betaR = b.betaR + (size_t)p * (m.S * m.nR * m.T);
+	tc.etab = b.etab + (size_t)p * (m.nefoi * m.T);
 	tc.partial = b.obs_partial + (size_t)p * m.nslot;
 	tc.sid = b.stream_id[p];
 	tc.infmask = (unsigned)b.infmask[p];
-	tc.diag = m.M_diag[c]; tc.fac = m.M_factor[c];
-	tc.j0 = m.Min_off[c]; tc.j1 = m.Min_off[c + 1];
-	tc.rg = m.area_rgrp[c];
+}
+__device__ __forceinline__ void tile_ctx_area(const AreaInfo &ai, int c, TileCtx &tc)
+{
+	tc.c = c;
+	tc.diag = ai.diag; tc.fac = ai.fac; tc.j0 = ai.j0; tc.nn = ai.nn; tc.rg = ai.rg; tc.ie0 = ai.ie0;
 }
 
 /* dinf[st][a] of one tile from its population (state.cc:223-264): infectivity-weighted
- * number of individuals by strain and age, summed in the oracle's (co, dp) order */
-__device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco, const double *pop, double *out, int ostride, int lane)
+ * number of individuals by strain and age, summed in the oracle's (co, dp) order over the
+ * particle's infectious compartments (adding the exact zeros of empty cells, which the
+ * reference skips, leaves every partial sum unchanged) */
+__device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco, const int *il, const double *pop, double *out, int ostride, int lane)
 {
-	const int G = m.G, Dq = m.Dq, D = m.D, C = m.C;
+	const int G = m.G, Dq = m.Dq, D = m.D;
+	const int ninf = il[0];
 	for (int st = 0; st < m.S; st++) {
 		if (lane < G) {
 			double sum = 0;
-			for (int co = 0; co < C; co++) {
+			for (int k = 1; k <= ninf; k++) {
+				const int co = il[k];
 				const double inf = infco[co];
-				if (inf != 0) {
-					if (m.age_fast) {
-						for (int dp = lane; dp < Dq; dp += G) { const double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
-					} else {
-						for (int dp = 0; dp < Dq; dp++) if (m.dp_age[dp] == lane) { const double pp = pop[co * D + st * Dq + dp]; if (pp != 0) sum += inf * pp; }
-					}
+				const double *pc = pop + co * D + st * Dq;
+				if (m.age_fast) {
+					for (int dp = lane; dp < Dq; dp += G) sum += inf * pc[dp];
+				} else {
+#pragma unroll 1
+					for (int dp = 0; dp < Dq; dp++) if (m.dp_age[dp] == lane) sum += inf * pc[dp];
 				}
 			}
 			out[st * ostride + lane] = sum;
@@ -403,7 +424,7 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
  *   4. observations, population update and infectivity, visiting only the
  *      transitions that had events.
  * KEEP = false compiles out every trajectory store (ABC-SMC / particle-filter use). */
-template <int MODE, bool KEEP>
+template <int MODE, bool KEEP, bool LATEWAIT>
 __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &tc, const int t, const int tday, const int lane, const TileSm &sm,
                                               const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
 {
@@ -414,11 +435,16 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 	double *pop = sm.pop, *ns = sm.ns, *foi = sm.foi, *nmi = sm.nmi;
 	const double *ds = tc.ds;
 
+	/* LATEWAIT: the tile's population is still streaming into shared memory (cp.async); the force of
+	 * infection does not read it, so the copy is awaited only after that phase */
+	if (LATEWAIT && S > 1) { cp_async_wait<0>(); __syncwarp(); }
 	/* state.cc:395-404: with several strains the susceptible pool lives in strain 0 */
 	if (S > 1) {
 		const int sfrom = a.tfrom[m.itr];
+#pragma unroll 1
 		for (int dp = lane; dp < Dq; dp += 32) {
 			double sum = 0;
+#pragma unroll 1
 			for (int st = 1; st < S; st++) { sum += pop[sfrom * D + Dq * st + dp]; pop[sfrom * D + Dq * st + dp] = 0; }
 			pop[sfrom * D + dp] += sum;
 		}
@@ -428,64 +454,79 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 	/* 1. state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
 	{
 		const double d = ds[m.geo_spline * T + t], omd = 1 - d;
-		const double afv = tc.af[(size_t)tday * A];
-		const int nn = tc.j1 - tc.j0;
-		/* lanes fetch the (source, weight) pairs of up to 32 neighbours once; they are broadcast below */
-		int nsrc = 0; double nval = 0;
-		if (lane < nn) { nsrc = m.Min_src[tc.j0 + lane]; nval = m.Min_val[tc.j0 + lane]; }
+		const double afv = tc.af[(size_t)tday * A + tc.c];
+		const int ll = lane < G ? lane : G - 1;        /* idle lanes repeat the last age: every load stays in range */
+		const bool fastdp = m.age_fast && Dq == G;     /* dp == age: the force of infection needs no NMI round trip */
+		bool staged = false;
 		for (int st = 0; st < S; st++) {
 			const double *dc = dinf_cur + (size_t)st * Ad * G;
+			const char *dcl = (const char *)(dc + ll);
+			/* Imap of this area (state.cc:204-216 transposed): the entries of the area's column of M are
+			 * staged through shared memory, 32 at a time, and read back as one 16-byte broadcast each;
+			 * sources ascending = the reference's accumulation order */
 			double Imap = 0;
-			const int nn32 = nn < 32 ? nn : 32;
-			for (int j = 0; j < nn32; j++) {
-				const int src = __shfl_sync(FULLMASK, nsrc, j);
-				const double val = __shfl_sync(FULLMASK, nval, j);
-				if (lane < G) { const double di = dc[src * G + lane]; if (di != 0) Imap += di * val; }
-			}
-			if (lane < G) for (int j = tc.j0 + 32; j < tc.j1; j++) { const double di = dc[m.Min_src[j] * G + lane]; if (di != 0) Imap += di * m.Min_val[j]; }
-			double Iv = 0;
-			bool live = false;
-			if (lane < G) {
-				const double Idiag = dc[ci * G + lane] * tc.diag;
-				if (G == 1) {
-					double val = Idiag * (d + tc.fac * omd) + Imap * d;
-					if (val < 0) val = 0;
-					nmi[0] = val;
-				} else {
-					Iv = (Idiag + Imap) * d + tc.fac * Idiag * omd;
-					live = (Iv != 0);
+			for (int jb = 0; jb < tc.nn; jb += 32) {
+				const int cnt = (tc.nn - jb < 32) ? tc.nn - jb : 32;
+				if (!staged) {
+					__syncwarp();
+					if (lane < cnt) sm.nbr[lane] = m.nbr[tc.j0 + jb + lane];
+					__syncwarp();
+					staged = (tc.nn <= 32);
+				}
+#pragma unroll 2
+				for (int j = 0; j < cnt; j++) {
+					const double2 raw = ((const double2 *)sm.nbr)[j];            /* one 16-byte broadcast: (weight, byte offset) */
+					Imap += *(const double *)(dcl + (unsigned)__double2loint(raw.y)) * raw.x;
 				}
 			}
-			if (G > 1) {
+			const double Idiag = dc[ci * G + ll] * tc.diag;
+			double nv = 0;                                 /* NMI of age `lane` */
+			if (G == 1) {
+				nv = Idiag * (d + tc.fac * omd) + Imap * d;
+				if (nv < 0) nv = 0;
+			} else {
+				const double Iv = (Idiag + Imap) * d + tc.fac * Idiag * omd;
 				/* a neighbourhood without infectious individuals has I = 0, hence NMI = 0 exactly */
-				if (__any_sync(FULLMASK, live)) {
+				if (__any_sync(FULLMASK, Iv != 0)) {
 					if (lane < G) sm.Iv[lane] = Iv;
 					__syncwarp();
 					if (lane < G) {
 						double sum = 0;
 						if (m.nmm == 0) {
-#pragma unroll 4
-							for (int aa = 0; aa < G; aa++) sum += sm.N0T[aa * G + lane] * sm.Iv[aa];
+							const double2 *row = (const double2 *)(sm.N0R + lane * sm.Gs);
+							const double2 *iv2 = (const double2 *)sm.Iv;
+							const int h = sm.Gs >> 1;
+#pragma unroll 2
+							for (int k = 0; k < h; k++) { const double2 n2 = row[k], v2 = iv2[k]; sum += n2.x * v2.x; sum += n2.y * v2.y; }
 						} else {
-							for (int aa = 0; aa < G; aa++) sum += ntime_elem(m, ds, t, lane, aa, sm.N0T[aa * G + lane]) * sm.Iv[aa];
+#pragma unroll 1
+							for (int aa = 0; aa < G; aa++) sum += ntime_elem(m, ds, t, lane, aa, sm.N0R[lane * sm.Gs + aa]) * sm.Iv[aa];
 						}
 						if (sum < 0) sum = 0;
-						nmi[lane] = sum;
+						nv = sum;
 					}
-				} else if (lane < G) nmi[lane] = 0;
+				}
 			}
-			__syncwarp();
 			double be = tc.betaR[(st * m.nR + tc.rg) * T + t];
 			be *= afv;
-			const int ie = m.efoi_ref[st * A + tc.c];
-			const double et = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize;
-			for (int dp = lane; dp < Dq; dp += 32) {
-				const int ag = m.dp_age[dp];
-				foi[st * Dq + dp] = be * nmi[ag] + et * m.efoi_agedist[ie * G + ag];
+			const int ie = (st == 0) ? tc.ie0 : m.efoi_ref[st * A + tc.c];
+			const double et = tc.etab[ie * T + t];
+			if (fastdp) {
+				if (lane < G) foi[st * Dq + lane] = be * nv + et * m.efoi_agedist[ie * G + lane];
+			} else {
+				if (lane < G) nmi[lane] = nv;
+				__syncwarp();
+#pragma unroll 1
+				for (int dp = lane; dp < Dq; dp += 32) {
+					const int ag = m.dp_age[dp];
+					foi[st * Dq + dp] = be * nmi[ag] + et * m.efoi_agedist[ie * G + ag];
+				}
 			}
 			__syncwarp();
 		}
 	}
+
+	if (LATEWAIT && S == 1) { cp_async_wait<0>(); __syncwarp(); }
 
 	/* 2. scan: transition means (state.cc:434-444); compact the cells that can have events */
 	const size_t tbase = KEEP ? (((size_t)tc.p * T + t) * A + tc.c) * (size_t)JD : 0;
@@ -495,6 +536,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 	const double dt = m.dt;
 	int nact = 0;
 	unsigned trbits = 0;
+#pragma unroll 2
 	for (int e0 = 0; e0 < JD; e0 += 32) {
 		const int e = e0 + lane;
 		double mean = 0.0;
@@ -503,9 +545,10 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 		if (e < JD) {
 			w = sm.ctab[e];
 			const double popu = pop[w & 0xfffu];
+			const double r = tc.rate[e];
 			if (popu > 0) {
 				const unsigned kind = w >> 24;
-				if (kind == 0) mean = dt * popu * tc.rate[e];
+				if (kind == 0) mean = dt * popu * r;
 				else if (kind == 1) { const int dp = (w >> 18) & 63; mean = dt * popu * tc.sus[dp] * foi[dp]; }
 			}
 			if (MODE == MODE_REPLAY) {
@@ -524,7 +567,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 		}
 		if (MODE != MODE_REPLAY) {
 			const unsigned bal = __ballot_sync(FULLMASK, act);
-			if (act) { const int q = nact + __popc(bal & lt); sm.ae[q] = (unsigned short)e; sm.am[q] = mean; }
+			if (act) { sm.ae[nact + __popc(bal & lt)] = (unsigned short)e; ns[e] = mean; }
 			nact += __popc(bal);
 		}
 	}
@@ -537,7 +580,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)tc.p * T + t) * A + tc.c];
 		for (int i = lane; i < nact; i += 32) {
 			const int e = sm.ae[i];
-			const double mean = sm.am[i];
+			const double mean = ns[e];
 			BeepStream rs;
 			beep_stream_init_cell(&rs, a.seed, tc.sid, cell0 + e);
 			int num;
@@ -554,7 +597,8 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 					else num = beep_binomial(&rs, mean / rate_i, num_i);
 				}
 			}
-			if (num != 0) { ns[e] = (double)num; trbits |= 1u << ((sm.ctab[e] >> 12) & 63); }
+			ns[e] = (double)num;                            /* replaces the mean: zero again unless there were events */
+			if (num != 0) trbits |= 1u << ((sm.ctab[e] >> 12) & 63);
 			if (keep_tn) b.tn[tbase + e] = num;
 		}
 	}
@@ -653,44 +697,45 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 		}
 		__syncwarp();
 		if (apply) {
-			if (trmask & tc.infmask) tile_dinf(m, tc.infco, pop, dinf_nxt + ci * G, Ad * G, lane);
-			else if (lane < G) for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
+			if (trmask & tc.infmask) tile_dinf(m, tc.infco, tc.il, pop, dinf_nxt + ci * G, Ad * G, lane);
+			else if (lane < G)
+#pragma unroll 1
+				for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
 		}
 	}
 	__syncwarp();
 	return apply ? trmask : 0u;
 }
 
-/* CTA-shared tables at the front of dynamic shared memory (doubles): N0T[G*G, even] ctab[J*D/2, even] */
-__device__ __forceinline__ double *sm_common_init(const DevModel &m, double *smem, TileSm &ts)
+/* tile index -> (particle, area): float reciprocal estimate (particle < 2^23) corrected by one */
+__device__ __forceinline__ void tile_split(int tile, int A, float invA, int &p, int &c)
 {
-	const int n0 = (m.G * m.G + 1) & ~1, ct = (((m.J * m.D + 1) >> 1) + 1) & ~1;
-	double *N0T = smem;
-	unsigned *ctab = (unsigned *)(smem + n0);
-	for (int i = threadIdx.x; i < m.G * m.G; i += blockDim.x) N0T[i] = m.N0T[i];
-	for (int i = threadIdx.x; i < m.J * m.D; i += blockDim.x) ctab[i] = m.cell_tab[i];
-	ts.N0T = N0T; ts.ctab = ctab;
-	return smem + n0 + ct;
+	p = (int)((float)tile * invA);
+	c = tile - p * A;
+	if (c < 0) { p--; c += A; }
+	else if (c >= A) { p++; c -= A; }
 }
-#define EVEN(x) (((x) + 1) & ~1)
 
-/* Shared memory after the common tables (doubles, every block even so that 16-byte copies stay aligned):
- *   W = ns[JD] am[JD] ae[JD/4] foi[D] nmi[G] Iv[G]      (per-warp work area)
- *   SYNC_NONE, per warp: pop[CDp] W dinf[2][S*G]
- *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: W
- *   SYNC_GRID, per warp: pop[2][CDp] W                  (pop double-buffered by cp.async) */
-#define WORK_DOUBLES(JD, De, Ge) (2 * (JD) + EVEN(((JD) + 3) / 4) + (De) + 2 * (Ge))
-__device__ __forceinline__ void work_init(TileSm &ts, double *w, int JD, int De, int Ge, int lane)
+/* CTA-shared tables at the front of dynamic shared memory */
+__device__ __forceinline__ double *sm_common_init(const DevModel &m, const TrajSm &L, double *smem, TileSm &ts)
 {
-	ts.ns = w; ts.am = ts.ns + JD; ts.ae = (unsigned short *)(ts.am + JD);
-	ts.foi = ts.am + JD + EVEN((JD + 3) / 4); ts.nmi = ts.foi + De; ts.Iv = ts.nmi + Ge;
-	for (int i = lane; i < JD; i += 32) ts.ns[i] = 0;
+	double *N0R = smem + L.n0;
+	unsigned *ctab = (unsigned *)(smem + L.ctab);
+	for (int i = threadIdx.x; i < m.G * L.Gs; i += blockDim.x) { const int r = i / L.Gs, k = i - r * L.Gs; N0R[i] = (k < m.G) ? m.N0[r * m.G + k] : 0.0; }
+	for (int i = threadIdx.x; i < m.J * m.D; i += blockDim.x) ctab[i] = m.cell_tab[i];
+	ts.N0R = N0R; ts.ctab = ctab; ts.Gs = L.Gs;
+	return smem + L.common;
+}
+
+__device__ __forceinline__ void work_init(TileSm &ts, const TrajSm &L, double *w, int lane)
+{
+	ts.ns = w + L.ns; ts.ae = (unsigned short *)(w + L.ae);
+	ts.foi = w + L.foi; ts.nmi = w + L.nmi; ts.Iv = w + L.iv; ts.nbr = (Nbr *)(w + L.nbr);
+	for (int i = lane; i < L.JDe; i += 32) ts.ns[i] = 0;
+	for (int i = lane; i < L.Gs; i += 32) ts.Iv[i] = 0;
 	__syncwarp();
 }
 
-#ifndef BEEP_TRAJ_MINB
-#define BEEP_TRAJ_MINB 3
-#endif
 template <int MODE, int SYNC, bool KEEP>
 __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
 {
@@ -698,104 +743,153 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 	const DevModel &m = a.m;
 	const DevBatch &b = a.b;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = a.nwarp;
-	const int A = m.A, D = m.D, J = m.J, G = m.G, S = m.S;
-	const int CDp = m.CDp, JD = EVEN(J * D), De = EVEN(D), Ge = EVEN(G);
+	const int A = m.A, G = m.G, S = m.S;
+	const int CDp = m.CDp;
+	const TrajSm &L = a.L;
 	TileSm ts;
-	double *sm = sm_common_init(m, smraw, ts);
+	double *sm = sm_common_init(m, L, smraw, ts);
 	__syncthreads();
 
 	if (SYNC == SYNC_NONE) {
-		const int per = CDp + WORK_DOUBLES(JD, De, Ge) + EVEN(2 * S * G);
+		const int per = CDp + L.work + BEEP_EVEN(2 * S * G);
 		ts.pop = sm + (size_t)warp * per;
-		work_init(ts, ts.pop + CDp, JD, De, Ge, lane);
-		double *dinf = ts.Iv + Ge;
+		work_init(ts, L, ts.pop + CDp, lane);
+		double *dinf = ts.pop + CDp + L.work;
 		const long long tile = (long long)blockIdx.x * nwarp + warp;
 		if (tile >= (long long)b.P * A) return;
 		TileCtx tc;
-		tile_ctx(a, (int)(tile / A), (int)(tile % A), tc);
+		tile_ctx_particle(a, (int)(tile / A), tc);
+		tile_ctx_area(m.area_info[(int)(tile % A)], (int)(tile % A), tc);
 		double *gp = b.pop_cur + (size_t)tile * CDp;
 		for (int i = lane; i < CDp; i += 32) ts.pop[i] = gp[i];
 		__syncwarp();
-		tile_dinf(m, tc.infco, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
+		tile_dinf(m, tc.infco, tc.il, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
 		__syncwarp();
 		for (int t = a.ti; t < a.tf; t++)
-			tile_step<MODE, KEEP>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+			tile_step<MODE, KEEP, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
 		for (int i = lane; i < CDp; i += 32) gp[i] = ts.pop[i];
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
 		double *popA = sm, *dinf = popA + (size_t)A * CDp;
-		const int perw = WORK_DOUBLES(JD, De, Ge);
-		work_init(ts, dinf + EVEN(2 * S * A * G) + (size_t)warp * perw, JD, De, Ge, lane);
+		work_init(ts, L, dinf + BEEP_EVEN(2 * S * A * G) + (size_t)warp * L.work, lane);
 		double *gp = b.pop_cur + (size_t)p * A * CDp;
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) popA[i] = gp[i];
 		__syncthreads();
-		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * m.C, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
+		TileCtx tc;
+		tile_ctx_particle(a, p, tc);
+		for (int c = warp; c < A; c += nwarp) tile_dinf(m, tc.infco, tc.il, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
 		__syncthreads();
 		for (int t = a.ti; t < a.tf; t++) {
 			const int tday = t / m.spu;
 			for (int c = warp; c < A; c += nwarp) {
-				TileCtx tc;
-				tile_ctx(a, p, c, tc);
+				tile_ctx_area(m.area_info[c], c, tc);
 				ts.pop = popA + (size_t)c * CDp;
-				tile_step<MODE, KEEP>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+				tile_step<MODE, KEEP, false>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
 			}
 			__syncthreads();
 		}
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) gp[i] = popA[i];
 	} else {
 		cg::grid_group grid = cg::this_grid();
-		const int per = 2 * CDp + WORK_DOUBLES(JD, De, Ge);
+		constexpr int NB = BEEP_TRAJ_NBUF;
+		const int per = NB * CDp + L.work;
 		double *popbuf = sm + (size_t)warp * per;
-		work_init(ts, popbuf + 2 * CDp, JD, De, Ge, lane);
-		/* tiles of this warp: gw, gw + nw, ... (32-bit: the launcher checks P*A < 2^31) */
-		const int ntile = b.P * A, nw = gridDim.x * nwarp, gw = blockIdx.x * nwarp + warp;
-		const int p0 = gw / A, c0 = gw - p0 * A, dpn = nw / A, dcn = nw - dpn * A;
+		work_init(ts, L, popbuf + NB * CDp, lane);
+		const int ntile = b.P * A, nw = gridDim.x * nwarp, gw = blockIdx.x * nwarp + warp;   /* 32-bit: the launcher checks P*A < 2^30 */
 		const size_t dsz = (size_t)b.P * S * A * G, psz = (size_t)S * A * G;
 		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
-		{
-			int p = p0, c = c0;
-			for (int tile = gw; tile < ntile; tile += nw) {
-				const double *gp = b.pop_cur + (size_t)tile * CDp;
-				for (int i = lane; i < CDp; i += 32) popbuf[i] = gp[i];
-				__syncwarp();
-				tile_dinf(m, b.infco + (size_t)p * m.C, popbuf, b.dinf + (a.ti & 1) * dsz + (size_t)p * psz + c * G, A * G, lane);
-				__syncwarp();
-				p += dpn; c += dcn; if (c >= A) { c -= A; p++; }
-			}
+		const int CH = a.chunk;
+		TileCtx tc;
+		tc.p = -1;
+		/* infectivity of the starting population (static tile split: done once) */
+#pragma unroll 1
+		for (int tile = gw; tile < ntile; tile += nw) {
+			const int p = tile / A, c = tile - p * A;
+			const double *gp = b.pop_cur + (size_t)tile * CDp;
+#pragma unroll 1
+			for (int i = lane; i < CDp; i += 32) popbuf[i] = gp[i];
+			__syncwarp();
+			tile_dinf(m, b.infco + (size_t)p * m.C, b.inflist + (size_t)p * (m.C + 1), popbuf, b.dinf + (a.ti & 1) * dsz + (size_t)p * psz + c * G, A * G, lane);
+			__syncwarp();
 		}
 		grid.sync();
+		/* Per step the tiles are handed out dynamically, CH consecutive tiles per grab of the step's
+		 * counter, so that the grid barrier waits for the slowest tile rather than the slowest warp.
+		 * The population of a tile streams into shared memory by cp.async: with two buffers tile k+1
+		 * loads while tile k computes; with one buffer the copy is issued when the previous tile
+		 * retires and awaited after the force-of-infection phase, which does not read it.  The
+		 * per-area constants of the next tile are fetched one tile ahead. */
+#pragma unroll 1
 		for (int t = a.ti; t < a.tf; t++) {
 			const int tday = t / m.spu;
 			const double *dcur = b.dinf + (t & 1) * dsz;
 			double *dnxt = b.dinf + ((t + 1) & 1) * dsz;
-			/* software pipeline over this warp's tiles: tile k+1 streams into the other buffer while tile k computes */
-			if (gw < ntile) {
-				const double *gp = b.pop_cur + (size_t)gw * CDp;
+			int *ctr = b.sched + t;
+			int grabbed = 0;
+			if (lane == 0) grabbed = atomicAdd(ctr, CH);
+			int base = __shfl_sync(FULLMASK, grabbed, 0);
+			AreaInfo ai_nx;
+			if (base < ntile) {
+				const double *gp = b.pop_cur + (size_t)base * CDp;
+#pragma unroll 1
 				for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gp + 2 * i);
 				cp_async_commit();
+				int p0, c0;
+				tile_split(base, A, a.invA, p0, c0);
+				ai_nx = m.area_info[c0];
 			}
-			int kb = 0, p = p0, c = c0;
-			for (int tile = gw; tile < ntile; tile += nw, kb ^= 1) {
-				double *gp = b.pop_cur + (size_t)tile * CDp;
-				if (tile + nw < ntile) {
-					const double *gn = gp + (size_t)nw * CDp;
-					double *dst = popbuf + (kb ^ 1) * CDp;
-					for (int i = lane; i < nchunk; i += 32) cp_async16(dst + 2 * i, gn + 2 * i);
-					cp_async_commit();
-					cp_async_wait<1>();
-				} else cp_async_wait<0>();
-				__syncwarp();
-				TileCtx tc;
-				tile_ctx(a, p, c, tc);
-				ts.pop = popbuf + kb * CDp;
-				const unsigned ev = tile_step<MODE, KEEP>(a, tc, t, tday, lane, ts, dcur + (size_t)p * psz, dnxt + (size_t)p * psz, A, c);
-				if (ev != 0 || S > 1) {
-					const double2 *s2 = (const double2 *)ts.pop;
-					double2 *g2 = (double2 *)gp;
-					for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
+			int kb = 0;
+#pragma unroll 1
+			while (base < ntile) {
+				const int cend = (base + CH < ntile) ? base + CH : ntile;
+				if (lane == 0) grabbed = atomicAdd(ctr, CH);        /* next chunk: the round trip hides behind this chunk's work */
+				int p, c;
+				tile_split(base, A, a.invA, p, c);
+#pragma unroll 1
+				for (int tile = base; tile < cend; tile++) {
+					double *gp = b.pop_cur + (size_t)tile * CDp;
+					int nxt = tile + 1;
+					if (nxt == cend) nxt = __shfl_sync(FULLMASK, grabbed, 0);
+					const AreaInfo ai = ai_nx;
+					if (NB == 2) {
+						if (nxt < ntile) {
+							const double *gn = b.pop_cur + (size_t)nxt * CDp;
+							double *dst = popbuf + (kb ^ 1) * CDp;
+#pragma unroll 1
+							for (int i = lane; i < nchunk; i += 32) cp_async16(dst + 2 * i, gn + 2 * i);
+							cp_async_commit();
+							cp_async_wait<1>();
+						} else cp_async_wait<0>();
+						__syncwarp();
+					}
+					if (nxt < ntile) {
+						int cn = c + 1;
+						if (cn == A) cn = 0;
+						if (nxt != tile + 1) { int pn; tile_split(nxt, A, a.invA, pn, cn); }
+						ai_nx = m.area_info[cn];
+					}
+					if (p != tc.p) tile_ctx_particle(a, p, tc);
+					tile_ctx_area(ai, c, tc);
+					ts.pop = popbuf + kb * CDp;
+					const unsigned ev = tile_step<MODE, KEEP, NB == 1>(a, tc, t, tday, lane, ts, dcur + (size_t)p * psz, dnxt + (size_t)p * psz, A, c);
+					if (ev != 0 || S > 1) {
+						const double2 *s2 = (const double2 *)ts.pop;
+						double2 *g2 = (double2 *)gp;
+#pragma unroll 1
+						for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
+					}
+					__syncwarp();
+					if (NB == 1) {
+						if (nxt < ntile) {
+							const double *gn = b.pop_cur + (size_t)nxt * CDp;
+#pragma unroll 1
+							for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gn + 2 * i);
+							cp_async_commit();
+						}
+					} else kb ^= 1;
+					if (++c == A) { c = 0; p++; }
 				}
-				__syncwarp();
-				p += dpn; c += dcn; if (c >= A) { c -= A; p++; }
+				base = __shfl_sync(FULLMASK, grabbed, 0);
 			}
 			grid.sync();
 		}

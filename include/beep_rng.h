@@ -31,8 +31,11 @@
 
 #if defined(__CUDACC__)
 #define BEEP_HD __host__ __device__ __forceinline__
+/* rarely taken acceptance tests: kept out of line so that the hot loop of a kernel stays small */
+#define BEEP_HD_COLD static __host__ __device__ __noinline__
 #else
 #define BEEP_HD static inline
+#define BEEP_HD_COLD static
 #include <math.h>
 #endif
 
@@ -155,8 +158,9 @@ BEEP_HD double beep_u2d(uint64_t u)
 #endif
 }
 
-/* natural log of a positive finite double */
-BEEP_HD double beep_log(double x)
+/* natural log of a positive finite double (out of line on the device: only the rarely
+ * taken exact acceptance tests of the rejection samplers call it) */
+BEEP_HD_COLD double beep_log(double x)
 {
 	const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
 	const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
@@ -190,22 +194,28 @@ BEEP_HD double beep_log(double x)
 	return BR_SUB(BR_MUL(dk, ln2_hi), BR_SUB(BR_SUB(hfsq, inner), f));
 }
 
-/* exp(x) for x in [-700, 700] (callers guarantee the range) */
+/* exp(x) for x in [-700, 700] (callers guarantee the range).  Division-free:
+ * x = k ln2 + r, |r| <= ln2/2 (two-part ln2 as in fdlibm), then
+ * exp(r) = 1 + (r + r^2 q(r)) with q the degree-11 Taylor tail 1/2 + r/6 + ... + r^11/13!
+ * (truncation < 5e-18), evaluated as two interleaved Horner chains in r^2 (even and odd
+ * coefficients) with explicit non-contracted operations: < 1 ulp, identical on host and device. */
 BEEP_HD double beep_exp(double x)
 {
 	const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
 	             invln2 = 1.44269504088896338700e+00;
-	const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
-	             P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
-	             P5 = 4.13813679705723846039e-08;
+	const double c2 = 5.0e-01, c3 = 1.66666666666666666667e-01, c4 = 4.16666666666666666667e-02,
+	             c5 = 8.33333333333333333333e-03, c6 = 1.38888888888888888889e-03, c7 = 1.98412698412698412698e-04,
+	             c8 = 2.48015873015873015873e-05, c9 = 2.75573192239858906526e-06, c10 = 2.75573192239858906526e-07,
+	             c11 = 2.50521083854417187751e-08, c12 = 2.08767569878680989792e-09, c13 = 1.60590438368216145994e-10;
 	int k = (int)BR_ADD(BR_MUL(invln2, x), (x < 0.0 ? -0.5 : 0.5));
 	double dk = (double)k;
-	double hi = BR_SUB(x, BR_MUL(dk, ln2HI));
-	double lo = BR_MUL(dk, ln2LO);
-	double r = BR_SUB(hi, lo);
-	double t = BR_MUL(r, r);
-	double c = BR_SUB(r, BR_MUL(t, BR_ADD(P1, BR_MUL(t, BR_ADD(P2, BR_MUL(t, BR_ADD(P3, BR_MUL(t, BR_ADD(P4, BR_MUL(t, P5))))))))));
-	double y = BR_SUB(1.0, BR_SUB(BR_SUB(lo, BR_DIV(BR_MUL(r, c), BR_SUB(2.0, c))), hi));
+	double r = BR_SUB(BR_SUB(x, BR_MUL(dk, ln2HI)), BR_MUL(dk, ln2LO));
+	double z = BR_MUL(r, r);
+	/* q(r) = E(z) + r O(z):  E = c2 + c4 z + ... + c12 z^5,  O = c3 + c5 z + ... + c13 z^5 */
+	double E = BR_ADD(c2, BR_MUL(z, BR_ADD(c4, BR_MUL(z, BR_ADD(c6, BR_MUL(z, BR_ADD(c8, BR_MUL(z, BR_ADD(c10, BR_MUL(z, c12))))))))));
+	double O = BR_ADD(c3, BR_MUL(z, BR_ADD(c5, BR_MUL(z, BR_ADD(c7, BR_MUL(z, BR_ADD(c9, BR_MUL(z, BR_ADD(c11, BR_MUL(z, c13))))))))));
+	double q = BR_ADD(E, BR_MUL(r, O));
+	double y = BR_ADD(1.0, BR_ADD(r, BR_MUL(z, q)));
 	/* scale by 2^k, k in [-1010, 1010]: two-step to stay in the normal range */
 	int k1 = k / 2, k2 = k - k1;
 	double s1 = beep_u2d((uint64_t)(1023 + k1) << 52);
@@ -263,6 +273,47 @@ static const double beep_inv_host[64] = {0.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 3.0, 1
 #define BEEP_INV(k) beep_inv_host[(k)]
 #endif
 
+/* PTRS squeeze failed: the exact acceptance test (Hormann 1993, step 3) */
+BEEP_HD_COLD int beep_ptrs_accept(double lam, double a, double b, double us, double V, double kf)
+{
+	double invalpha = BR_ADD(1.1239, BR_DIV(1.1328, BR_SUB(b, 3.4)));
+	double loglam = beep_log(lam);
+	double lhs_c = beep_log(invalpha);
+	double lhs = BR_SUB(BR_ADD(beep_log(V), lhs_c), beep_log(BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
+	double rhs = BR_SUB(BR_SUB(BR_MUL(kf, loglam), lam), beep_lfact(kf));
+	return lhs <= rhs;
+}
+
+/* PTRS transformed rejection (Hormann 1993) for lam >= 10 */
+BEEP_HD int beep_poisson_ptrs(BeepStream *s, double lam)
+{
+	double slam = BR_SQRT(lam);
+	double b = BR_ADD(0.931, BR_MUL(2.53, slam));
+	double a = BR_ADD(-0.059, BR_MUL(0.02483, b));
+	double vr = BR_SUB(0.9277, BR_DIV(3.6224, BR_SUB(b, 2.0)));
+	for (int it = 0; it < 100000; it++) {
+		double U = BR_SUB(beep_next_uniform(s), 0.5);
+		double V = beep_next_uniform(s);
+		double us = BR_SUB(0.5, BR_FABS(U));
+		double kf = BR_FLOOR(BR_ADD(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), lam), 0.43));
+		if (us >= 0.07 && V <= vr) return (int)kf;
+		if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+		if (beep_ptrs_accept(lam, a, b, us, V, kf)) return (int)kf;
+	}
+	return (int)lam;
+}
+#if defined(__CUDACC__)
+/* Device: a fresh stream (nothing read yet) runs PTRS out of line, so that kernels dominated
+ * by small means keep a small hot loop; the caller's copy of the stream is not advanced --
+ * on the device a stream serves exactly one draw. */
+static __device__ __noinline__ int beep_poisson_ptrs_fresh(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double lam)
+{
+	BeepStream st;
+	st.key[0] = k0; st.key[1] = k1; st.ctr[0] = c0; st.ctr[1] = c1; st.ctr[2] = c2; st.ctr[3] = c3; st.have = 0;
+	return beep_poisson_ptrs(&st, lam);
+}
+#endif
+
 BEEP_HD int beep_poisson(BeepStream *s, double lam)
 {
 	if (!(lam > 0.0)) return 0;
@@ -275,44 +326,41 @@ BEEP_HD int beep_poisson(BeepStream *s, double lam)
 		double p = beep_exp(BR_SUB(0.0, lam));
 		double cdf = p;
 		int k = 0;
+		double ik = BEEP_INV(1);                       /* 1/(k+1), fetched one step ahead of its use */
 		while (u > cdf && k < 1000) {
 			k++;
-			p = (k < 64) ? BR_MUL(BR_MUL(p, lam), BEEP_INV(k)) : BR_DIV(BR_MUL(p, lam), (double)k);
+			double ikn = BEEP_INV(k < 62 ? k + 1 : 63);
+			p = (k < 64) ? BR_MUL(BR_MUL(p, lam), ik) : BR_DIV(BR_MUL(p, lam), (double)k);
 			cdf = BR_ADD(cdf, p);
+			ik = ikn;
 		}
 		return k;
 	}
-	/* PTRS */
-	double slam = BR_SQRT(lam);
-	double b = BR_ADD(0.931, BR_MUL(2.53, slam));
-	double a = BR_ADD(-0.059, BR_MUL(0.02483, b));
-	double vr = BR_SUB(0.9277, BR_DIV(3.6224, BR_SUB(b, 2.0)));
-	double loglam = 0.0, lhs_c = 0.0;
-	int have_slow = 0;
-	for (int it = 0; it < 100000; it++) {
-		double U = BR_SUB(beep_next_uniform(s), 0.5);
-		double V = beep_next_uniform(s);
-		double us = BR_SUB(0.5, BR_FABS(U));
-		double kf = BR_FLOOR(BR_ADD(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), lam), 0.43));
-		if (us >= 0.07 && V <= vr) return (int)kf;
-		if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-		if (!have_slow) {
-			double invalpha = BR_ADD(1.1239, BR_DIV(1.1328, BR_SUB(b, 3.4)));
-			loglam = beep_log(lam);
-			lhs_c = beep_log(invalpha);
-			have_slow = 1;
-		}
-		double lhs = BR_SUB(BR_ADD(beep_log(V), lhs_c), beep_log(BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
-		double rhs = BR_SUB(BR_SUB(BR_MUL(kf, loglam), lam), beep_lfact(kf));
-		if (lhs <= rhs) return (int)kf;
-	}
-	return (int)lam;
+#if defined(__CUDA_ARCH__)
+	if (s->have == 0) return beep_poisson_ptrs_fresh(s->key[0], s->key[1], s->ctr[0], s->ctr[1], s->ctr[2], s->ctr[3], lam);
+#endif
+	return beep_poisson_ptrs(s, lam);
 }
 
 /* ------------------------------------------------------------------------ */
 /* Binomial                                                                  */
 /* ------------------------------------------------------------------------ */
-BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
+/* BTRS squeeze failed: the exact acceptance test (Hormann 1993) */
+BEEP_HD_COLD int beep_btrs_accept(double dn, double q, double omq, double spq, double a, double b, double us, double V, double kf)
+{
+	double alpha = BR_MUL(BR_ADD(2.83, BR_DIV(5.1, b)), spq);
+	double lpq = beep_log(BR_DIV(q, omq));
+	double m = BR_FLOOR(BR_MUL(BR_ADD(dn, 1.0), q));
+	double h = BR_ADD(beep_lfact(m), beep_lfact(BR_SUB(dn, m)));
+	double lv = beep_log(BR_DIV(BR_MUL(V, alpha), BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
+	double rhs = BR_ADD(BR_SUB(BR_SUB(h, beep_lfact(kf)), beep_lfact(BR_SUB(dn, kf))), BR_MUL(BR_SUB(kf, m), lpq));
+	return lv <= rhs;
+}
+
+/* BINV start value (1-q)^n = exp(n log(1-q)) */
+BEEP_HD_COLD double beep_binv_r0(double dn, double omq) { return beep_exp(BR_MUL(dn, beep_log(omq))); }
+
+BEEP_HD int beep_binomial_body(BeepStream *s, double p, int n)
 {
 	if (n <= 0 || !(p > 0.0)) return 0;
 	if (p >= 1.0) return n;
@@ -330,7 +378,7 @@ BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
 		if (!(u <= BR_SUB(BR_SUB(1.0, BR_MUL(dn, q)), 1e-14))) {
 			double sr = BR_DIV(q, omq);
 			double a = BR_MUL(BR_ADD(dn, 1.0), sr);
-			double r = beep_exp(BR_MUL(dn, beep_log(omq)));
+			double r = beep_binv_r0(dn, omq);
 			while (u > r && k < n) {
 				u = BR_SUB(u, r);
 				k++;
@@ -345,8 +393,6 @@ BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
 		double a = BR_ADD(BR_ADD(-0.0873, BR_MUL(0.0248, b)), BR_MUL(0.01, q));
 		double c = BR_ADD(BR_MUL(dn, q), 0.5);
 		double vr = BR_SUB(0.92, BR_DIV(4.2, b));
-		double alpha = 0.0, lpq = 0.0, m = 0.0, h = 0.0;
-		int have_slow = 0;
 		k = (int)BR_MUL(dn, q);
 		for (int it = 0; it < 100000; it++) {
 			double U = BR_SUB(beep_next_uniform(s), 0.5);
@@ -355,19 +401,28 @@ BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
 			double kf = BR_FLOOR(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), c));
 			if (kf < 0.0 || kf > dn) continue;
 			if (us >= 0.07 && V <= vr) { k = (int)kf; break; }
-			if (!have_slow) {
-				alpha = BR_MUL(BR_ADD(2.83, BR_DIV(5.1, b)), spq);
-				lpq = beep_log(BR_DIV(q, omq));
-				m = BR_FLOOR(BR_MUL(BR_ADD(dn, 1.0), q));
-				h = BR_ADD(beep_lfact(m), beep_lfact(BR_SUB(dn, m)));
-				have_slow = 1;
-			}
-			double lv = beep_log(BR_DIV(BR_MUL(V, alpha), BR_ADD(BR_DIV(a, BR_MUL(us, us)), b)));
-			double rhs = BR_ADD(BR_SUB(BR_SUB(h, beep_lfact(kf)), beep_lfact(BR_SUB(dn, kf))), BR_MUL(BR_SUB(kf, m), lpq));
-			if (lv <= rhs) { k = (int)kf; break; }
+			if (beep_btrs_accept(dn, q, omq, spq, a, b, us, V, kf)) { k = (int)kf; break; }
 		}
 	}
 	return flip ? n - k : k;
+}
+
+#if defined(__CUDACC__)
+/* Device: the whole binomial draw of a fresh stream runs out of line (see beep_poisson_ptrs_fresh) */
+static __device__ __noinline__ int beep_binomial_fresh(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double p, int n)
+{
+	BeepStream st;
+	st.key[0] = k0; st.key[1] = k1; st.ctr[0] = c0; st.ctr[1] = c1; st.ctr[2] = c2; st.ctr[3] = c3; st.have = 0;
+	return beep_binomial_body(&st, p, n);
+}
+#endif
+
+BEEP_HD int beep_binomial(BeepStream *s, double p, int n)
+{
+#if defined(__CUDA_ARCH__)
+	if (s->have == 0) return beep_binomial_fresh(s->key[0], s->key[1], s->ctr[0], s->ctr[1], s->ctr[2], s->ctr[3], p, n);
+#endif
+	return beep_binomial_body(s, p, n);
 }
 
 #endif /* BEEP_RNG_H */

@@ -832,3 +832,7 @@ void oracle_binomial_many(uint64_t seed, uint64_t stream_id, const double *p, co
 	}
 }
 void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { beep_philox4x32_10(ctr, key, out); }
+
+/* the shared software exp / log (include/beep_rng.h), exposed so that tests can pin their accuracy against libm */
+void oracle_exp_many(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = beep_exp(x[i]); }
+void oracle_log_many(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = beep_log(x[i]); }

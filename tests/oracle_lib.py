@@ -49,6 +49,8 @@ def lib():
         L.oracle_poisson_many.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.oracle_binomial_many.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.oracle_philox.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_exp_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_log_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         _LIB = L
     return _LIB
 
