@@ -43,7 +43,7 @@ struct alignas(16) Nbr { double val; unsigned off; int pad; };   /* off in BYTES
 /* Shared-memory layout of the trajectory kernel, in doubles (every block even so that 16-byte
  * accesses stay aligned); computed identically by the launcher and by the kernel.
  *   CTA common : N0R[G][Gs] age matrix rows, stride Gs even with Gs/2 odd (conflict-free 16-byte row reads)
- *                ctab[J*D]  packed cell table (u32)
+ *                ctab[JD32] packed cell table (u32), J*D rounded up to 32 with never-firing cells
  *   per warp   : ns[JD] ae[JD u16] foi[D] Iv[Gs] nbr[32 Nbr] nmi[G]      (work area)
  *   SYNC_NONE, per warp: pop[CDp] W dinf[2][S*G]
  *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: W
@@ -55,7 +55,7 @@ struct alignas(16) Nbr { double val; unsigned off; int pad; };   /* off in BYTES
 #ifndef BEEP_TRAJ_MINB
 #define BEEP_TRAJ_MINB 4
 #endif
-struct TrajSm { int Gs, n0, ctab, common, JDe, ns, ae, foi, nmi, iv, nbr, work; };
+struct TrajSm { int Gs, n0, ctab, common, JDe, JD32, ns, ae, foi, nmi, iv, nbr, work; };
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
@@ -66,7 +66,8 @@ static inline TrajSm traj_sm_layout(int G, int J, int D)
 	if (((gs >> 1) & 1) == 0) gs += 2;
 	L.Gs = gs;
 	L.n0 = 0; L.ctab = BEEP_EVEN(G * gs);
-	L.common = L.ctab + BEEP_EVEN((J * D + 1) >> 1);
+	L.JD32 = (J * D + 31) & ~31;                  /* cell table padded to whole warp passes */
+	L.common = L.ctab + (L.JD32 >> 1);
 	L.JDe = BEEP_EVEN(J * D);
 	L.ns = 0; L.ae = L.JDe;
 	L.foi = L.ae + BEEP_EVEN((L.JDe + 3) >> 2);
@@ -112,6 +113,8 @@ struct DevModel {
 struct DevBatch {
 	int P; unsigned flags;
 	double *theta, *pd, *transrate, *disc_spline, *sus, *areafactor, *betaR, *infco;
+	double *crate;                 /* [P][JD32] per-cell multiplier of dt*pop: transition rate, susceptibility for the
+	                                  infection transition, 0 for cells that never fire (and the padding) */
 	double *etab;                  /* [P][nefoi][T] external force of infection per individual, spline / popsize */
 	int *inflist;                  /* [P][C+1] count, then the compartments with non-zero infectivity (ascending) */
 	int *sched;                    /* [T] tile counters of the grid-synchronised kernel (dynamic tile scheduling) */
@@ -135,6 +138,7 @@ struct TrajArgs {
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
 	int nwarp;          /* warps per CTA */
 	int chunk;          /* SYNC_GRID: tiles a warp takes per grab of the step's tile counter */
+	int fast;           /* the model has the common structure tile_step_fast handles */
 	float invA;         /* 1/A: tile index -> (particle, area) without an integer division */
 	TrajSm L;           /* shared-memory layout (traj_sm_layout), computed once by the launcher */
 	unsigned char tfrom[32], tto[32], tkind[32];   /* per transition: source, target, kind (0 ordinary, 1 infection, 2 never) */

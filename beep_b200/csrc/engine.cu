@@ -411,6 +411,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
 	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
 	BA(b.stream_id, P); BA(b.infmask, P);
+	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
 	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)m.T);
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(K5_CHUNKS, (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
@@ -504,6 +505,9 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
 	a.nwarp = eng->nwarp; a.chunk = 1;
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D);
+	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
+	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && mode != MODE_REPLAY && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
+	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;
 	if (ti == 0) {
@@ -718,6 +722,7 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	if ((rc = gather_inplace(bt, b.infco, m.C, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.infmask, 1, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.etab, (size_t)m.nefoi * m.T, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.crate, ((size_t)m.J * m.D + 31) & ~(size_t)31, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.inflist, (size_t)m.C + 1, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map))) return rc;
@@ -760,6 +765,7 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if ((rc = copy_flagged(init, a.infco, b.infco, m.C))) return rc;
 	if ((rc = copy_flagged(init, a.infmask, b.infmask, 1))) return rc;
 	if ((rc = copy_flagged(init, a.etab, b.etab, (size_t)m.nefoi * m.T))) return rc;
+	if ((rc = copy_flagged(init, a.crate, b.crate, ((size_t)m.J * m.D + 31) & ~(size_t)31))) return rc;
 	if ((rc = copy_flagged(init, a.inflist, b.inflist, (size_t)m.C + 1))) return rc;
 	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.CDp))) return rc;
 	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;

@@ -132,6 +132,16 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		}
 	}
 	__syncthreads();
+	/* per-cell multiplier table of the trajectory kernel's scan */
+	{
+		const int JD32 = (J * D + 31) & ~31;
+		double *crate = b.crate + (size_t)p * JD32;
+		for (int e = tid; e < JD32; e += nth) {
+			double v = 0;
+			if (e < J * D) { const int tr = e / D; v = (tr == m.itr) ? sus[e - tr * D] : transrate[e]; }
+			crate[e] = v;
+		}
+	}
 	/* external force of infection per individual (state.cc:423): spline value / population size */
 	{
 		double *etab = b.etab + (size_t)p * m.nefoi * T;
@@ -337,6 +347,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+/* Explicit shared-memory accesses through 32-bit shared-window addresses.  The hot path keeps ONE
+ * laundered base address per warp and adds layout offsets that sit in the constant bank; with C++
+ * pointers the compiler re-derives every shared base (special registers + constants) at each use
+ * once registers are tight, which cost ~15 % of the issued instructions (profiles/README.md). */
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned launder(unsigned x) { asm volatile("mov.u32 %0, %0;" : "+r"(x)); return x; }
+__device__ __forceinline__ double lds64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ unsigned lds32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ double2 lds128(unsigned a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts128(unsigned a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+
 /* per-warp scratch, all in shared memory (layout: traj_sm_layout, dev_types.h) */
 struct TileSm {
 	double *pop;      /* [CDp] population of the tile                                   */
@@ -356,7 +380,7 @@ struct TileSm {
  * part changes only when the warp moves to another particle, the area part per tile */
 struct TileCtx {
 	int p, c;
-	const double *rate, *ds, *sus, *infco, *af, *betaR, *etab;
+	const double *rate, *crate, *ds, *sus, *infco, *af, *betaR, *etab;
 	const int *il;
 	double *partial;
 	unsigned long long sid;
@@ -371,6 +395,7 @@ __device__ __forceinline__ void tile_ctx_particle(const TrajArgs &a, int p, Tile
 	const DevBatch &b = a.b;
 	tc.p = p;
 	tc.rate = b.transrate + (size_t)p * (m.J * m.D);
+	tc.crate = b.crate + (size_t)p * a.L.JD32;
 	tc.ds = b.disc_spline + (size_t)p * (m.nspline * m.T);
 	tc.sus = b.sus + (size_t)p * m.D;
 	tc.infco = b.infco + (size_t)p * m.C;
@@ -707,6 +732,252 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 	return apply ? trmask : 0u;
 }
 
+/* The same tile step for the common model structure -- one strain, dp == age (D == G > 1),
+ * stochastic dynamics, MODE_SIM / MODE_MBP -- written against explicit shared addresses:
+ *   wb    the warp's work area (ns, ae, foi, Iv, nbr), pa the tile's population, ca the CTA tables.
+ * Same operations in the same order as tile_step (hence as the oracle); the scan is branch-free:
+ * the cell table is padded to a multiple of 32 with never-firing cells and crate[] holds the
+ * per-cell multiplier (rate, or susceptibility for the infection transition, 0 otherwise). */
+template <int MODE, bool KEEP, bool LATEWAIT>
+__device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int p, const int c, const int t, const int tday, const int lane,
+                                                   const unsigned wb, const unsigned pa, const unsigned ca,
+                                                   double *dbase, const size_t dflip, const int ci)
+{
+	/* Loop-carried state is (p, c) and three shared addresses: every table pointer is re-derived from
+	 * the kernel parameters where it is used, so that nothing else stays live across the phases. */
+	const double *dinf_cur = dbase + (t & 1) * dflip;
+	double *dinf_nxt = dbase + ((t + 1) & 1) * dflip;
+	const DevModel &m = a.m;
+	const DevBatch &b = a.b;
+	const TrajSm &L = a.L;
+	const int T = m.T, A = m.A, J = m.J, G = m.G;
+	const int JD = J * G;
+	const unsigned ns_a = wb + L.ns * 8, ae_a = wb + L.ae * 8, foi_a = wb + L.foi * 8, iv_a = wb + L.iv * 8, nbr_a = wb + L.nbr * 8;
+	const unsigned ctab_a = ca + L.ctab * 8;
+	const double *ds = b.disc_spline + (size_t)p * (m.nspline * T);
+
+	/* 1. state.cc:547-578 get_NMI + the infection part of set_transmean (:406-432) */
+	{
+		const double d = ds[m.geo_spline * T + t], omd = 1 - d;
+		const double afv = b.areafactor[((size_t)p * m.period + tday) * A + c];
+		const AreaInfo tc = m.area_info[c];
+		const int ll = lane < G ? lane : G - 1;        /* idle lanes repeat the last age: every load stays in range */
+		const char *dcl = (const char *)(dinf_cur + ll);
+		double Imap = 0;
+#pragma unroll 1
+		for (int jb = 0; jb < tc.nn; jb += 32) {
+			const int cnt = (tc.nn - jb < 32) ? tc.nn - jb : 32;
+			__syncwarp();
+			if (lane < cnt) sts128(nbr_a + lane * 16, *(const double2 *)&m.nbr[tc.j0 + jb + lane]);
+			__syncwarp();
+#pragma unroll 5
+			for (int j = 0; j < cnt; j++) {
+				const double2 raw = lds128(nbr_a + j * 16);                  /* one 16-byte broadcast: (weight, byte offset) */
+				Imap += *(const double *)(dcl + (unsigned)__double2loint(raw.y)) * raw.x;
+			}
+		}
+		const double Idiag = dinf_cur[ci * G + ll] * tc.diag;
+		const double Iv = (Idiag + Imap) * d + tc.fac * Idiag * omd;
+		double nv = 0;
+		/* a neighbourhood without infectious individuals has I = 0, hence NMI = 0 exactly */
+		if (__any_sync(FULLMASK, Iv != 0)) {
+			if (lane < G) sts64(iv_a + lane * 8, Iv);
+			__syncwarp();
+			if (lane < G) {
+				double sum = 0;
+				const unsigned row = ca + L.n0 * 8 + lane * (L.Gs * 8);
+				if (m.nmm == 0) {
+					const int h = L.Gs >> 1;
+#pragma unroll 2
+					for (int k = 0; k < h; k++) { const double2 n2 = lds128(row + k * 16), v2 = lds128(iv_a + k * 16); sum += n2.x * v2.x; sum += n2.y * v2.y; }
+				} else {
+#pragma unroll 1
+					for (int aa = 0; aa < G; aa++) sum += ntime_elem(m, ds, t, lane, aa, lds64(row + aa * 8)) * lds64(iv_a + aa * 8);
+				}
+				if (sum < 0) sum = 0;
+				nv = sum;
+			}
+		}
+		double be = b.betaR[((size_t)p * m.nR + tc.rg) * T + t];
+		be *= afv;
+		const double et = b.etab[((size_t)p * m.nefoi + tc.ie0) * T + t];
+		if (lane < G) sts64(foi_a + lane * 8, be * nv + et * m.efoi_agedist[tc.ie0 * G + lane]);
+		__syncwarp();
+	}
+	if (LATEWAIT) { cp_async_wait<0>(); __syncwarp(); }
+
+	/* 2. scan: transition means (state.cc:434-444); compact the cells that can have events */
+	const size_t tbase = (KEEP || MODE == MODE_MBP) ? (((size_t)p * T + t) * A + c) * (size_t)JD : 0;
+	const bool keep_tn = KEEP && (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = KEEP && (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
+	const unsigned lt = (1u << lane) - 1u;
+	const double dt = m.dt;
+	int nact = 0;
+	unsigned trbits = 0;
+	const double *crate = b.crate + (size_t)p * L.JD32;
+#pragma unroll 1
+	for (int e0 = 0; e0 < JD; e0 += 32) {
+		const int e = e0 + lane;
+		const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
+		const double popu = lds64(pa + ((w & 0xfffu) << 3));
+		const double cr = crate[e];
+		double mean = dt * popu * cr;
+		if ((w >> 24) == 1u) mean *= lds64(foi_a + ((w >> 15) & 0x1f8u));
+		if (!(popu > 0)) mean = 0;
+		const bool act = (mean != 0);
+		if (KEEP && e < JD) {
+			if (keep_tm) b.tm[tbase + e] = mean;
+			if (keep_tn && !act) b.tn[tbase + e] = 0;
+		}
+		const unsigned bal = __ballot_sync(FULLMASK, act);
+		if (act) { sts16(ae_a + (nact + __popc(bal & lt)) * 2, e); sts64(ns_a + e * 8, mean); }
+		nact += __popc(bal);
+	}
+
+	/* 3. draws on the dense list */
+	if (nact > 0) {
+		__syncwarp();
+		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
+		const unsigned long long sid = b.stream_id[p];
+		int simu = 0;
+		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
+#pragma unroll 1
+		for (int i = lane; i < nact; i += 32) {
+			const int e = lds16(ae_a + i * 2);
+			const double mean = lds64(ns_a + e * 8);
+			BeepStream rs;
+			beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
+			int num;
+			if (MODE == MODE_SIM) num = beep_poisson(&rs, mean);             /* state.cc:624-626 */
+			else {
+				/* mbp.cc:286-311 */
+				const int num_i = a.init_tn[tbase + e];
+				if (simu) num = beep_poisson(&rs, mean);
+				else {
+					const double rate_i = a.init_tm[tbase + e];
+					if (mean > rate_i) num = num_i + beep_poisson(&rs, mean - rate_i);
+					else if (mean == rate_i) num = num_i;
+					else if (num_i == 0) num = 0;
+					else num = beep_binomial(&rs, mean / rate_i, num_i);
+				}
+			}
+			sts64(ns_a + e * 8, (double)num);               /* replaces the mean: zero again unless there were events */
+			if (num != 0) trbits |= 1u << ((lds32(ctab_a + e * 4) >> 12) & 63);
+			if (keep_tn) b.tn[tbase + e] = num;
+		}
+	}
+	/* transitions with events, warp-wide (also orders the ns[] writes before the reads below) */
+	const unsigned trmask = __reduce_or_sync(FULLMASK, trbits);
+
+	/* 4a. obsmodel.cc:74-109: add this (sett, area) cell block to the observations that list it */
+	{
+		const int k0 = m.cell_off[t * A + c], k1 = m.cell_off[t * A + c + 1];
+		double *partial = b.obs_partial + (size_t)p * m.nslot;
+		if (m.obs_wide) {
+			/* observations summing many dp: lanes over dp, one warp reduction per entry */
+#pragma unroll 1
+			for (int k = k0; k < k1; k++) {
+				const ObsEnt en = m.cell_ent[k];
+				const int ob = en.ob;
+				const unsigned tmask0 = m.obs_tmask[ob] & trmask, cm0 = m.obs_cmask[ob];
+				if (tmask0 == 0 && cm0 == 0) continue;         /* no events in the observed transitions */
+				const unsigned long long dmask = m.obs_dmask[ob];
+				const double factor = m.obs_factor[ob];
+				const int fs = m.obs_fs[ob];
+				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
+				double val = 0;
+				if (lane < G && ((dmask >> lane) & 1ull)) {
+					unsigned tmask = tmask0;
+					while (tmask) {
+						const int tr = __ffs(tmask) - 1; tmask &= tmask - 1;
+						const double num = lds64(ns_a + (tr * G + lane) * 8);
+						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+					}
+					unsigned cm = cm0;
+					while (cm) {
+						const int co = __ffs(cm) - 1; cm &= cm - 1;
+						val += factor * lds64(pa + (co * G + lane) * 8);
+					}
+				}
+				for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULLMASK, val, o);
+				if (lane == 0 && val != 0) atomicAdd(&partial[en.slot], val);
+			}
+		} else {
+			/* narrow observations (one or a few dp each): one lane per entry */
+#pragma unroll 1
+			for (int k = k0 + lane; k < k1; k += 32) {
+				const ObsEnt en = m.cell_ent[k];
+				const int ob = en.ob;
+				unsigned tmask = m.obs_tmask[ob] & trmask, cm = m.obs_cmask[ob];
+				if (tmask == 0 && cm == 0) continue;
+				const double factor = m.obs_factor[ob];
+				const int fs = m.obs_fs[ob];
+				const unsigned long long dmask = m.obs_dmask[ob];
+				double val = 0;
+				const double dsv = (fs >= 0) ? ds[fs * T + t] : 1.0;
+				while (tmask) {
+					const int tr = __ffs(tmask) - 1; tmask &= tmask - 1;
+					unsigned long long dm = dmask;
+					while (dm) {
+						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+						const double num = lds64(ns_a + (tr * G + dp) * 8);
+						if (num != 0) { if (fs < 0) val += factor * num; else val += factor * num * dsv; }
+					}
+				}
+				while (cm) {
+					const int co = __ffs(cm) - 1; cm &= cm - 1;
+					unsigned long long dm = dmask;
+					while (dm) {
+						const int dp = __ffsll((long long)dm) - 1; dm &= dm - 1;
+						val += factor * lds64(pa + (co * G + dp) * 8);
+					}
+				}
+				/* the slot has a single owner (this tile) and steps are ordered: a plain RED */
+				if (val != 0) atomicAdd(&partial[en.slot], val);
+			}
+		}
+	}
+	__syncwarp();
+
+	/* 4b. state.cc:460-485 update_pop in transition order (the last step's events are never
+	 * applied), consuming -- and clearing -- the event counts; then the infectivity of the
+	 * new population.  Without events both are unchanged. */
+	const bool apply = (t < T - 1);
+	{
+		unsigned tm_ = trmask;
+		while (tm_) {
+			const int tr = __ffs(tm_) - 1; tm_ &= tm_ - 1;
+			if (lane < G) {
+				const unsigned na = ns_a + (tr * G + lane) * 8;
+				const double num = lds64(na);
+				if (num != 0) {
+					if (apply) {
+						const unsigned fa = pa + (a.tfrom[tr] * G + lane) * 8, ta = pa + (a.tto[tr] * G + lane) * 8;
+						sts64(fa, lds64(fa) - num);
+						sts64(ta, lds64(ta) + num);
+					}
+					sts64(na, 0.0);
+				}
+			}
+		}
+		__syncwarp();
+		if (apply && lane < G) {
+			double *out = dinf_nxt + ci * G + lane;
+			if (trmask & (unsigned)b.infmask[p]) {
+				/* state.cc:223-264: infectivity-weighted individuals by age over the infectious compartments */
+				const int *il = b.inflist + (size_t)p * (m.C + 1);
+				const double *infco = b.infco + (size_t)p * m.C;
+				const int ninf = il[0];
+				double sum = 0;
+#pragma unroll 1
+				for (int k = 1; k <= ninf; k++) { const int co = il[k]; sum += infco[co] * lds64(pa + (co * G + lane) * 8); }
+				*out = sum;
+			} else *out = dinf_cur[ci * G + lane];
+		}
+	}
+	__syncwarp();
+	return apply ? trmask : 0u;
+}
+
 /* tile index -> (particle, area): float reciprocal estimate (particle < 2^23) corrected by one */
 __device__ __forceinline__ void tile_split(int tile, int A, float invA, int &p, int &c)
 {
@@ -722,7 +993,7 @@ __device__ __forceinline__ double *sm_common_init(const DevModel &m, const TrajS
 	double *N0R = smem + L.n0;
 	unsigned *ctab = (unsigned *)(smem + L.ctab);
 	for (int i = threadIdx.x; i < m.G * L.Gs; i += blockDim.x) { const int r = i / L.Gs, k = i - r * L.Gs; N0R[i] = (k < m.G) ? m.N0[r * m.G + k] : 0.0; }
-	for (int i = threadIdx.x; i < m.J * m.D; i += blockDim.x) ctab[i] = m.cell_tab[i];
+	for (int i = threadIdx.x; i < L.JD32; i += blockDim.x) ctab[i] = (i < m.J * m.D) ? m.cell_tab[i] : (2u << 24);
 	ts.N0R = N0R; ts.ctab = ctab; ts.Gs = L.Gs;
 	return smem + L.common;
 }
@@ -736,6 +1007,13 @@ __device__ __forceinline__ void work_init(TileSm &ts, const TrajSm &L, double *w
 	__syncwarp();
 }
 
+/* per-warp pointers of the generic tile step, rebuilt where it is called (cold path) */
+__device__ __forceinline__ void work_ptrs(TileSm &ts, const TrajSm &L, double *w)
+{
+	ts.ns = w + L.ns; ts.ae = (unsigned short *)(w + L.ae);
+	ts.foi = w + L.foi; ts.nmi = w + L.nmi; ts.Iv = w + L.iv; ts.nbr = (Nbr *)(w + L.nbr);
+}
+
 template <int MODE, int SYNC, bool KEEP>
 __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
 {
@@ -746,45 +1024,76 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 	const int A = m.A, G = m.G, S = m.S;
 	const int CDp = m.CDp;
 	const TrajSm &L = a.L;
-	TileSm ts;
-	double *sm = sm_common_init(m, L, smraw, ts);
+	{
+		TileSm ts0;
+		sm_common_init(m, L, smraw, ts0);
+	}
 	__syncthreads();
+	const unsigned ca = launder(smem_addr(smraw));
+	const bool fast = MODE != MODE_REPLAY && a.fast != 0;
+	double *sm = smraw + L.common;
 
 	if (SYNC == SYNC_NONE) {
 		const int per = CDp + L.work + BEEP_EVEN(2 * S * G);
-		ts.pop = sm + (size_t)warp * per;
-		work_init(ts, L, ts.pop + CDp, lane);
-		double *dinf = ts.pop + CDp + L.work;
+		double *pop = sm + (size_t)warp * per;
+		{
+			TileSm ts0;
+			work_init(ts0, L, pop + CDp, lane);
+		}
+		double *dinf = pop + CDp + L.work;
 		const long long tile = (long long)blockIdx.x * nwarp + warp;
 		if (tile >= (long long)b.P * A) return;
-		TileCtx tc;
-		tile_ctx_particle(a, (int)(tile / A), tc);
-		tile_ctx_area(m.area_info[(int)(tile % A)], (int)(tile % A), tc);
+		const int p = (int)(tile / A), c = (int)(tile % A);
 		double *gp = b.pop_cur + (size_t)tile * CDp;
-		for (int i = lane; i < CDp; i += 32) ts.pop[i] = gp[i];
+		for (int i = lane; i < CDp; i += 32) pop[i] = gp[i];
 		__syncwarp();
-		tile_dinf(m, tc.infco, tc.il, ts.pop, dinf + (a.ti & 1) * S * G, G, lane);
+		tile_dinf(m, b.infco + (size_t)p * m.C, b.inflist + (size_t)p * (m.C + 1), pop, dinf + (a.ti & 1) * S * G, G, lane);
 		__syncwarp();
-		for (int t = a.ti; t < a.tf; t++)
-			tile_step<MODE, KEEP, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
-		for (int i = lane; i < CDp; i += 32) gp[i] = ts.pop[i];
+		if (fast) {
+			const unsigned wb = launder(smem_addr(pop + CDp)), pa = launder(smem_addr(pop));
+#pragma unroll 1
+			for (int t = a.ti; t < a.tf; t++) tile_step_fast<MODE, KEEP, false>(a, p, c, t, t / m.spu, lane, wb, pa, ca, dinf, (size_t)(S * G), 0);
+		} else {
+			TileSm ts;
+			ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = pop;
+			work_ptrs(ts, L, pop + CDp);
+			TileCtx tc;
+			tile_ctx_particle(a, p, tc);
+			tile_ctx_area(m.area_info[c], c, tc);
+#pragma unroll 1
+			for (int t = a.ti; t < a.tf; t++)
+				tile_step<MODE, KEEP, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+		}
+		for (int i = lane; i < CDp; i += 32) gp[i] = pop[i];
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
 		double *popA = sm, *dinf = popA + (size_t)A * CDp;
-		work_init(ts, L, dinf + BEEP_EVEN(2 * S * A * G) + (size_t)warp * L.work, lane);
+		double *wk = dinf + BEEP_EVEN(2 * S * A * G) + (size_t)warp * L.work;
+		{
+			TileSm ts0;
+			work_init(ts0, L, wk, lane);
+		}
 		double *gp = b.pop_cur + (size_t)p * A * CDp;
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) popA[i] = gp[i];
 		__syncthreads();
-		TileCtx tc;
-		tile_ctx_particle(a, p, tc);
-		for (int c = warp; c < A; c += nwarp) tile_dinf(m, tc.infco, tc.il, popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
+		for (int c = warp; c < A; c += nwarp) tile_dinf(m, b.infco + (size_t)p * m.C, b.inflist + (size_t)p * (m.C + 1), popA + (size_t)c * CDp, dinf + (a.ti & 1) * S * A * G + c * G, A * G, lane);
 		__syncthreads();
+		const unsigned wb = launder(smem_addr(wk)), pa0 = launder(smem_addr(popA));
+#pragma unroll 1
 		for (int t = a.ti; t < a.tf; t++) {
 			const int tday = t / m.spu;
+#pragma unroll 1
 			for (int c = warp; c < A; c += nwarp) {
-				tile_ctx_area(m.area_info[c], c, tc);
-				ts.pop = popA + (size_t)c * CDp;
-				tile_step<MODE, KEEP, false>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+				if (fast) tile_step_fast<MODE, KEEP, false>(a, p, c, t, tday, lane, wb, pa0 + c * (CDp * 8), ca, dinf, (size_t)(S * A * G), c);
+				else {
+					TileSm ts;
+					ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popA + (size_t)c * CDp;
+					work_ptrs(ts, L, wk);
+					TileCtx tc;
+					tile_ctx_particle(a, p, tc);
+					tile_ctx_area(m.area_info[c], c, tc);
+					tile_step<MODE, KEEP, false>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+				}
 			}
 			__syncthreads();
 		}
@@ -794,13 +1103,15 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		constexpr int NB = BEEP_TRAJ_NBUF;
 		const int per = NB * CDp + L.work;
 		double *popbuf = sm + (size_t)warp * per;
-		work_init(ts, L, popbuf + NB * CDp, lane);
+		{
+			TileSm ts0;
+			work_init(ts0, L, popbuf + NB * CDp, lane);
+		}
+		const unsigned wb = launder(smem_addr(popbuf + NB * CDp)), pa0 = launder(smem_addr(popbuf));
 		const int ntile = b.P * A, nw = gridDim.x * nwarp, gw = blockIdx.x * nwarp + warp;   /* 32-bit: the launcher checks P*A < 2^30 */
 		const size_t dsz = (size_t)b.P * S * A * G, psz = (size_t)S * A * G;
 		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
 		const int CH = a.chunk;
-		TileCtx tc;
-		tc.p = -1;
 		/* infectivity of the starting population (static tile split: done once) */
 #pragma unroll 1
 		for (int tile = gw; tile < ntile; tile += nw) {
@@ -817,26 +1128,19 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		 * counter, so that the grid barrier waits for the slowest tile rather than the slowest warp.
 		 * The population of a tile streams into shared memory by cp.async: with two buffers tile k+1
 		 * loads while tile k computes; with one buffer the copy is issued when the previous tile
-		 * retires and awaited after the force-of-infection phase, which does not read it.  The
-		 * per-area constants of the next tile are fetched one tile ahead. */
+		 * retires and awaited after the force-of-infection phase, which does not read it. */
 #pragma unroll 1
 		for (int t = a.ti; t < a.tf; t++) {
 			const int tday = t / m.spu;
-			const double *dcur = b.dinf + (t & 1) * dsz;
-			double *dnxt = b.dinf + ((t + 1) & 1) * dsz;
 			int *ctr = b.sched + t;
 			int grabbed = 0;
 			if (lane == 0) grabbed = atomicAdd(ctr, CH);
 			int base = __shfl_sync(FULLMASK, grabbed, 0);
-			AreaInfo ai_nx;
 			if (base < ntile) {
 				const double *gp = b.pop_cur + (size_t)base * CDp;
 #pragma unroll 1
 				for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gp + 2 * i);
 				cp_async_commit();
-				int p0, c0;
-				tile_split(base, A, a.invA, p0, c0);
-				ai_nx = m.area_info[c0];
 			}
 			int kb = 0;
 #pragma unroll 1
@@ -847,10 +1151,8 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 				tile_split(base, A, a.invA, p, c);
 #pragma unroll 1
 				for (int tile = base; tile < cend; tile++) {
-					double *gp = b.pop_cur + (size_t)tile * CDp;
 					int nxt = tile + 1;
 					if (nxt == cend) nxt = __shfl_sync(FULLMASK, grabbed, 0);
-					const AreaInfo ai = ai_nx;
 					if (NB == 2) {
 						if (nxt < ntile) {
 							const double *gn = b.pop_cur + (size_t)nxt * CDp;
@@ -862,19 +1164,20 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 						} else cp_async_wait<0>();
 						__syncwarp();
 					}
-					if (nxt < ntile) {
-						int cn = c + 1;
-						if (cn == A) cn = 0;
-						if (nxt != tile + 1) { int pn; tile_split(nxt, A, a.invA, pn, cn); }
-						ai_nx = m.area_info[cn];
+					unsigned ev;
+					if (fast) ev = tile_step_fast<MODE, KEEP, NB == 1>(a, p, c, t, tday, lane, wb, pa0 + kb * (CDp * 8), ca, b.dinf + (size_t)p * psz, dsz, c);
+					else {
+						TileSm ts;
+						ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popbuf + kb * CDp;
+						work_ptrs(ts, L, popbuf + NB * CDp);
+						TileCtx tc;
+						tile_ctx_particle(a, p, tc);
+						tile_ctx_area(m.area_info[c], c, tc);
+						ev = tile_step<MODE, KEEP, NB == 1>(a, tc, t, tday, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * psz, b.dinf + ((t + 1) & 1) * dsz + (size_t)p * psz, A, c);
 					}
-					if (p != tc.p) tile_ctx_particle(a, p, tc);
-					tile_ctx_area(ai, c, tc);
-					ts.pop = popbuf + kb * CDp;
-					const unsigned ev = tile_step<MODE, KEEP, NB == 1>(a, tc, t, tday, lane, ts, dcur + (size_t)p * psz, dnxt + (size_t)p * psz, A, c);
 					if (ev != 0 || S > 1) {
-						const double2 *s2 = (const double2 *)ts.pop;
-						double2 *g2 = (double2 *)gp;
+						const double2 *s2 = (const double2 *)(popbuf + kb * CDp);
+						double2 *g2 = (double2 *)(b.pop_cur + (size_t)tile * CDp);
 #pragma unroll 1
 						for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
 					}
