@@ -47,11 +47,8 @@ struct alignas(16) Nbr { double val; unsigned off; int pad; };   /* off in BYTES
  *   per warp   : ns[JD] ae[JD u16] foi[D] Iv[Gs] nbr[32 Nbr] nmi[G]      (work area)
  *   SYNC_NONE, per warp: pop[CDp] W dinf[2][S*G]
  *   SYNC_CTA,  per CTA:  pop[A][CDp] dinf[2][S*A*G]; per warp: W
- *   SYNC_GRID, per warp: pop[BEEP_TRAJ_NBUF][CDp] W     (2 = cp.async double buffer: tile k+1 streams
- *                                                        in while tile k computes; 1 = more warps per SM) */
-#ifndef BEEP_TRAJ_NBUF
-#define BEEP_TRAJ_NBUF 1
-#endif
+ *   SYNC_GRID, per warp: pop[CDp] W                     (the tile streams in by cp.async while the
+ *                                                        force of infection is computed) */
 #ifndef BEEP_TRAJ_MINB
 #define BEEP_TRAJ_MINB 4
 #endif
@@ -95,6 +92,8 @@ struct DevModel {
 	const int *region_effect_param, *area_effect_param, *covar_param; const double *covar_value;
 	const int *level_param, *level_map; const double *area_total_pop;
 	const double *N0, *N0T; const int *mm_spline, *mm_cnt; const int *dp_age;
+	const int *mm_prog_off, *mm_prog;   /* per element (a,b) of the age matrix: the splines that multiply it, in the
+	                                       reference's order (model.cc:1254-1285; a spline appears once per hit) */
 	const int *R_spline_ref, *area_rgrp; const double *R_dist; const int *strain_Rfactor_param;
 	const int *efoi_spline_ref, *efoi_ref; const double *efoi_agedist;
 	const int *Min_off, *Min_src; const double *Min_val; const double *M_diag, *M_factor;
@@ -117,7 +116,8 @@ struct DevBatch {
 	                                  infection transition, 0 for cells that never fire (and the padding) */
 	double *etab;                  /* [P][nefoi][T] external force of infection per individual, spline / popsize */
 	int *inflist;                  /* [P][C+1] count, then the compartments with non-zero infectivity (ascending) */
-	int *sched;                    /* [T] tile counters of the grid-synchronised kernel (dynamic tile scheduling) */
+	unsigned long long *sched;     /* [P][16] per particle, one 128-byte line: word 0 = (step << 32 | next tile) of the
+	                                  particle-step scheduler, word 1 = tiles of that step completed */
 	double *pop_cur, *dinf;
 	double *scratchA;              /* [P][A] K0 scratch (per-area averages) */
 	int *tn; double *tm; double *poptraj;

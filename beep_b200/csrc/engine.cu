@@ -170,6 +170,14 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		for (int mm = 0; mm < m.nmm; mm++)
 			for (int k = d->matmod_age_off[mm]; k < d->matmod_age_off[mm + 1]; k++) { NEED(d->matmod_age[k] >= 0 && d->matmod_age[k] < G, "matmod age out of range"); cnt[(size_t)mm * G + d->matmod_age[k]]++; }
 		UPV(mm_cnt, cnt);
+		std::vector<int> poff((size_t)G * G + 1, 0), prog;
+		for (int a = 0; a < G; a++) for (int b = 0; b < G; b++) {
+			for (int mm = 0; mm < m.nmm; mm++)
+				for (int k = cnt[(size_t)mm * G + a] + cnt[(size_t)mm * G + b]; k > 0; k--) prog.push_back(d->matmod_spline[mm]);
+			poff[(size_t)a * G + b + 1] = (int)prog.size();
+		}
+		if (prog.empty()) prog.push_back(0);
+		UPV(mm_prog_off, poff); UPV(mm_prog, prog);
 	}
 	UP(mm_spline, d->matmod_spline, m.nmm); UP(dp_age, d->dp_age, Dq);
 	m.age_fast = 1;
@@ -318,7 +326,8 @@ static int choose_launch(BeepEngine *eng)
 	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * work) * sizeof(double); };
 	if (m.M_nnz == 0) {
 		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
-		eng->smem_traj = (common + eng->nwarp * (CDp + work + even(2 * (size_t)m.S * m.G))) * sizeof(double);
+		const size_t ntsz = (m.nmm > 0) ? (size_t)m.G * L.Gs : 0;      /* the warp's copy of Ntime (k_traj) */
+		eng->smem_traj = (common + eng->nwarp * (CDp + work + even(2 * (size_t)m.S * m.G) + ntsz)) * sizeof(double);
 	} else {
 		eng->nwarp = std::min(8, m.A);
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
@@ -331,7 +340,7 @@ static int choose_launch(BeepEngine *eng)
 	}
 	if (eng->sync_mode == SYNC_GRID) {
 		eng->nwarp = 8;
-		eng->smem_traj = (common + eng->nwarp * (BEEP_TRAJ_NBUF * CDp + work)) * sizeof(double);
+		eng->smem_traj = (common + eng->nwarp * (CDp + work)) * sizeof(double);
 	}
 	if ((long long)m.A * m.G >= (1ll << 28)) return fail(BEEP_ERR_UNSUPPORTED, "too many areas (A*G must be below 2^28)");
 	if (eng->smem_traj > (size_t)eng->smem_optin) return fail(BEEP_ERR_UNSUPPORTED, "tile needs %zu B of shared memory (> %d)", eng->smem_traj, eng->smem_optin);
@@ -413,7 +422,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.stream_id, P); BA(b.infmask, P);
 	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
-	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)m.T);
+	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)P * 16);
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(K5_CHUNKS, (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
@@ -459,10 +468,17 @@ static int launch_set_param(BeepBatch *bt)
 {
 	BeepEngine *eng = bt->eng;
 	const DevModel &m = eng->dm;
-	size_t smem = (32 + (size_t)K0_MAXINF * m.Dq + (size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq) * sizeof(double);
-	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_set_param, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int P = bt->db.P;
-	k_set_param<<<P, K0_THREADS, smem, bt->stream>>>(m, bt->db);
+	k_set_param<<<P, K0_THREADS, 0, bt->stream>>>(m, bt->db);
+	{
+		/* beta: one warp per particle, as many particles per CTA as keep >= 4 CTAs' worth of shared memory per SM */
+		const size_t per = ((size_t)K0_MAXINF * m.Dq + (size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq) * sizeof(double);
+		int nw = (int)std::max<size_t>(1, std::min<size_t>(K0_BETA_WARPS, (48 * 1024) / per));
+		const size_t smem = per * nw;
+		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_beta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_beta<<<(P + nw - 1) / nw, nw * 32, smem, bt->stream>>>(m, bt->db, nw);
+		eng->launches++;
+	}
 	k_areafactor_fill<<<dim3(P, (m.A + 127) / 128), 128, 0, bt->stream>>>(m, bt->db);
 	k_areafactor_sum<<<(P + 63) / 64, 64, 0, bt->stream>>>(m, bt->db);
 	size_t naf = (size_t)m.period * m.A;
@@ -531,11 +547,13 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	} else {
 		long long ntile = (long long)P * m.A;
 		int grid = (int)std::min<long long>(eng->coop_grid, (ntile + eng->nwarp - 1) / eng->nwarp);
-		/* dynamic tile scheduling: about 32 grabs per warp and step, at most 8 tiles per grab */
+		/* dynamic tile scheduling: about 8 grabs per warp and sweep over the particles, at most 16 tiles
+		 * per grab and at least 4 grabs per particle-step */
 		const long long nw = (long long)grid * eng->nwarp;
-		a.chunk = (int)std::max<long long>(1, std::min<long long>(8, ntile / (nw * 32)));
+		a.chunk = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, m.A / 4), ntile / (nw * 8)));
 		if (const char *ch = getenv("BEEP_TRAJ_CHUNK")) a.chunk = std::max(1, atoi(ch));
-		CU(cudaMemsetAsync(bt->db.sched, 0, (size_t)m.T * sizeof(int), bt->stream));
+		k_sched_init<<<(P + 127) / 128, 128, 0, bt->stream>>>(bt->db.sched, P, ti);
+		eng->launches++;
 		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
 	}
 	eng->launches++;

@@ -45,31 +45,47 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ double ntime_elem(const DevModel &m, const double *ds, int t, int a, int b, double n0)
 {
 	double x = n0;
-	for (int mm = 0; mm < m.nmm; mm++) {
-		int k = m.mm_cnt[mm * m.G + a] + m.mm_cnt[mm * m.G + b];
-		if (k > 0) {
-			double f = ds[m.mm_spline[mm] * m.T + t];
-			for (; k > 0; k--) x *= f;
-		}
-	}
+	const int e = a * m.G + b;
+	const double *dst = ds + t;
+	for (int q = m.mm_prog_off[e], q1 = m.mm_prog_off[e + 1]; q < q1; q++) x *= dst[m.mm_prog[q] * m.T];
 	return x;
+}
+
+/* true when no spline that modifies the age matrix changes value from step t-1 to step t:
+ * Ntime[t] is then Ntime[t-1] bit for bit (lanes share the work; warp-uniform result) */
+__device__ __forceinline__ bool ntime_same(const DevModel &m, const double *ds, int t, int lane)
+{
+	int ch = 0;
+	for (int mm = lane; mm < m.nmm; mm += 32) { const double *q = ds + m.mm_spline[mm] * m.T + t; if (q[0] != q[-1]) ch = 1; }
+	return !__any_sync(0xffffffffu, ch);
+}
+
+/* the warp's copy of Ntime[t] (rows padded to Gs like n0r; the padding is zero), rebuilt from the
+ * base matrix at the first step and wherever a modifying spline moved */
+__device__ __forceinline__ void ntime_refresh(const DevModel &m, const double *ds, int t, int t0, const double *n0r, double *nt, int Gs, int lane)
+{
+	if (t != t0 && ntime_same(m, ds, t, lane)) return;
+	__syncwarp();
+	for (int i = lane; i < m.G * Gs; i += 32) {
+		const int r = i / Gs, k = i - r * Gs;
+		nt[i] = (k < m.G) ? ntime_elem(m, ds, t, r, k, n0r[i]) : 0.0;
+	}
+	__syncwarp();
 }
 
 #define K0_THREADS 128
 #define K0_MAXINF 8
+#define K0_BETA_WARPS 8
 
-/* dynamic smem: 32 + K0_MAXINF*Dq + Dq*(Dq+1) + 2*Dq doubles */
 __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b)
 {
-	extern __shared__ double sm[];
 	const int p = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-	const int T = m.T, A = m.A, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
+	const int T = m.T, J = m.J, D = m.D;
 	const double *theta = b.theta + (size_t)p * m.nparam;
 	double *pd = b.pd + (size_t)p * m.nparam;
 	double *transrate = b.transrate + (size_t)p * J * D;
 	double *ds = b.disc_spline + (size_t)p * m.nspline * T;
 	double *sus = b.sus + (size_t)p * D;
-	double *betaR = b.betaR + (size_t)p * S * m.nR * T;
 	double *infco = b.infco + (size_t)p * m.C;
 
 	/* model.cc:2685-2695 dirichlet_correct */
@@ -147,132 +163,145 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		double *etab = b.etab + (size_t)p * m.nefoi * T;
 		for (int i = tid; i < m.nefoi * T; i += nth) { const int ie = i / T, t = i - ie * T; etab[i] = ds[m.efoi_spline_ref[ie] * T + t] / m.popsize; }
 	}
+}
 
-	/* model.cc:1318-1362 calculate_beta_from_R.  The next-generation matrix NGM = F V^-1
-	 * (model.cc:2485-2576): V is block diagonal in dp, so only column (state 0, dp = i) of the
-	 * dp = i block of V^-1 contributes to NGM[q][i]; the blocks are inverted by the reference's
-	 * Gauss-Jordan (matrix.cc:703-765) and the terms are accumulated in the reference's order.
-	 * The dominant eigenvalue is the reference's power iteration (matrix.cc:1139-1220), started
-	 * from the flat vector and warm-started from solve to solve as the reference does -- one warp,
-	 * every reduction in the oracle's sequential order, so beta is bit-identical to the oracle's. */
-	{
-		const int warp = tid >> 5, lane = tid & 31;
-		const int ninf = m.ninf;
-		double *vinv0 = sm + 32;                            /* [ninf][Dq] column 0 of each block inverse, per strain */
-		double *ngm = vinv0 + K0_MAXINF * Dq, *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
-		if (warp == 0) for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
-		for (int st = 0; st < S; st++) {
-			__syncthreads();
-			for (int dp = tid; dp < Dq; dp += nth) {
-				double V[K0_MAXINF * K0_MAXINF], inv[K0_MAXINF * K0_MAXINF];
-				for (int i = 0; i < ninf * ninf; i++) { V[i] = 0; inv[i] = 0; }
-				for (int i = 0; i < ninf; i++) inv[i * ninf + i] = 1;
-				for (int tr = 0; tr < J; tr++) {
-					int from = m.inf_ref[m.trans_from[tr]], to = m.inf_ref[m.trans_to[tr]];
-					if (from >= 0) {
-						double rate = transrate[tr * D + st * Dq + dp];
-						V[from * ninf + from] += rate;
-						if (to >= 0) V[to * ninf + from] -= rate;
-					}
+/* model.cc:1318-1362 calculate_beta_from_R, ONE WARP per particle (K0_BETA_WARPS particles per CTA:
+ * the eigenvalue iteration is a sequential chain per particle, so the machine is filled with
+ * particles, not with threads of one particle).  The next-generation matrix NGM = F V^-1
+ * (model.cc:2485-2576): V is block diagonal in dp, so only column (state 0, dp = i) of the
+ * dp = i block of V^-1 contributes to NGM[q][i]; the blocks are inverted by the reference's
+ * Gauss-Jordan (matrix.cc:703-765) and the terms are accumulated in the reference's order.
+ * The dominant eigenvalue is the reference's power iteration (matrix.cc:1139-1220), started
+ * from the flat vector and warm-started from solve to solve as the reference does -- every
+ * reduction in the oracle's sequential order, so beta is bit-identical to the oracle's.
+ * dynamic smem per warp: K0_MAXINF*Dq + Dq*(Dq+1) + 2*Dq doubles */
+__global__ void __launch_bounds__(K0_BETA_WARPS * 32) k_beta(DevModel m, DevBatch b, int nwarp)
+{
+	extern __shared__ double sm[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int p = blockIdx.x * nwarp + warp;
+	if (p >= b.P) return;
+	const int T = m.T, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
+	const double *pd = b.pd + (size_t)p * m.nparam;
+	const double *transrate = b.transrate + (size_t)p * J * D;
+	const double *ds = b.disc_spline + (size_t)p * m.nspline * T;
+	const double *sus = b.sus + (size_t)p * D;
+	double *betaR = b.betaR + (size_t)p * S * m.nR * T;
+	const int ninf = m.ninf;
+	double *vinv0 = sm + (size_t)warp * (K0_MAXINF * Dq + Dq * (Dq + 1) + 2 * Dq);   /* [ninf][Dq] column 0 of each block inverse, per strain */
+	double *ngm = vinv0 + K0_MAXINF * Dq, *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
+	for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
+	for (int st = 0; st < S; st++) {
+		__syncwarp();
+		for (int dp = lane; dp < Dq; dp += 32) {
+			double V[K0_MAXINF * K0_MAXINF], inv[K0_MAXINF * K0_MAXINF];
+			for (int i = 0; i < ninf * ninf; i++) { V[i] = 0; inv[i] = 0; }
+			for (int i = 0; i < ninf; i++) inv[i * ninf + i] = 1;
+			for (int tr = 0; tr < J; tr++) {
+				int from = m.inf_ref[m.trans_from[tr]], to = m.inf_ref[m.trans_to[tr]];
+				if (from >= 0) {
+					double rate = transrate[tr * D + st * Dq + dp];
+					V[from * ninf + from] += rate;
+					if (to >= 0) V[to * ninf + from] -= rate;
 				}
-				for (int ii = 0; ii < ninf; ii++) {
-					double r = V[ii * ninf + ii];
-					for (int i = ii; i < ninf; i++) V[ii * ninf + i] /= r;
-					for (int i = 0; i <= ii; i++) inv[ii * ninf + i] /= r;
-					for (int jj = ii + 1; jj < ninf; jj++) {
-						double rr = V[jj * ninf + ii];
-						if (rr != 0) {
-							for (int i = ii; i < ninf; i++) V[jj * ninf + i] -= rr * V[ii * ninf + i];
-							for (int i = 0; i <= ii; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
-						}
-					}
-				}
-				for (int ii = ninf - 1; ii > 0; ii--)
-					for (int jj = ii - 1; jj >= 0; jj--) {
-						double rr = V[jj * ninf + ii];
-						if (rr != 0) for (int i = 0; i < ninf; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
-					}
-				for (int is = 0; is < ninf; is++) vinv0[is * Dq + dp] = inv[is * ninf + 0];
 			}
-			__syncthreads();
-			if (warp == 0) for (int ir = 0; ir < m.nR; ir++) {
-				const int spl = m.R_spline_ref[ir];
-				const double *dist = m.R_dist + (size_t)ir * Dq;
-				const double rfac = pd[m.strain_Rfactor_param[st]];
-				double *out = betaR + ((size_t)st * m.nR + ir) * T;
-				__syncwarp();
-				double ratio = 0;
-				for (int t = 0; t < T; t++) {
-					bool recompute = (t == 0);
-					if (!recompute && m.nmm > 0) {
-						/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY */
-						int ch = 0;
-						for (int i = lane; i < G * G; i += 32) {
-							int aa = i / G, bb = i - aa * G;
-							double n0 = m.N0[i];
-							double x = ntime_elem(m, ds, t, aa, bb, n0), y = ntime_elem(m, ds, t - 1, aa, bb, n0);
-							if (y < x - 0.00000001 || y > x + 0.00000001) ch = 1;
-						}
-						recompute = __any_sync(FULLMASK, ch);
+			for (int ii = 0; ii < ninf; ii++) {
+				double r = V[ii * ninf + ii];
+				for (int i = ii; i < ninf; i++) V[ii * ninf + i] /= r;
+				for (int i = 0; i <= ii; i++) inv[ii * ninf + i] /= r;
+				for (int jj = ii + 1; jj < ninf; jj++) {
+					double rr = V[jj * ninf + ii];
+					if (rr != 0) {
+						for (int i = ii; i < ninf; i++) V[jj * ninf + i] -= rr * V[ii * ninf + i];
+						for (int i = 0; i <= ii; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
 					}
-					if (recompute) {
-						for (int i = lane; i < Dq * Dq; i += 32) {
-							int q = i / Dq, k = i - q * Dq;
-							int aq = m.dp_age[q], ak = m.dp_age[k];
-							double nt = ntime_elem(m, ds, t, aq, ak, m.N0[aq * G + ak]);
-							double sum = 0;
-							for (int is = 0; is < ninf; is++) {
-								double inf = pd[m.comp_inf_param[m.inf_state[is]]];
-								if (inf != 0) sum += dist[q] * sus[Dq * st + q] * inf * nt * vinv0[is * Dq + k];
-							}
-							ngm[q * (Dq + 1) + k] = sum;
+				}
+			}
+			for (int ii = ninf - 1; ii > 0; ii--)
+				for (int jj = ii - 1; jj >= 0; jj--) {
+					double rr = V[jj * ninf + ii];
+					if (rr != 0) for (int i = 0; i < ninf; i++) inv[jj * ninf + i] -= rr * inv[ii * ninf + i];
+				}
+			for (int is = 0; is < ninf; is++) vinv0[is * Dq + dp] = inv[is * ninf + 0];
+		}
+		__syncwarp();
+		for (int ir = 0; ir < m.nR; ir++) {
+			const int spl = m.R_spline_ref[ir];
+			const double *dist = m.R_dist + (size_t)ir * Dq;
+			const double rfac = pd[m.strain_Rfactor_param[st]];
+			double *out = betaR + ((size_t)st * m.nR + ir) * T;
+			__syncwarp();
+			double ratio = 0;
+			for (int t = 0; t < T; t++) {
+				bool recompute = (t == 0);
+				if (!recompute && m.nmm > 0 && !ntime_same(m, ds, t, lane)) {
+					/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY */
+					int ch = 0;
+					for (int i = lane; i < G * G; i += 32) {
+						int aa = i / G, bb = i - aa * G;
+						double n0 = m.N0[i];
+						double x = ntime_elem(m, ds, t, aa, bb, n0), y = ntime_elem(m, ds, t - 1, aa, bb, n0);
+						if (y < x - 0.00000001 || y > x + 0.00000001) ch = 1;
+					}
+					recompute = __any_sync(FULLMASK, ch);
+				}
+				if (recompute) {
+					for (int i = lane; i < Dq * Dq; i += 32) {
+						int q = i / Dq, k = i - q * Dq;
+						int aq = m.dp_age[q], ak = m.dp_age[k];
+						double nt = ntime_elem(m, ds, t, aq, ak, m.N0[aq * G + ak]);
+						double sum = 0;
+						for (int is = 0; is < ninf; is++) {
+							double inf = pd[m.comp_inf_param[m.inf_state[is]]];
+							if (inf != 0) sum += dist[q] * sus[Dq * st + q] * inf * nt * vinv0[is * Dq + k];
+						}
+						ngm[q * (Dq + 1) + k] = sum;
+					}
+					__syncwarp();
+					double ev = 0;
+					for (unsigned loop = 0;; loop++) {
+						for (int q = lane; q < Dq; q += 32) {
+							double acc = 0;
+							for (int k = 0; k < Dq; k++) acc += ngm[q * (Dq + 1) + k] * vec[k];
+							vec2[q] = acc;
 						}
 						__syncwarp();
-						double ev = 0;
-						for (unsigned loop = 0;; loop++) {
-							for (int q = lane; q < Dq; q += 32) {
-								double acc = 0;
-								for (int k = 0; k < Dq; k++) acc += ngm[q * (Dq + 1) + k] * vec[k];
-								vec2[q] = acc;
-							}
-							__syncwarp();
-							double sum = 0;
-							for (int k = 0; k < Dq; k++) sum += vec2[k];          /* every lane, the oracle's order */
-							const double ev_new = sum;
-							int bad = 0;
-							double lim = 100 * 0.000000000000001;
-							if (loop > 100) lim *= 10;
-							if (loop > 1000) lim *= 10;
-							__syncwarp();
-							for (int q = lane; q < Dq; q += 32) {
-								double v2 = vec2[q] / sum;
-								double dif = v2 - vec[q];
-								if (dif > lim || dif < -lim) bad = 1;
-								vec2[q] = v2;
-							}
-							bool conv = false;
-							if (loop % 10 == 0) {
-								bool evok = (ev_new - ev > -lim && ev_new - ev < lim);
-								conv = evok && !__any_sync(FULLMASK, bad);
-							}
-							__syncwarp();
-							if (conv) break;                    /* as the reference: keep the pre-update ev and vec */
-							for (int q = lane; q < Dq; q += 32) vec[q] = vec2[q];
-							__syncwarp();
-							ev = ev_new;
-							if (loop + 1 > 10000) break;
+						double sum = 0;
+						for (int k = 0; k < Dq; k++) sum += vec2[k];          /* every lane, the oracle's order */
+						const double ev_new = sum;
+						int bad = 0;
+						double lim = 100 * 0.000000000000001;
+						if (loop > 100) lim *= 10;
+						if (loop > 1000) lim *= 10;
+						__syncwarp();
+						for (int q = lane; q < Dq; q += 32) {
+							double v2 = vec2[q] / sum;
+							double dif = v2 - vec[q];
+							if (dif > lim || dif < -lim) bad = 1;
+							vec2[q] = v2;
 						}
-						ratio = ev;
+						bool conv = false;
+						if (loop % 10 == 0) {
+							bool evok = (ev_new - ev > -lim && ev_new - ev < lim);
+							conv = evok && !__any_sync(FULLMASK, bad);
+						}
+						__syncwarp();
+						if (conv) break;                    /* as the reference: keep the pre-update ev and vec */
+						for (int q = lane; q < Dq; q += 32) vec[q] = vec2[q];
+						__syncwarp();
+						ev = ev_new;
+						if (loop + 1 > 10000) break;
 					}
-					if (m.nmm == 0) {
-						/* age matrix constant in time: one eigenvalue serves every step */
-						for (int tt = lane; tt < T; tt += 32) out[tt] = rfac * ds[spl * T + tt] / ratio;
-						break;
-					}
-					if (lane == 0) out[t] = rfac * ds[spl * T + t] / ratio;
+					ratio = ev;
 				}
-				__syncwarp();
+				if (m.nmm == 0) {
+					/* age matrix constant in time: one eigenvalue serves every step */
+					for (int tt = lane; tt < T; tt += 32) out[tt] = rfac * ds[spl * T + tt] / ratio;
+					break;
+				}
+				if (lane == 0) out[t] = rfac * ds[spl * T + t] / ratio;
 			}
+			__syncwarp();
 		}
 	}
 }
@@ -332,6 +361,13 @@ __global__ void k_pop_reset(DevModel m, DevBatch b)
 	}
 }
 
+/* particle-step scheduler state: every particle stands at step ti with no tile handed out */
+__global__ void k_sched_init(unsigned long long *sched, int P, int ti)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < P) { sched[(size_t)p * 16] = (unsigned long long)(unsigned)ti << 32; sched[(size_t)p * 16 + 1] = 0; }
+}
+
 __global__ void k_zero(double *x, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = 0;
@@ -361,6 +397,19 @@ __device__ __forceinline__ void sts16(unsigned a, unsigned v) { asm volatile("st
 __device__ __forceinline__ double2 lds128(unsigned a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts128(unsigned a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
 
+/* gpu-scope primitives of the particle-step scheduler.  Mutable data that crosses warps (dinf, pop_cur,
+ * the scheduler words) is only ever read at L2 (ld.relaxed.gpu / cp.async.cg), so publishing needs a
+ * release (MEMBAR.GPU before the atomic) but no acquire fence -- which would invalidate the whole L1
+ * (CCTL.IVALL) and with it the read-only model tables. */
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ double ld_l2(const double *p) { double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ unsigned long long atom_add_release_u64(unsigned long long *p, unsigned long long x) { unsigned long long v; asm volatile("atom.add.release.gpu.global.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(x) : "memory"); return v; }
+__device__ __forceinline__ void red_add_release_u64(unsigned long long *p, unsigned long long x) { asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long x) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long x) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
+/* dinf lives in global memory (grid flavour: read at L2) or in shared memory (generic pointer) */
+template <bool DGLOB> __device__ __forceinline__ double ld_dinf(const double *p) { return DGLOB ? ld_l2(p) : *p; }
+
 /* per-warp scratch, all in shared memory (layout: traj_sm_layout, dev_types.h) */
 struct TileSm {
 	double *pop;      /* [CDp] population of the tile                                   */
@@ -371,7 +420,10 @@ struct TileSm {
 	double *Iv;       /* [Gs]  infectivity vector before the age matvec, zero padded   */
 	unsigned short *ae; /* [J*D] cell index of the active cells, compacted             */
 	Nbr *nbr;         /* [32]  staged entries of the transposed mixing matrix          */
-	const double *N0R;     /* [G][Gs] base age matrix, padded rows (CTA shared)         */
+	const double *N0R;     /* [G][Gs] age matrix, padded rows: the base matrix N0 (CTA shared), or the warp's
+	                          own Ntime of the current step when it caches it (SYNC_NONE) */
+	bool ntfly;            /* N0R is the base matrix and the model modifies it in time: apply
+	                          model.cc:1254-1285 element by element                      */
 	const unsigned *ctab;  /* [J*D] packed cell table (CTA shared)                      */
 	int Gs;
 };
@@ -449,7 +501,7 @@ __device__ __forceinline__ void tile_dinf(const DevModel &m, const double *infco
  *   4. observations, population update and infectivity, visiting only the
  *      transitions that had events.
  * KEEP = false compiles out every trajectory store (ABC-SMC / particle-filter use). */
-template <int MODE, bool KEEP, bool LATEWAIT>
+template <int MODE, bool KEEP, bool LATEWAIT, bool DGLOB>
 __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &tc, const int t, const int tday, const int lane, const TileSm &sm,
                                               const double *dinf_cur, double *dinf_nxt, const int Ad, const int ci)
 {
@@ -501,10 +553,10 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 #pragma unroll 2
 				for (int j = 0; j < cnt; j++) {
 					const double2 raw = ((const double2 *)sm.nbr)[j];            /* one 16-byte broadcast: (weight, byte offset) */
-					Imap += *(const double *)(dcl + (unsigned)__double2loint(raw.y)) * raw.x;
+					Imap += ld_dinf<DGLOB>((const double *)(dcl + (unsigned)__double2loint(raw.y))) * raw.x;
 				}
 			}
-			const double Idiag = dc[ci * G + ll] * tc.diag;
+			const double Idiag = ld_dinf<DGLOB>(dc + ci * G + ll) * tc.diag;
 			double nv = 0;                                 /* NMI of age `lane` */
 			if (G == 1) {
 				nv = Idiag * (d + tc.fac * omd) + Imap * d;
@@ -517,7 +569,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 					__syncwarp();
 					if (lane < G) {
 						double sum = 0;
-						if (m.nmm == 0) {
+						if (!sm.ntfly) {
 							const double2 *row = (const double2 *)(sm.N0R + lane * sm.Gs);
 							const double2 *iv2 = (const double2 *)sm.Iv;
 							const int h = sm.Gs >> 1;
@@ -725,7 +777,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 			if (trmask & tc.infmask) tile_dinf(m, tc.infco, tc.il, pop, dinf_nxt + ci * G, Ad * G, lane);
 			else if (lane < G)
 #pragma unroll 1
-				for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = dinf_cur[(st * Ad + ci) * G + lane];
+				for (int st = 0; st < S; st++) dinf_nxt[(st * Ad + ci) * G + lane] = ld_dinf<DGLOB>(dinf_cur + (st * Ad + ci) * G + lane);
 		}
 	}
 	__syncwarp();
@@ -738,10 +790,10 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
  * Same operations in the same order as tile_step (hence as the oracle); the scan is branch-free:
  * the cell table is padded to a multiple of 32 with never-firing cells and crate[] holds the
  * per-cell multiplier (rate, or susceptibility for the infection transition, 0 otherwise). */
-template <int MODE, bool KEEP, bool LATEWAIT>
+template <int MODE, bool KEEP, bool LATEWAIT, bool DGLOB>
 __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int p, const int c, const int t, const int tday, const int lane,
                                                    const unsigned wb, const unsigned pa, const unsigned ca,
-                                                   double *dbase, const size_t dflip, const int ci)
+                                                   double *dbase, const size_t dflip, const int ci, const unsigned n0_a, const bool ntfly)
 {
 	/* Loop-carried state is (p, c) and three shared addresses: every table pointer is re-derived from
 	 * the kernel parameters where it is used, so that nothing else stays live across the phases. */
@@ -773,10 +825,10 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 #pragma unroll 5
 			for (int j = 0; j < cnt; j++) {
 				const double2 raw = lds128(nbr_a + j * 16);                  /* one 16-byte broadcast: (weight, byte offset) */
-				Imap += *(const double *)(dcl + (unsigned)__double2loint(raw.y)) * raw.x;
+				Imap += ld_dinf<DGLOB>((const double *)(dcl + (unsigned)__double2loint(raw.y))) * raw.x;
 			}
 		}
-		const double Idiag = dinf_cur[ci * G + ll] * tc.diag;
+		const double Idiag = ld_dinf<DGLOB>(dinf_cur + ci * G + ll) * tc.diag;
 		const double Iv = (Idiag + Imap) * d + tc.fac * Idiag * omd;
 		double nv = 0;
 		/* a neighbourhood without infectious individuals has I = 0, hence NMI = 0 exactly */
@@ -785,8 +837,8 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 			__syncwarp();
 			if (lane < G) {
 				double sum = 0;
-				const unsigned row = ca + L.n0 * 8 + lane * (L.Gs * 8);
-				if (m.nmm == 0) {
+				const unsigned row = n0_a + lane * (L.Gs * 8);
+				if (!ntfly) {
 					const int h = L.Gs >> 1;
 #pragma unroll 2
 					for (int k = 0; k < h; k++) { const double2 n2 = lds128(row + k * 16), v2 = lds128(iv_a + k * 16); sum += n2.x * v2.x; sum += n2.y * v2.y; }
@@ -971,7 +1023,7 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 #pragma unroll 1
 				for (int k = 1; k <= ninf; k++) { const int co = il[k]; sum += infco[co] * lds64(pa + (co * G + lane) * 8); }
 				*out = sum;
-			} else *out = dinf_cur[ci * G + lane];
+			} else *out = ld_dinf<DGLOB>(dinf_cur + ci * G + lane);
 		}
 	}
 	__syncwarp();
@@ -1034,8 +1086,13 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 	double *sm = smraw + L.common;
 
 	if (SYNC == SYNC_NONE) {
-		const int per = CDp + L.work + BEEP_EVEN(2 * S * G);
+		/* a warp keeps its tile for the whole trajectory, so it also keeps Ntime: the modified age
+		 * matrix is rebuilt only at steps where a modifying spline changes value */
+		const int ntsz = (m.nmm > 0) ? G * L.Gs : 0;
+		const int per = CDp + L.work + BEEP_EVEN(2 * S * G) + ntsz;
 		double *pop = sm + (size_t)warp * per;
+		double *ntw = ntsz ? pop + CDp + L.work + BEEP_EVEN(2 * S * G) : nullptr;
+		const unsigned n0_a = launder(smem_addr(ntw ? ntw : smraw + L.n0));
 		{
 			TileSm ts0;
 			work_init(ts0, L, pop + CDp, lane);
@@ -1052,17 +1109,22 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		if (fast) {
 			const unsigned wb = launder(smem_addr(pop + CDp)), pa = launder(smem_addr(pop));
 #pragma unroll 1
-			for (int t = a.ti; t < a.tf; t++) tile_step_fast<MODE, KEEP, false>(a, p, c, t, t / m.spu, lane, wb, pa, ca, dinf, (size_t)(S * G), 0);
+			for (int t = a.ti; t < a.tf; t++) {
+				if (ntw) ntime_refresh(m, b.disc_spline + (size_t)p * (m.nspline * m.T), t, a.ti, smraw + L.n0, ntw, L.Gs, lane);
+				tile_step_fast<MODE, KEEP, false, false>(a, p, c, t, t / m.spu, lane, wb, pa, ca, dinf, (size_t)(S * G), 0, n0_a, false);
+			}
 		} else {
 			TileSm ts;
-			ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = pop;
+			ts.N0R = ntw ? ntw : smraw + L.n0; ts.ntfly = false; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = pop;
 			work_ptrs(ts, L, pop + CDp);
 			TileCtx tc;
 			tile_ctx_particle(a, p, tc);
 			tile_ctx_area(m.area_info[c], c, tc);
 #pragma unroll 1
-			for (int t = a.ti; t < a.tf; t++)
-				tile_step<MODE, KEEP, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+			for (int t = a.ti; t < a.tf; t++) {
+				if (ntw) ntime_refresh(m, tc.ds, t, a.ti, smraw + L.n0, ntw, L.Gs, lane);
+				tile_step<MODE, KEEP, false, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
+			}
 		}
 		for (int i = lane; i < CDp; i += 32) gp[i] = pop[i];
 	} else if (SYNC == SYNC_CTA) {
@@ -1084,15 +1146,15 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 			const int tday = t / m.spu;
 #pragma unroll 1
 			for (int c = warp; c < A; c += nwarp) {
-				if (fast) tile_step_fast<MODE, KEEP, false>(a, p, c, t, tday, lane, wb, pa0 + c * (CDp * 8), ca, dinf, (size_t)(S * A * G), c);
+				if (fast) tile_step_fast<MODE, KEEP, false, false>(a, p, c, t, tday, lane, wb, pa0 + c * (CDp * 8), ca, dinf, (size_t)(S * A * G), c, ca + L.n0 * 8, m.nmm != 0);
 				else {
 					TileSm ts;
-					ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popA + (size_t)c * CDp;
+					ts.N0R = smraw + L.n0; ts.ntfly = m.nmm != 0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popA + (size_t)c * CDp;
 					work_ptrs(ts, L, wk);
 					TileCtx tc;
 					tile_ctx_particle(a, p, tc);
 					tile_ctx_area(m.area_info[c], c, tc);
-					tile_step<MODE, KEEP, false>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
+					tile_step<MODE, KEEP, false, false>(a, tc, t, tday, lane, ts, dinf + (t & 1) * S * A * G, dinf + ((t + 1) & 1) * S * A * G, A, c);
 				}
 			}
 			__syncthreads();
@@ -1100,14 +1162,13 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		for (int i = threadIdx.x; i < A * CDp; i += blockDim.x) gp[i] = popA[i];
 	} else {
 		cg::grid_group grid = cg::this_grid();
-		constexpr int NB = BEEP_TRAJ_NBUF;
-		const int per = NB * CDp + L.work;
+		const int per = CDp + L.work;
 		double *popbuf = sm + (size_t)warp * per;
 		{
 			TileSm ts0;
-			work_init(ts0, L, popbuf + NB * CDp, lane);
+			work_init(ts0, L, popbuf + CDp, lane);
 		}
-		const unsigned wb = launder(smem_addr(popbuf + NB * CDp)), pa0 = launder(smem_addr(popbuf));
+		const unsigned wb = launder(smem_addr(popbuf + CDp)), pa0 = launder(smem_addr(popbuf));
 		const int ntile = b.P * A, nw = gridDim.x * nwarp, gw = blockIdx.x * nwarp + warp;   /* 32-bit: the launcher checks P*A < 2^30 */
 		const size_t dsz = (size_t)b.P * S * A * G, psz = (size_t)S * A * G;
 		const int nchunk = CDp >> 1;                    /* 16-byte chunks per tile */
@@ -1124,77 +1185,105 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 			__syncwarp();
 		}
 		grid.sync();
-		/* Per step the tiles are handed out dynamically, CH consecutive tiles per grab of the step's
-		 * counter, so that the grid barrier waits for the slowest tile rather than the slowest warp.
-		 * The population of a tile streams into shared memory by cp.async: with two buffers tile k+1
-		 * loads while tile k computes; with one buffer the copy is issued when the previous tile
-		 * retires and awaited after the force-of-infection phase, which does not read it. */
+		/* PARTICLE-STEP SCHEDULER.  Areas of one particle couple from step to step (Imap of step t+1
+		 * needs dinf of every source area after step t), particles never do.  So instead of a grid
+		 * barrier per step, each particle carries its own step barrier: sched[p] word 0 holds
+		 * (step << 32 | next tile); a warp grabs CH consecutive tiles of the particle it is on
+		 * with one 64-bit atomicAdd, works them, and adds them to word 1 (tiles completed) with
+		 * release semantics; the warp that completes the step's last tile resets word 1 and publishes
+		 * ((step + 1) << 32 | 0).  A warp that finds its particle exhausted (the step's last tiles
+		 * are in flight) moves on to the next particle, whose step is in full swing -- the tail of
+		 * one particle-step overlaps the head of another, and no warp waits for the grid.
+		 * The tile's population streams into shared memory by cp.async (awaited after the
+		 * force-of-infection phase, which does not read it) and is written back once per step. */
+		const int P = b.P;
+		int p = (int)(((long long)gw * P) / nw);        /* warps start spread over the particles */
+		int nmiss = 0;                                  /* consecutive particles without a tile to hand out */
+		int nfin = 0;                                   /* ... of which had finished their trajectory */
+		int nspin = 0;                                  /* idle rounds in a row: a scheduler that never hands out work traps */
+		unsigned long long v = 0;                       /* lane 0: the grab in hand */
+		bool have = false;                              /* v was grabbed ahead, during the previous chunk */
 #pragma unroll 1
-		for (int t = a.ti; t < a.tf; t++) {
-			const int tday = t / m.spu;
-			int *ctr = b.sched + t;
-			int grabbed = 0;
-			if (lane == 0) grabbed = atomicAdd(ctr, CH);
-			int base = __shfl_sync(FULLMASK, grabbed, 0);
-			if (base < ntile) {
-				const double *gp = b.pop_cur + (size_t)base * CDp;
+		while (true) {
+			unsigned long long *sp = b.sched + (size_t)p * 16;
+			if (!have) {
+				if (lane == 0) {
+					v = ld_relaxed_u64(sp);
+					if ((int)(v >> 32) < a.tf && (unsigned)v < (unsigned)A) v = atomicAdd(sp, (unsigned long long)CH);
+				}
+			}
+			have = false;
+			v = __shfl_sync(FULLMASK, v, 0);
+			const int t = (int)(v >> 32);
+			const unsigned idx = (unsigned)v;
+			if (t >= a.tf || idx >= (unsigned)A) {
+				/* nothing to take here: finished, or the step's last tiles are still in flight */
+				nmiss++;
+				if (t >= a.tf) nfin++;
+				if (nmiss >= P) {
+					if (nfin >= P) break;                   /* a full round of finished particles */
+					nmiss = 0; nfin = 0;
+					if (++nspin > 8000000) __trap();
+					__nanosleep(500);
+				}
+				if (++p == P) p = 0;
+				continue;
+			}
+			nmiss = 0; nfin = 0; nspin = 0;
+			const int c0 = (int)idx, c1 = (c0 + CH < A) ? c0 + CH : A;
+			{
+				const double *gp = b.pop_cur + ((size_t)p * A + c0) * CDp;
 #pragma unroll 1
 				for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gp + 2 * i);
 				cp_async_commit();
 			}
-			int kb = 0;
+			/* the next grab of this particle travels while this chunk is worked (a grab past the
+			 * step's last tile is a miss and only overshoots the tile field, reset with the step) */
+			unsigned long long vn = 0;
+			if (c1 < A) { have = true; if (lane == 0) vn = atomicAdd(sp, (unsigned long long)CH); }
+			const int tday = t / m.spu;
 #pragma unroll 1
-			while (base < ntile) {
-				const int cend = (base + CH < ntile) ? base + CH : ntile;
-				if (lane == 0) grabbed = atomicAdd(ctr, CH);        /* next chunk: the round trip hides behind this chunk's work */
-				int p, c;
-				tile_split(base, A, a.invA, p, c);
-#pragma unroll 1
-				for (int tile = base; tile < cend; tile++) {
-					int nxt = tile + 1;
-					if (nxt == cend) nxt = __shfl_sync(FULLMASK, grabbed, 0);
-					if (NB == 2) {
-						if (nxt < ntile) {
-							const double *gn = b.pop_cur + (size_t)nxt * CDp;
-							double *dst = popbuf + (kb ^ 1) * CDp;
-#pragma unroll 1
-							for (int i = lane; i < nchunk; i += 32) cp_async16(dst + 2 * i, gn + 2 * i);
-							cp_async_commit();
-							cp_async_wait<1>();
-						} else cp_async_wait<0>();
-						__syncwarp();
-					}
-					unsigned ev;
-					if (fast) ev = tile_step_fast<MODE, KEEP, NB == 1>(a, p, c, t, tday, lane, wb, pa0 + kb * (CDp * 8), ca, b.dinf + (size_t)p * psz, dsz, c);
-					else {
-						TileSm ts;
-						ts.N0R = smraw + L.n0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popbuf + kb * CDp;
-						work_ptrs(ts, L, popbuf + NB * CDp);
-						TileCtx tc;
-						tile_ctx_particle(a, p, tc);
-						tile_ctx_area(m.area_info[c], c, tc);
-						ev = tile_step<MODE, KEEP, NB == 1>(a, tc, t, tday, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * psz, b.dinf + ((t + 1) & 1) * dsz + (size_t)p * psz, A, c);
-					}
-					if (ev != 0 || S > 1) {
-						const double2 *s2 = (const double2 *)(popbuf + kb * CDp);
-						double2 *g2 = (double2 *)(b.pop_cur + (size_t)tile * CDp);
-#pragma unroll 1
-						for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
-					}
-					__syncwarp();
-					if (NB == 1) {
-						if (nxt < ntile) {
-							const double *gn = b.pop_cur + (size_t)nxt * CDp;
-#pragma unroll 1
-							for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gn + 2 * i);
-							cp_async_commit();
-						}
-					} else kb ^= 1;
-					if (++c == A) { c = 0; p++; }
+			for (int c = c0; c < c1; c++) {
+				unsigned ev;
+				if (fast) ev = tile_step_fast<MODE, KEEP, true, true>(a, p, c, t, tday, lane, wb, pa0, ca, b.dinf + (size_t)p * psz, dsz, c, ca + L.n0 * 8, m.nmm != 0);
+				else {
+					TileSm ts;
+					ts.N0R = smraw + L.n0; ts.ntfly = m.nmm != 0; ts.ctab = (const unsigned *)(smraw + L.ctab); ts.Gs = L.Gs; ts.pop = popbuf;
+					work_ptrs(ts, L, popbuf + CDp);
+					TileCtx tc;
+					tile_ctx_particle(a, p, tc);
+					tile_ctx_area(m.area_info[c], c, tc);
+					ev = tile_step<MODE, KEEP, true, true>(a, tc, t, tday, lane, ts, b.dinf + (t & 1) * dsz + (size_t)p * psz, b.dinf + ((t + 1) & 1) * dsz + (size_t)p * psz, A, c);
 				}
-				base = __shfl_sync(FULLMASK, grabbed, 0);
+				if (ev != 0 || S > 1) {
+					const double2 *s2 = (const double2 *)popbuf;
+					double2 *g2 = (double2 *)(b.pop_cur + ((size_t)p * A + c) * CDp);
+#pragma unroll 1
+					for (int i = lane; i < nchunk; i += 32) g2[i] = s2[i];
+				}
+				__syncwarp();
+				if (c + 1 < c1) {
+					const double *gn = b.pop_cur + ((size_t)p * A + c + 1) * CDp;
+#pragma unroll 1
+					for (int i = lane; i < nchunk; i += 32) cp_async16(popbuf + 2 * i, gn + 2 * i);
+					cp_async_commit();
+				}
 			}
-			grid.sync();
+			/* publish: the lanes' stores are ordered before lane 0's release by the warp barrier.
+			 * Completions are fire-and-forget REDs; the warp that took the step's LAST chunk closes the
+			 * step: it waits for the chunks still in flight (their warps never wait for anything, so
+			 * this ends), clears the counter and opens the next step. */
+			__syncwarp();
+			if (lane == 0) {
+				red_add_release_u64(sp + 1, (unsigned long long)(c1 - c0));
+				if (c1 == A) {
+					int spin = 0;
+					while (ld_relaxed_u64(sp + 1) != (unsigned long long)A) { if (++spin > 20000000) __trap(); __nanosleep(64); }
+					st_relaxed_u64(sp + 1, 0ull);
+					st_release_u64(sp, (unsigned long long)(unsigned)(t + 1) << 32);
+				}
+			}
+			v = vn;
 		}
 	}
 }

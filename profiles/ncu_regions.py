@@ -19,17 +19,23 @@ for r in rows:
         agg[cur][0] += sa; agg[cur][1] += ins; agg[cur][2] += thr; ti += ins; ts += sa
 print("instructions per tile-step: %.1f" % (ti / ntile))
 lines = open("beep_b200/csrc/kernels.cuh").read().split("\n")
-def find(pat):
-    for i, l in enumerate(lines):
-        if pat in l: return i + 1
+def find(pat, start=0):
+    for i in range(start, len(lines)):
+        if pat in lines[i]: return i + 1
     return None
-marks = [("tile_dinf", "tile_dinf(const DevModel &m, const double *infco"), ("(structs)", "/* per-warp scratch, all in shared"), ("pool+setup", "template <int MODE>\n"),
-         ("FOI", "/* 1. state.cc:547-578"), ("scan", "/* 2. scan:"), ("draw", "/* 3. draws on the dense"), ("trmask", "/* transitions with events, warp-wide"),
-         ("obs", "/* 4a. obsmodel"), ("keep_pop", "(b.flags & BEEP_KEEP_POP)) {"), ("update", "/* 4b. state.cc:460-485"), ("kernel", "/* CTA-shared tables at the front"), ("end", "/* K4  observation model")]
+# regions of the fast tile step (tile_step_fast) and of the kernel body
+f0 = find("__device__ __forceinline__ unsigned tile_step_fast(")
+marks = [("generic", "__device__ __forceinline__ unsigned tile_step("), ("fast:setup", None), ("fast:FOI", "/* 1. state.cc:547-578"), ("fast:scan", "/* 2. scan:"),
+         ("fast:draw", "/* 3. draws on the dense"), ("fast:trmask", "/* transitions with events, warp-wide"), ("fast:obs", "/* 4a. obsmodel"),
+         ("fast:update", "/* 4b. state.cc:460-485"), ("kernel", "/* tile index -> (particle, area)"), ("end", "/* K4  observation model")]
 pos = []
 for name, pat in marks:
-    ln = find(pat.split("\n")[0]) if name != "pool+setup" else find("__device__ __forceinline__ unsigned tile_step")
+    if name == "generic": ln = find(pat)
+    elif name == "fast:setup": ln = f0
+    elif name.startswith("fast:"): ln = find(pat, f0)
+    else: ln = find(pat, f0)
     pos.append((name, ln))
+pos = [("helpers", find("/* K1-K3  trajectory kernel"))] + pos
 def reg(f, a, b):
     s = [0, 0, 0]
     for (ff, l, _), (sa, i, th) in agg.items():
