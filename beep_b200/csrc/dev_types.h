@@ -80,6 +80,7 @@ struct DevModel {
 	int stochastic, siminf, itr, geo_spline, nR, nefoi, ninf, nmm, ncovar, nlevel, ndir;
 	int nslot, nsection, has_region, has_area_eff, age_fast, M_nnz;
 	int CDp;            /* C*D rounded up to even: tile stride of pop_cur (16-byte async copies) */
+	int mm_packed;      /* every element of the age matrix is hit by at most three spline factors (and nspline < 64) */
 	int obs_wide;       /* observations span many dp: reduce them warp-cooperatively */
 	double popsize, dt;
 
@@ -92,6 +93,9 @@ struct DevModel {
 	const int *region_effect_param, *area_effect_param, *covar_param; const double *covar_value;
 	const int *level_param, *level_map; const double *area_total_pop;
 	const double *N0, *N0T; const int *mm_spline, *mm_cnt; const int *dp_age;
+	const unsigned *mm_packp;           /* the same words laid out like the padded shared-memory matrix, [G][Gs] (padding: all unused) */
+	const unsigned *mm_pack;            /* [G*G] when mm_packed: up to three spline indices, one per byte (unused = nspline,
+	                                       whose staged value is 1.0), so that an element is n0 * f0 * f1 * f2 exactly */
 	const int *mm_prog_off, *mm_prog;   /* per element (a,b) of the age matrix: the splines that multiply it, in the
 	                                       reference's order (model.cc:1254-1285; a spline appears once per hit) */
 	const int *R_spline_ref, *area_rgrp; const double *R_dist; const int *strain_Rfactor_param;

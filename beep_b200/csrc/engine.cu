@@ -176,8 +176,22 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 				for (int k = cnt[(size_t)mm * G + a] + cnt[(size_t)mm * G + b]; k > 0; k--) prog.push_back(d->matmod_spline[mm]);
 			poff[(size_t)a * G + b + 1] = (int)prog.size();
 		}
+		std::vector<unsigned> pack((size_t)G * G, 0);
+		m.mm_packed = (m.nmm > 0 && m.nspline < 64) ? 1 : 0;
+		for (int e = 0; e < G * G; e++) {
+			const int n = poff[e + 1] - poff[e];
+			if (n > 3) m.mm_packed = 0;
+			unsigned w = 0;
+			for (int k = 0; k < 3; k++) w |= (unsigned)((k < n && n <= 3) ? prog[poff[e] + k] : m.nspline) << (8 * k);
+			pack[e] = w;
+		}
 		if (prog.empty()) prog.push_back(0);
-		UPV(mm_prog_off, poff); UPV(mm_prog, prog);
+		UPV(mm_prog_off, poff); UPV(mm_prog, prog); UPV(mm_pack, pack);
+		const int Gs = traj_sm_layout(G, m.J, m.D).Gs;
+		const unsigned unused = (unsigned)m.nspline * 0x010101u;
+		std::vector<unsigned> packp((size_t)G * Gs, unused);
+		for (int a = 0; a < G; a++) for (int b = 0; b < G; b++) packp[(size_t)a * Gs + b] = pack[(size_t)a * G + b];
+		UPV(mm_packp, packp);
 	}
 	UP(mm_spline, d->matmod_spline, m.nmm); UP(dp_age, d->dp_age, Dq);
 	m.age_fast = 1;
@@ -472,7 +486,7 @@ static int launch_set_param(BeepBatch *bt)
 	k_set_param<<<P, K0_THREADS, 0, bt->stream>>>(m, bt->db);
 	{
 		/* beta: one warp per particle, as many particles per CTA as keep >= 4 CTAs' worth of shared memory per SM */
-		const size_t per = ((size_t)K0_MAXINF * m.Dq + (size_t)m.Dq * (m.Dq + 1) + 2 * m.Dq) * sizeof(double);
+		const size_t per = k_beta_smem(m.Dq, m.G, m.nspline, m.nmm) * sizeof(double);
 		int nw = (int)std::max<size_t>(1, std::min<size_t>(K0_BETA_WARPS, (48 * 1024) / per));
 		const size_t smem = per * nw;
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_beta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

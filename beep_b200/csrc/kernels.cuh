@@ -60,17 +60,54 @@ __device__ __forceinline__ bool ntime_same(const DevModel &m, const double *ds, 
 	return !__any_sync(0xffffffffu, ch);
 }
 
+/* the step's spline values staged for the packed factor programs: fv[sp] = spline sp at step t, fv[nspline] = 1 */
+__device__ __forceinline__ void ntime_stage(const DevModel &m, const double *ds, int t, double *fv, int lane)
+{
+	for (int sp = lane; sp <= m.nspline; sp += 32) fv[sp] = (sp < m.nspline) ? ds[sp * m.T + t] : 1.0;
+	__syncwarp();
+}
+/* element e = a*G+b of Ntime from the staged values: n0 * f0 * f1 * f2 (multiplying by the 1.0 of an unused slot is exact) */
+__device__ __forceinline__ double ntime_packed(const unsigned w, const double *fv, double n0)
+{
+	return n0 * fv[w & 255u] * fv[(w >> 8) & 255u] * fv[(w >> 16) & 255u];
+}
+
 /* the warp's copy of Ntime[t] (rows padded to Gs like n0r; the padding is zero), rebuilt from the
- * base matrix at the first step and wherever a modifying spline moved */
-__device__ __forceinline__ void ntime_refresh(const DevModel &m, const double *ds, int t, int t0, const double *n0r, double *nt, int Gs, int lane)
+ * base matrix at the first step and wherever a modifying spline moved.  fv: nspline+1 doubles of
+ * warp scratch (used when the model's factor programs are packed) */
+__device__ __forceinline__ void ntime_refresh(const DevModel &m, const double *ds, int t, int t0, const double *n0r, double *nt, int Gs, double *fv, int lane)
 {
 	if (t != t0 && ntime_same(m, ds, t, lane)) return;
 	__syncwarp();
-	for (int i = lane; i < m.G * Gs; i += 32) {
-		const int r = i / Gs, k = i - r * Gs;
-		nt[i] = (k < m.G) ? ntime_elem(m, ds, t, r, k, n0r[i]) : 0.0;
+	if (m.mm_packed) {
+		/* branch-free over the padded layout: padding has n0 = 0 and multiplies by the staged 1.0 */
+		ntime_stage(m, ds, t, fv, lane);
+		const unsigned fa = (unsigned)__cvta_generic_to_shared(fv), na = (unsigned)__cvta_generic_to_shared(n0r), ta = (unsigned)__cvta_generic_to_shared(nt);
+		const int n = m.G * Gs;
+#pragma unroll 2
+		for (int i = lane; i < n; i += 32) {
+			const unsigned w = m.mm_packp[i];
+			double x, f0, f1, f2;
+			asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(na + i * 8));
+			asm volatile("ld.shared.f64 %0, [%1];" : "=d"(f0) : "r"(fa + ((w & 255u) << 3)));
+			asm volatile("ld.shared.f64 %0, [%1];" : "=d"(f1) : "r"(fa + ((w >> 5) & 0x7f8u)));
+			asm volatile("ld.shared.f64 %0, [%1];" : "=d"(f2) : "r"(fa + ((w >> 13) & 0x7f8u)));
+			x = x * f0 * f1 * f2;
+			asm volatile("st.shared.f64 [%0], %1;" ::"r"(ta + i * 8), "d"(x) : "memory");
+		}
+	} else {
+		for (int i = lane; i < m.G * Gs; i += 32) {
+			const int r = i / Gs, k = i - r * Gs;
+			nt[i] = (k < m.G) ? ntime_elem(m, ds, t, r, k, n0r[i]) : 0.0;
+		}
 	}
 	__syncwarp();
+}
+
+/* per-warp shared memory of k_beta in doubles: vinv0[K0_MAXINF][Dq] ngm[Dq][Dq+1] vec[Dq] vec2[Dq] ntc[G*G] fv[nspline+1] */
+__host__ __device__ inline size_t k_beta_smem(int Dq, int G, int nspline, int nmm)
+{
+	return (size_t)8 * Dq + (size_t)Dq * (Dq + 1) + 2 * Dq + (nmm > 0 ? (size_t)G * G + nspline + 1 : 0);
 }
 
 #define K0_THREADS 128
@@ -188,8 +225,10 @@ __global__ void __launch_bounds__(K0_BETA_WARPS * 32) k_beta(DevModel m, DevBatc
 	const double *sus = b.sus + (size_t)p * D;
 	double *betaR = b.betaR + (size_t)p * S * m.nR * T;
 	const int ninf = m.ninf;
-	double *vinv0 = sm + (size_t)warp * (K0_MAXINF * Dq + Dq * (Dq + 1) + 2 * Dq);   /* [ninf][Dq] column 0 of each block inverse, per strain */
+	double *vinv0 = sm + (size_t)warp * k_beta_smem(Dq, G, m.nspline, m.nmm);   /* [ninf][Dq] column 0 of each block inverse, per strain */
 	double *ngm = vinv0 + K0_MAXINF * Dq, *vec = ngm + Dq * (Dq + 1), *vec2 = vec + Dq;
+	double *ntc = vec2 + Dq;                             /* [G*G] Ntime of the last step that was evaluated */
+	double *fv = ntc + G * G;                            /* [nspline+1] staged spline values */
 	for (int i = lane; i < Dq; i += 32) vec[i] = 1.0 / Dq;
 	for (int st = 0; st < S; st++) {
 		__syncwarp();
@@ -234,22 +273,27 @@ __global__ void __launch_bounds__(K0_BETA_WARPS * 32) k_beta(DevModel m, DevBatc
 			double ratio = 0;
 			for (int t = 0; t < T; t++) {
 				bool recompute = (t == 0);
-				if (!recompute && m.nmm > 0 && !ntime_same(m, ds, t, lane)) {
-					/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY */
+				if (m.nmm > 0 && (t == 0 || !ntime_same(m, ds, t, lane))) {
+					/* model.cc:1305-1314 equal(): any element of Ntime moved by more than TINY since the
+					 * previous step (ntc holds Ntime[t-1]: steps skipped above left it bit-identical) */
 					int ch = 0;
+					if (m.mm_packed) ntime_stage(m, ds, t, fv, lane);
 					for (int i = lane; i < G * G; i += 32) {
-						int aa = i / G, bb = i - aa * G;
-						double n0 = m.N0[i];
-						double x = ntime_elem(m, ds, t, aa, bb, n0), y = ntime_elem(m, ds, t - 1, aa, bb, n0);
-						if (y < x - 0.00000001 || y > x + 0.00000001) ch = 1;
+						double x;
+						if (m.mm_packed) x = ntime_packed(m.mm_pack[i], fv, m.N0[i]);
+						else { const int aa = i / G, bb = i - aa * G; x = ntime_elem(m, ds, t, aa, bb, m.N0[i]); }
+						const double y = ntc[i];
+						if (t > 0 && (y < x - 0.00000001 || y > x + 0.00000001)) ch = 1;
+						ntc[i] = x;
 					}
-					recompute = __any_sync(FULLMASK, ch);
+					if (__any_sync(FULLMASK, ch)) recompute = true;
+					__syncwarp();
 				}
 				if (recompute) {
 					for (int i = lane; i < Dq * Dq; i += 32) {
 						int q = i / Dq, k = i - q * Dq;
 						int aq = m.dp_age[q], ak = m.dp_age[k];
-						double nt = ntime_elem(m, ds, t, aq, ak, m.N0[aq * G + ak]);
+						double nt = (m.nmm > 0) ? ntc[aq * G + ak] : m.N0[aq * G + ak];
 						double sum = 0;
 						for (int is = 0; is < ninf; is++) {
 							double inf = pd[m.comp_inf_param[m.inf_state[is]]];
@@ -863,7 +907,10 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 	const bool keep_tn = KEEP && (b.flags & BEEP_KEEP_TRANSNUM) != 0, keep_tm = KEEP && (b.flags & BEEP_KEEP_TRANSMEAN) != 0;
 	const unsigned lt = (1u << lane) - 1u;
 	const double dt = m.dt;
-	int nact = 0;
+	/* two lists in ae[]: cells with a small mean (Poisson by inversion) from the front, cells with a
+	 * large mean (transformed rejection) from the back -- the two samplers never share a warp pass */
+	int nsmall = 0, nbig = 0;
+	const int top = L.JDe - 1;
 	unsigned trbits = 0;
 	const double *crate = b.crate + (size_t)p * L.JD32;
 #pragma unroll 1
@@ -876,45 +923,87 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		if ((w >> 24) == 1u) mean *= lds64(foi_a + ((w >> 15) & 0x1f8u));
 		if (!(popu > 0)) mean = 0;
 		const bool act = (mean != 0);
+		const bool big = mean >= BEEP_POISSON_INV_MAX;
 		if (KEEP && e < JD) {
 			if (keep_tm) b.tm[tbase + e] = mean;
 			if (keep_tn && !act) b.tn[tbase + e] = 0;
 		}
-		const unsigned bal = __ballot_sync(FULLMASK, act);
-		if (act) { sts16(ae_a + (nact + __popc(bal & lt)) * 2, e); sts64(ns_a + e * 8, mean); }
-		nact += __popc(bal);
+		const unsigned bal = __ballot_sync(FULLMASK, act), balb = __ballot_sync(FULLMASK, big);
+		if (act) {
+			const int pos = big ? top - (nbig + __popc(balb & lt)) : nsmall + __popc(bal & ~balb & lt);
+			sts16(ae_a + pos * 2, e); sts64(ns_a + e * 8, mean);
+		}
+		nbig += __popc(balb);
+		nsmall += __popc(bal & ~balb);
 	}
 
-	/* 3. draws on the dense list */
-	if (nact > 0) {
+	/* 3. draws on the dense lists */
+	if (nsmall + nbig > 0) {
 		__syncwarp();
 		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
 		const unsigned long long sid = b.stream_id[p];
 		int simu = 0;
 		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
-#pragma unroll 1
-		for (int i = lane; i < nact; i += 32) {
-			const int e = lds16(ae_a + i * 2);
-			const double mean = lds64(ns_a + e * 8);
+		/* one cell: the draw of MODE (state.cc:624-626 / mbp.cc:286-311) from the cell's own stream */
+		auto draw = [&](const int e, const double mean) -> int {
 			BeepStream rs;
 			beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
-			int num;
-			if (MODE == MODE_SIM) num = beep_poisson(&rs, mean);             /* state.cc:624-626 */
-			else {
-				/* mbp.cc:286-311 */
-				const int num_i = a.init_tn[tbase + e];
-				if (simu) num = beep_poisson(&rs, mean);
-				else {
-					const double rate_i = a.init_tm[tbase + e];
-					if (mean > rate_i) num = num_i + beep_poisson(&rs, mean - rate_i);
-					else if (mean == rate_i) num = num_i;
-					else if (num_i == 0) num = 0;
-					else num = beep_binomial(&rs, mean / rate_i, num_i);
-				}
-			}
-			sts64(ns_a + e * 8, (double)num);               /* replaces the mean: zero again unless there were events */
+			if (MODE == MODE_SIM) return beep_poisson(&rs, mean);
+			const int num_i = a.init_tn[tbase + e];
+			if (simu) return beep_poisson(&rs, mean);
+			const double rate_i = a.init_tm[tbase + e];
+			if (mean > rate_i) return num_i + beep_poisson(&rs, mean - rate_i);
+			if (mean == rate_i) return num_i;
+			if (num_i == 0) return 0;
+			return beep_binomial(&rs, mean / rate_i, num_i);
+		};
+		/* replaces the mean by the count: zero again unless there were events */
+		auto finish = [&](const int e, const int num) {
+			sts64(ns_a + e * 8, (double)num);
 			if (num != 0) trbits |= 1u << ((lds32(ctab_a + e * 4) >> 12) & 63);
 			if (keep_tn) b.tn[tbase + e] = num;
+		};
+#pragma unroll 1
+		for (int i = lane; i < nsmall; i += 32) {
+			const int e = lds16(ae_a + i * 2);
+			finish(e, draw(e, lds64(ns_a + e * 8)));
+		}
+		if (nbig > 0) {
+			if (MODE == MODE_SIM) {
+				/* first the squeeze of every cell's first attempt; the cells it does not settle are
+				 * collected (over the slots already read) and run the full sampler together */
+				int ndef = 0;
+#pragma unroll 1
+				for (int i0 = 0; i0 < nbig; i0 += 32) {
+					const int i = i0 + lane;
+					bool defer = false;
+					int e = 0;
+					if (i < nbig) {
+						e = lds16(ae_a + (top - i) * 2);
+						const double mean = lds64(ns_a + e * 8);
+						BeepStream rs;
+						beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
+						int num;
+						if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num)) finish(e, num);
+						else defer = true;
+					}
+					const unsigned bd = __ballot_sync(FULLMASK, defer);
+					if (defer) sts16(ae_a + (top - (ndef + __popc(bd & lt))) * 2, e);
+					ndef += __popc(bd);
+				}
+				__syncwarp();
+#pragma unroll 1
+				for (int i = lane; i < ndef; i += 32) {
+					const int e = lds16(ae_a + (top - i) * 2);
+					finish(e, draw(e, lds64(ns_a + e * 8)));
+				}
+			} else {
+#pragma unroll 1
+				for (int i = lane; i < nbig; i += 32) {
+					const int e = lds16(ae_a + (top - i) * 2);
+					finish(e, draw(e, lds64(ns_a + e * 8)));
+				}
+			}
 		}
 	}
 	/* transitions with events, warp-wide (also orders the ns[] writes before the reads below) */
@@ -1110,7 +1199,7 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 			const unsigned wb = launder(smem_addr(pop + CDp)), pa = launder(smem_addr(pop));
 #pragma unroll 1
 			for (int t = a.ti; t < a.tf; t++) {
-				if (ntw) ntime_refresh(m, b.disc_spline + (size_t)p * (m.nspline * m.T), t, a.ti, smraw + L.n0, ntw, L.Gs, lane);
+				if (ntw) ntime_refresh(m, b.disc_spline + (size_t)p * (m.nspline * m.T), t, a.ti, smraw + L.n0, ntw, L.Gs, pop + CDp + L.nbr, lane);
 				tile_step_fast<MODE, KEEP, false, false>(a, p, c, t, t / m.spu, lane, wb, pa, ca, dinf, (size_t)(S * G), 0, n0_a, false);
 			}
 		} else {
@@ -1122,7 +1211,7 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 			tile_ctx_area(m.area_info[c], c, tc);
 #pragma unroll 1
 			for (int t = a.ti; t < a.tf; t++) {
-				if (ntw) ntime_refresh(m, tc.ds, t, a.ti, smraw + L.n0, ntw, L.Gs, lane);
+				if (ntw) ntime_refresh(m, tc.ds, t, a.ti, smraw + L.n0, ntw, L.Gs, pop + CDp + L.nbr, lane);
 				tile_step<MODE, KEEP, false, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
 			}
 		}

@@ -303,6 +303,26 @@ BEEP_HD int beep_poisson_ptrs(BeepStream *s, double lam)
 	return (int)lam;
 }
 #if defined(__CUDACC__)
+/* Device: the FIRST PTRS attempt of a fresh stream, squeeze only.  Returns 1 and the draw when the
+ * squeeze accepts (the same value beep_poisson_ptrs returns from its first iteration); 0 when the
+ * attempt needs the exact test or is rejected -- the caller then runs beep_poisson_ptrs_fresh,
+ * which repeats this attempt and carries on.  Lets a warp do the cheap, common part of all its
+ * cells first and the expensive logarithms of the rest together. */
+static __device__ __forceinline__ int beep_poisson_ptrs_try(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double lam, int *out)
+{
+	BeepStream st;
+	st.key[0] = k0; st.key[1] = k1; st.ctr[0] = c0; st.ctr[1] = c1; st.ctr[2] = c2; st.ctr[3] = c3; st.have = 0;
+	double slam = BR_SQRT(lam);
+	double b = BR_ADD(0.931, BR_MUL(2.53, slam));
+	double a = BR_ADD(-0.059, BR_MUL(0.02483, b));
+	double vr = BR_SUB(0.9277, BR_DIV(3.6224, BR_SUB(b, 2.0)));
+	double U = BR_SUB(beep_next_uniform(&st), 0.5);
+	double V = beep_next_uniform(&st);
+	double us = BR_SUB(0.5, BR_FABS(U));
+	double kf = BR_FLOOR(BR_ADD(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), lam), 0.43));
+	if (us >= 0.07 && V <= vr) { *out = (int)kf; return 1; }
+	return 0;
+}
 /* Device: a fresh stream (nothing read yet) runs PTRS out of line, so that kernels dominated
  * by small means keep a small hot loop; the caller's copy of the stream is not advanced --
  * on the device a stream serves exactly one draw. */
