@@ -1287,6 +1287,19 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 		 * force-of-infection phase, which does not read it) and is written back once per step. */
 		const int P = b.P;
 		int p = (int)(((long long)gw * P) / nw);        /* warps start spread over the particles */
+		/* a warp that finds its particle exhausted moves on by its OWN stride (coprime with P, so P hops
+		 * still visit every particle): warps leaving a particle together scatter instead of arriving
+		 * together at the next one and exhausting it at once */
+		int hop = 1;
+		if (P > 2) {
+			hop = 1 + (int)(((unsigned)gw * 2654435761u >> 8) % (unsigned)(P - 1));
+			while (true) {
+				int x = hop, y = P;
+				while (y) { const int r = x % y; x = y; y = r; }
+				if (x == 1) break;
+				if (++hop >= P) hop = 1;
+			}
+		}
 		int nmiss = 0;                                  /* consecutive particles without a tile to hand out */
 		int nfin = 0;                                   /* ... of which had finished their trajectory */
 		int nspin = 0;                                  /* idle rounds in a row: a scheduler that never hands out work traps */
@@ -1315,7 +1328,8 @@ __global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_const
 					if (++nspin > 8000000) __trap();
 					__nanosleep(500);
 				}
-				if (++p == P) p = 0;
+				p += hop;
+				if (p >= P) p -= P;
 				continue;
 			}
 			nmiss = 0; nfin = 0; nspin = 0;
