@@ -648,8 +648,12 @@ extern "C" int beep_obs_loglik_dev(BeepBatch *bt, int section, double *L_dev, do
 	if (section >= eng->dm.nsection) return fail(BEEP_ERR_INVALID, "section %d out of range", section);
 	CU(cudaSetDevice(eng->device));
 	const int P = bt->db.P, wt = EF_dev ? 1 : 0, nq = wt ? 1 + eng->dm.ntable : 1;
-	k_obs_final<<<dim3(P, OBS_CHUNKS), RED_THREADS, 0, bt->stream>>>(eng->dm, bt->db, section, wt, bt->d_scratch);
-	k_obs_reduce<<<(P * nq + 127) / 128, 128, 0, bt->stream>>>(eng->dm, P, wt, bt->d_scratch, L_dev ? L_dev : bt->db.L, EF_dev);
+	/* chunks of at least a block's worth of observations; small observation sets get small blocks */
+	const int nobs = eng->dm.nobs;
+	const int nch = std::max(1, std::min(OBS_CHUNKS, (nobs + RED_THREADS - 1) / RED_THREADS));
+	const int nth = std::min(RED_THREADS, std::max(32, ((nobs + nch - 1) / nch + 31) & ~31));
+	k_obs_final<<<dim3(P, nch), nth, 0, bt->stream>>>(eng->dm, bt->db, section, wt, bt->d_scratch);
+	k_obs_reduce<<<(P * nq + 127) / 128, 128, 0, bt->stream>>>(eng->dm, P, wt, nch, bt->d_scratch, L_dev ? L_dev : bt->db.L, EF_dev);
 	eng->launches += 2;
 	CU(cudaGetLastError());
 	return BEEP_OK;

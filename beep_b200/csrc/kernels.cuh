@@ -164,24 +164,32 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		for (int co = 0; co < m.C; co++) if (pd[m.comp_inf_param[co]] != 0) il[1 + n++] = co;
 		il[0] = n;
 	}
-	/* model.cc:1020-1043 create_disc_spline: one thread walks one spline */
-	for (int sp = tid; sp < m.nspline; sp += nth) {
-		double factor = pd[m.spline_factor_param[sp]];
-		int o = m.spline_off[sp], np = m.spline_off[sp + 1] - o;
+	/* model.cc:1020-1043 create_disc_spline, one thread per (spline, step): the knot interval is found
+	 * by the reference's forward walk from the first knot; a step past the last knot repeats the value
+	 * of the last step inside the knots (the reference's `prev`; 0 when there is none), filled in
+	 * a second pass */
+	for (int i = tid; i < m.nspline * T; i += nth) {
+		const int sp = i / T, st = i - sp * T;
+		const double factor = pd[m.spline_factor_param[sp]];
+		const int o = m.spline_off[sp], np = m.spline_off[sp + 1] - o;
+		const double t = (double)((st + 0.5) * m.period) / T;
 		int q = 0;
-		double prev = 0;
-		for (int st = 0; st < T; st++) {
-			double t = (double)((st + 0.5) * m.period) / T;
-			while (q + 1 < np && t > m.spline_t[o + q + 1]) q++;
-			double v;
-			if (q + 1 == np) v = prev;
-			else {
-				double fac = (t - m.spline_t[o + q]) / (m.spline_t[o + q + 1] - m.spline_t[o + q]);
-				v = factor * (pd[m.spline_param[o + q]] * m.spline_multfac[o + q] * (1 - fac) +
-				              pd[m.spline_param[o + q + 1]] * m.spline_multfac[o + q + 1] * fac);
-			}
-			ds[sp * T + st] = v;
-			prev = v;
+		while (q + 1 < np && t > m.spline_t[o + q + 1]) q++;
+		if (q + 1 < np) {
+			const double fac = (t - m.spline_t[o + q]) / (m.spline_t[o + q + 1] - m.spline_t[o + q]);
+			ds[i] = factor * (pd[m.spline_param[o + q]] * m.spline_multfac[o + q] * (1 - fac) +
+			                  pd[m.spline_param[o + q + 1]] * m.spline_multfac[o + q + 1] * fac);
+		}
+	}
+	__syncthreads();
+	for (int i = tid; i < m.nspline * T; i += nth) {
+		const int sp = i / T, st = i - sp * T;
+		const int o = m.spline_off[sp], np = m.spline_off[sp + 1] - o;
+		const double tl = m.spline_t[o + np - 1];
+		if (np < 2 || (double)((st + 0.5) * m.period) / T > tl) {
+			int sl = st - 1;                               /* last step at or before the last knot */
+			while (sl >= 0 && (double)((sl + 0.5) * m.period) / T > tl) sl--;
+			ds[i] = (sl >= 0 && np > 1) ? ds[sp * T + sl] : 0.0;
 		}
 	}
 	__syncthreads();
@@ -1459,8 +1467,8 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 __global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch b, int section, int want_tables, double *part)
 {
 	__shared__ double red[RED_THREADS / 32];
-	const int p = blockIdx.x, ch = blockIdx.y;
-	const int lo = (int)((long long)m.nobs * ch / OBS_CHUNKS), hi = (int)((long long)m.nobs * (ch + 1) / OBS_CHUNKS);
+	const int p = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;      /* nch <= OBS_CHUNKS: as many chunks as the observations fill */
+	const int lo = (int)((long long)m.nobs * ch / nch), hi = (int)((long long)m.nobs * (ch + 1) / nch);
 	const double *pt = b.obs_partial + (size_t)p * m.nslot;
 	double *oval = b.obs_val + (size_t)p * m.nobs;
 	double *out = part + ((size_t)p * OBS_CHUNKS + ch) * (1 + m.ntable);
@@ -1484,14 +1492,14 @@ __global__ void __launch_bounds__(RED_THREADS) k_obs_final(DevModel m, DevBatch 
 		}
 	}
 }
-__global__ void k_obs_reduce(DevModel m, int P, int want_tables, const double *part, double *L_out, double *EF_out)
+__global__ void k_obs_reduce(DevModel m, int P, int want_tables, int nch, const double *part, double *L_out, double *EF_out)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int nq = want_tables ? 1 + m.ntable : 1;
 	if (i >= P * nq) return;
 	const int p = i / nq, q = i - p * nq;
 	double s = 0;
-	for (int ch = 0; ch < OBS_CHUNKS; ch++) s += part[((size_t)p * OBS_CHUNKS + ch) * (1 + m.ntable) + q];
+	for (int ch = 0; ch < nch; ch++) s += part[((size_t)p * OBS_CHUNKS + ch) * (1 + m.ntable) + q];
 	if (q == 0) L_out[p] = s;
 	else EF_out[(size_t)p * m.ntable + (q - 1)] = s;
 }
