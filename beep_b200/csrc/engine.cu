@@ -46,6 +46,7 @@ struct BeepEngine {
 	int sync_mode = SYNC_NONE, nwarp = 4;
 	size_t smem_traj = 0;
 	int coop_grid = 0;
+	void *mvn_buf = nullptr; size_t mvn_cap = 0;   /* grow-only scratch of beep_mvn_kernel_sums */
 };
 
 struct BeepBatch {
@@ -88,6 +89,7 @@ extern "C" void beep_engine_destroy(BeepEngine *eng)
 	if (!eng) return;
 	cudaSetDevice(eng->device);
 	for (void *p : eng->dev_allocs) cudaFree(p);
+	if (eng->mvn_buf) cudaFree(eng->mvn_buf);
 	delete eng;
 }
 
@@ -996,6 +998,77 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 /* ------------------------------------------------------------------------ */
 /* PMCMC bootstrap, pmcmc.cc:211-268 (host, O(Ntot))                          */
 /* ------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------ */
+/* K7  ABC-SMC importance weights                                            */
+/* ------------------------------------------------------------------------ */
+extern "C" int beep_mvn_kernel_sums(BeepEngine *eng, int nvar, int nparam, const int *var, const double *inv_M, double size,
+                                    const double *param_prop, int N, const double *param_last, const double *w_last, int Nlast, double *sums_out)
+{
+	if (!eng || !var || !inv_M || !param_prop || !param_last || !w_last || !sums_out) return fail(BEEP_ERR_INVALID, "null argument");
+	if (nvar <= 0 || nparam < nvar || N <= 0 || Nlast <= 0 || !(size > 0)) return fail(BEEP_ERR_INVALID, "bad sizes for beep_mvn_kernel_sums");
+	for (int v = 0; v < nvar; v++) if (var[v] < 0 || var[v] >= nparam) return fail(BEEP_ERR_INVALID, "var[%d] = %d out of range", v, var[v]);
+	/* inv_M / size^2 = Lm Lm' on the host in extended precision (nvar ~ 10^2): the symmetric part is
+	 * what the quadratic form sees */
+	std::vector<long double> L((size_t)nvar * nvar, 0.0L);
+	for (int a = 0; a < nvar; a++)
+		for (int b = 0; b <= a; b++) {
+			long double s = 0.5L * ((long double)inv_M[(size_t)a * nvar + b] + (long double)inv_M[(size_t)b * nvar + a]) / ((long double)size * (long double)size);
+			for (int k = 0; k < b; k++) s -= L[(size_t)a * nvar + k] * L[(size_t)b * nvar + k];
+			if (a == b) {
+				if (!(s > 0)) return fail(BEEP_ERR_INVALID, "inv_M is not positive definite (pivot %d)", a);
+				L[(size_t)a * nvar + a] = sqrtl(s);
+			} else L[(size_t)a * nvar + b] = s / L[(size_t)b * nvar + b];
+		}
+	std::vector<double> Lm((size_t)nvar * nvar), mu(nvar);
+	for (size_t k = 0; k < Lm.size(); k++) Lm[k] = (double)L[k];
+	{
+		long double wsum = 0;
+		std::vector<long double> acc(nvar, 0.0L);
+		for (int j = 0; j < Nlast; j++) { wsum += w_last[j]; for (int v = 0; v < nvar; v++) acc[v] += (long double)w_last[j] * param_last[(size_t)j * nparam + var[v]]; }
+		for (int v = 0; v < nvar; v++) mu[v] = (wsum > 0) ? (double)(acc[v] / wsum) : 0.0;
+	}
+	CU(cudaSetDevice(eng->device));
+	cudaStream_t st = 0;
+	const int ti = (N + MVN_TI - 1) / MVN_TI;
+	int nslice = std::max(1, std::min((Nlast + MVN_TJ - 1) / MVN_TJ, (4 * eng->nsm + ti - 1) / ti));
+	int jslice = (((Nlast + nslice - 1) / nslice) + MVN_TJ - 1) / MVN_TJ * MVN_TJ;
+	nslice = (Nlast + jslice - 1) / jslice;
+	/* one grow-only device scratch per engine, carved into 256-byte aligned pieces */
+	auto al = [](size_t n) { return (n + 255) & ~(size_t)255; };
+	const size_t sz[10] = {al((size_t)N * nparam * 8), al((size_t)Nlast * nparam * 8), al((size_t)Nlast * 8), al(Lm.size() * 8), al((size_t)nvar * 8),
+	                       al((size_t)nvar * 4), al((size_t)N * nvar * 8), al((size_t)Nlast * nvar * 8), al((size_t)nslice * N * 8), al((size_t)N * 8)};
+	size_t tot = 0;
+	for (size_t x : sz) tot += x;
+	if (tot > eng->mvn_cap) {
+		if (eng->mvn_buf) { cudaFree(eng->mvn_buf); eng->mvn_buf = nullptr; eng->mvn_cap = 0; }
+		CU(cudaMalloc(&eng->mvn_buf, tot));
+		eng->mvn_cap = tot;
+	}
+	char *base = (char *)eng->mvn_buf;
+	size_t off = 0;
+	auto take = [&](int k) { char *p = base + off; off += sz[k]; return p; };
+	double *d_prop = (double *)take(0), *d_last = (double *)take(1), *d_w = (double *)take(2), *d_L = (double *)take(3), *d_mu = (double *)take(4);
+	int *d_var = (int *)take(5);
+	double *d_xw = (double *)take(6), *d_yw = (double *)take(7), *d_part = (double *)take(8), *d_out = (double *)take(9);
+#define MV(x) CU(x)
+	MV(cudaMemcpyAsync(d_prop, param_prop, (size_t)N * nparam * sizeof(double), cudaMemcpyHostToDevice, st));
+	MV(cudaMemcpyAsync(d_last, param_last, (size_t)Nlast * nparam * sizeof(double), cudaMemcpyHostToDevice, st));
+	MV(cudaMemcpyAsync(d_w, w_last, (size_t)Nlast * sizeof(double), cudaMemcpyHostToDevice, st));
+	MV(cudaMemcpyAsync(d_L, Lm.data(), Lm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+	MV(cudaMemcpyAsync(d_mu, mu.data(), nvar * sizeof(double), cudaMemcpyHostToDevice, st));
+	MV(cudaMemcpyAsync(d_var, var, nvar * sizeof(int), cudaMemcpyHostToDevice, st));
+	k_mvn_whiten<<<N, 128, 0, st>>>(d_prop, N, nparam, d_var, nvar, d_mu, d_L, d_xw);
+	k_mvn_whiten<<<Nlast, 128, 0, st>>>(d_last, Nlast, nparam, d_var, nvar, d_mu, d_L, d_yw);
+	k_mvn_pair_sums<<<dim3(ti, nslice), 256, 0, st>>>(d_xw, N, d_yw, d_w, Nlast, nvar, jslice, d_part);
+	k_mvn_reduce<<<(N + 127) / 128, 128, 0, st>>>(d_part, N, nslice, d_out);
+	eng->launches += 4;
+	MV(cudaGetLastError());
+	MV(cudaMemcpyAsync(sums_out, d_out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+	MV(cudaStreamSynchronize(st));
+#undef MV
+	return BEEP_OK;
+}
+
 extern "C" int beep_bootstrap(const double *L, int ntot, double invT, uint64_t seed, int section, double *loglik_inc, uint32_t *backpart)
 {
 	if (!L || ntot <= 0 || !loglik_inc || !backpart) return fail(BEEP_ERR_INVALID, "bad argument to beep_bootstrap");

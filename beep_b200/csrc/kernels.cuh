@@ -1557,6 +1557,98 @@ __global__ void k_copy_flagged(Tp *dst, const Tp *src, const unsigned char *flag
 	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) dp[i] = sp[i];
 }
 
+/* ------------------------------------------------------------------------ */
+/* K7  ABC-SMC importance-weight denominators, abcsmc.cc:260-271             */
+/* ------------------------------------------------------------------------ */
+/* The reference evaluates, for every proposal i, SUM_j w_j exp(-1/2 (d/size)' inv_M (d/size)) with
+ * d = prop_i - last_j over the free parameters (MVN::probability, mvn.cc:185-196): O(N Nlast nvar^2).
+ * With inv_M / size^2 = Lm Lm' (Cholesky, host, extended precision) the quadratic form is
+ * |Lm'(x - y)|^2: both sets are whitened once (k_mvn_whiten, O((N + Nlast) nvar^2)) around the
+ * weighted mean of the last generation (keeps magnitudes at the scale of d), and the pair sums
+ * cost O(N Nlast nvar) (k_mvn_pair_sums).  Agrees with the reference's own sum to ~1e-12 relative
+ * at cond(M) = 5e5 (tests/test_mvn_*.py); the contract is 1e-10. */
+__global__ void k_mvn_whiten(const double *param, int n, int nparam, const int *var, int nvar, const double *mu, const double *Lm, double *out)
+{
+	/* out[i][k] = SUM_v (param[i][var[v]] - mu[v]) Lm[v][k],  k >= v only (Lm lower triangular), v ascending */
+	const int i = blockIdx.x;
+	const double *x = param + (size_t)i * nparam;
+	for (int k = threadIdx.x; k < nvar; k += blockDim.x) {
+		double acc = 0;
+		for (int v = k; v < nvar; v++) acc = fma(x[var[v]] - mu[v], Lm[(size_t)v * nvar + k], acc);
+		out[(size_t)i * nvar + k] = acc;
+	}
+}
+
+#define MVN_TI 64
+#define MVN_TJ 64
+#define MVN_KC 16
+/* partial[js][i] = SUM_{j in slice js} w[j] exp(-1/2 |xw_i - yw_j|^2).  CTA = 64 proposals x one slice of
+ * the last generation, walked in tiles of 64; 256 threads, each a 4 x 4 block of pairs; operands staged
+ * k-major in shared memory.  Every sum has a fixed order (k ascending; j by tile, then the 16 threads
+ * of a row in lane order), so the result does not depend on the launch. */
+__global__ void __launch_bounds__(256) k_mvn_pair_sums(const double *xw, int N, const double *yw, const double *w, int Nl, int nvar, int jslice, double *partial)
+{
+	__shared__ __align__(16) double xs[MVN_KC][MVN_TI + 2], ys[MVN_KC][MVN_TJ + 2];
+	__shared__ double red[MVN_TI][17];
+	const int i0 = blockIdx.x * MVN_TI, js = blockIdx.y;
+	const int jbeg = js * jslice, jend = min(Nl, jbeg + jslice);
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          /* tx: 4 columns (j), ty: 4 rows (i) */
+	double rowsum[4] = {0, 0, 0, 0};
+	for (int j0 = jbeg; j0 < jend; j0 += MVN_TJ) {
+		double acc[4][4];
+#pragma unroll
+		for (int a = 0; a < 4; a++)
+#pragma unroll
+			for (int b = 0; b < 4; b++) acc[a][b] = 0;
+		for (int k0 = 0; k0 < nvar; k0 += MVN_KC) {
+			__syncthreads();
+			for (int e = threadIdx.x; e < MVN_KC * MVN_TI; e += 256) {
+				const int r = e / MVN_KC, k = e - r * MVN_KC;               /* consecutive threads read consecutive k: coalesced rows */
+				const int i = i0 + r, j = j0 + r, kk = k0 + k;
+				xs[k][r] = (i < N && kk < nvar) ? xw[(size_t)i * nvar + kk] : 0.0;
+				ys[k][r] = (j < jend && kk < nvar) ? yw[(size_t)j * nvar + kk] : 0.0;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int k = 0; k < MVN_KC; k++) {
+				double xv[4], yv[4];
+#pragma unroll
+				for (int a = 0; a < 4; a++) { xv[a] = xs[k][ty * 4 + a]; yv[a] = ys[k][tx * 4 + a]; }
+#pragma unroll
+				for (int a = 0; a < 4; a++)
+#pragma unroll
+					for (int b = 0; b < 4; b++) { const double d = xv[a] - yv[b]; acc[a][b] = fma(d, d, acc[a][b]); }
+			}
+		}
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const int j = j0 + tx * 4 + b;
+			if (j < jend) {
+				const double wj = w[j];
+#pragma unroll
+				for (int a = 0; a < 4; a++) rowsum[a] += wj * exp(-0.5 * acc[a][b]);
+			}
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int a = 0; a < 4; a++) red[ty * 4 + a][tx] = rowsum[a];
+	__syncthreads();
+	if (threadIdx.x < MVN_TI && i0 + threadIdx.x < N) {
+		double s = 0;
+		for (int t = 0; t < 16; t++) s += red[threadIdx.x][t];
+		partial[(size_t)js * N + i0 + threadIdx.x] = s;
+	}
+}
+__global__ void k_mvn_reduce(const double *partial, int N, int nslice, double *out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double s = 0;
+	for (int k = 0; k < nslice; k++) s += partial[(size_t)k * N + i];
+	out[i] = s;
+}
+
 /* sampler parity helpers (tests/test_rng_parity.py) */
 __global__ void k_poisson_many(unsigned long long seed, unsigned long long stream_id, const double *lam, int n, int *out)
 {

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
+    "beep_mvn_kernel_sums": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]),
     "beep_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _c_dp, _vp]),
     "beep_test_poisson": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_int, _vp]),
     "beep_test_binomial": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, ctypes.c_int, _vp]),
@@ -281,6 +282,20 @@ class Batch:
     @property
     def last_simulate_ms(self):
         return self.L.beep_last_simulate_ms(self.h)
+
+
+def mvn_kernel_sums(engine, var, inv_M, size, param_prop, param_last, w_last):
+    """ABCSMC::calculate_particle_weight's sum over the previous generation (abcsmc.cc:264-268) for every
+    proposal: SUM_j w_last[j] exp(MVN::probability(prop_i, last_j)) -- beep_mvn_kernel_sums."""
+    var = np.ascontiguousarray(var, dtype=np.int32)
+    inv_M = _f64(inv_M)
+    pp, pl, w = _f64(param_prop), _f64(param_last), _f64(w_last)
+    if pp.ndim != 2 or pl.ndim != 2 or pp.shape[1] != pl.shape[1] or w.size != pl.shape[0] or inv_M.size != var.size ** 2:
+        raise ValueError("inconsistent shapes")
+    out = np.zeros(pp.shape[0])
+    _check(engine.L.beep_mvn_kernel_sums(engine.h, var.size, pp.shape[1], var.ctypes.data, inv_M.ctypes.data, float(size),
+                                         pp.ctypes.data, pp.shape[0], pl.ctypes.data, w.ctypes.data, pl.shape[0], out.ctypes.data))
+    return out
 
 
 def bootstrap(L_all, invT, seed, section):

@@ -33,6 +33,16 @@ public:
 	BeepEngine *handle() const { return h_; }
 	int nsection() const { return beep_num_sections(h_); }
 	void section_range(int s, int &ti, int &tf) const { check(beep_section_range(h_, s, &ti, &tf)); }
+	/// ABCSMC::calculate_particle_weight's sum over the previous generation (abcsmc.cc:264-268) for all proposals:
+	/// sums[i] = SUM_j w_last[j] exp(MVN::probability(prop_i, last_j)); parameters are rows of nparam doubles
+	std::vector<double> mvn_kernel_sums(const std::vector<int> &var, const std::vector<double> &inv_M, double size, int nparam,
+	                                    const std::vector<double> &param_prop, const std::vector<double> &param_last, const std::vector<double> &w_last) const
+	{
+		const int N = (int)(param_prop.size() / nparam), Nl = (int)w_last.size();
+		std::vector<double> sums(N);
+		check(beep_mvn_kernel_sums(h_, (int)var.size(), nparam, var.data(), inv_M.data(), size, param_prop.data(), N, param_last.data(), w_last.data(), Nl, sums.data()));
+		return sums;
+	}
 private:
 	BeepEngine *h_ = nullptr;
 };

@@ -836,3 +836,32 @@ void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
 /* the shared software exp / log (include/beep_rng.h), exposed so that tests can pin their accuracy against libm */
 void oracle_exp_many(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = beep_exp(x[i]); }
 void oracle_log_many(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = beep_log(x[i]); }
+
+/* ---------------------------------------------------------------------- */
+/* ABC-SMC importance-weight denominators            */
+/* ---------------------------------------------------------------------- */
+/* MVN::probability, mvn.cc:185-196: -1/2 SUM_v1 SUM_v2 (d_v1/size) inv_M[v1][v2] (d_v2/size), in the
+ * reference's loop order */
+static double oracle_mvn_probability(int nvar, const int32_t *var, const double *inv_M, double size, const double *pend, const double *pstart)
+{
+	double sum = 0;
+	for (int v1 = 0; v1 < nvar; v1++)
+		for (int v2 = 0; v2 < nvar; v2++) {
+			double val1 = pend[var[v1]] - pstart[var[v1]];
+			double val2 = pend[var[v2]] - pstart[var[v2]];
+			sum += (val1 / size) * inv_M[v1 * nvar + v2] * (val2 / size);
+		}
+	return -0.5 * sum;
+}
+/* the sum of ABCSMC::calculate_particle_weight, abcsmc.cc:264-268, for each of N proposals:
+ * out[i] = SUM_j w_last[j] exp(probability(prop_i, last_j)); the caller divides exp(prior) by it (:270) */
+void oracle_mvn_kernel_sums(int nvar, int nparam, const int32_t *var, const double *inv_M, double size,
+                            const double *param_prop, int N, const double *param_last, const double *w_last, int Nlast, double *out)
+{
+	for (int i = 0; i < N; i++) {
+		double sum = 0;
+		for (int j = 0; j < Nlast; j++)
+			sum += w_last[j] * exp(oracle_mvn_probability(nvar, var, inv_M, size, param_prop + (size_t)i * nparam, param_last + (size_t)j * nparam));
+		out[i] = sum;
+	}
+}

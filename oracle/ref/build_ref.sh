@@ -6,6 +6,7 @@
 #                            runtests.cc, old_code.cc) with CMakeLists.txt:27 flags
 #   oracle/_ref/BEEP         the reference executable (single-rank MPI shim)
 #   oracle/_ref/ref_harness  adapter + golden-vector generator (ref_harness.cc)
+#   oracle/_ref/ref_mvn      golden vectors of the ABC-SMC weight kernel (ref_mvn.cc)
 # The reference's CMake cannot be used here (find_package(MPI REQUIRED) and a
 # network FetchContent); nothing is copied into the repo.  TEST INFRASTRUCTURE.
 set -e
@@ -27,4 +28,6 @@ g++ -o "$OUT/BEEP" "$OUT"/obj/*.o
 OBJS=$(ls "$OUT"/obj/*.o | grep -v -E "/(main|utils)\.o$")
 g++ $CXXFLAGS -ffp-contract=off -I"$ROOT/include" -c "$HERE/ref_harness.cc" -o "$OUT/ref_harness.oo"
 g++ -o "$OUT/ref_harness" "$OUT/ref_harness.oo" $OBJS "$OUT/obj/utils_renamed.oo"
-echo "build_ref: built $OUT/BEEP and $OUT/ref_harness"
+g++ $CXXFLAGS -ffp-contract=off -c "$HERE/ref_mvn.cc" -o "$OUT/ref_mvn.oo"
+g++ -o "$OUT/ref_mvn" "$OUT/ref_mvn.oo" $OBJS "$OUT/obj/utils.o"
+echo "build_ref: built $OUT/BEEP, $OUT/ref_harness and $OUT/ref_mvn"

@@ -53,6 +53,10 @@ STAT = {
     "stat_EX": ("examples/EX.toml", ["mode=sim"], 1, 61, 10000),
     "stat_EX_C4": ("examples/EX_C4.toml", ["mode=sim"], 1, 67, 10000),
 }
+MVN_CASES = {
+    "mvn_small": (12, 7, 60, 16, 71),          # a handful of free parameters (EX_A1-like)
+    "mvn_england": (180, 140, 400, 24, 73),    # England_AS-like: 180 parameters, most of them free
+}
 SUBST = {"England_AS": [('obsmodel="scale"', 'obsmodel="normal 10%"')]}
 BIG = {"England_AS"}
 
@@ -128,6 +132,20 @@ def main():
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: {reps} replicates, {os.path.getsize(path) / 1024:.0f} KiB")
+    # ABC-SMC weight kernel: the reference's MVN::setup / propose / probability
+    # (oracle/ref/ref_mvn.cc): name -> (nparam, nvar, Nlast, Nprop, seed)
+    for name, (nparam, nvar, nl, npr, seed) in MVN_CASES.items():
+        if only and name not in only:
+            continue
+        bpk = os.path.join(work, name + ".bpk")
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_mvn"), bpk, str(nparam), str(nvar), str(nl), str(npr), str(seed)],
+                           cwd=work, capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(bpk):
+            print(f"{name}: ref_mvn FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, **read_bpk(bpk))
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
     shutil.rmtree(work, ignore_errors=True)
 
 

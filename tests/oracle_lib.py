@@ -51,8 +51,23 @@ def lib():
         L.oracle_philox.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_exp_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.oracle_log_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_mvn_kernel_sums.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         _LIB = L
     return _LIB
+
+
+def mvn_kernel_sums(var, inv_M, size, param_prop, param_last, w_last):
+    """SUM_j w_last[j] exp(MVN::probability(prop_i, last_j)) for every proposal i (abcsmc.cc:264-268, mvn.cc:185-196)."""
+    var = np.ascontiguousarray(var, dtype=np.int32)
+    inv_M = np.ascontiguousarray(inv_M, dtype=np.float64)
+    pp = np.ascontiguousarray(param_prop, dtype=np.float64)
+    pl = np.ascontiguousarray(param_last, dtype=np.float64)
+    w = np.ascontiguousarray(w_last, dtype=np.float64)
+    out = np.zeros(pp.shape[0])
+    lib().oracle_mvn_kernel_sums(var.size, pp.shape[1], var.ctypes.data, inv_M.ctypes.data, float(size), pp.ctypes.data, pp.shape[0],
+                                 pl.ctypes.data, w.ctypes.data, pl.shape[0], out.ctypes.data)
+    return out
 
 
 class OracleState:
