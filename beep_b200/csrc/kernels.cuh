@@ -916,8 +916,10 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 	const unsigned lt = (1u << lane) - 1u;
 	const double dt = m.dt;
 	/* two lists in ae[]: cells with a small mean (Poisson by inversion) from the front, cells with a
-	 * large mean (transformed rejection) from the back -- the two samplers never share a warp pass */
-	int nsmall = 0, nbig = 0;
+	 * large mean (transformed rejection) from the back -- the two samplers never share a warp pass.
+	 * A pass whose 32 cells all have an empty source compartment (most passes of an epidemic's
+	 * early and late phases) leaves after four instructions. */
+	unsigned cnt2 = 0;                                  /* nsmall | nbig << 16 (one register across the loop) */
 	const int top = L.JDe - 1;
 	unsigned trbits = 0;
 	const double *crate = b.crate + (size_t)p * L.JD32;
@@ -926,6 +928,13 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		const int e = e0 + lane;
 		const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
 		const double popu = lds64(pa + ((w & 0xfffu) << 3));
+		if (!__any_sync(FULLMASK, popu > 0 && (w >> 25) == 0u)) {          /* kind 2 (and the padding) never fires */
+			if (KEEP && e < JD) {
+				if (keep_tm) b.tm[tbase + e] = 0;
+				if (keep_tn) b.tn[tbase + e] = 0;
+			}
+			continue;
+		}
 		const double cr = crate[e];
 		double mean = dt * popu * cr;
 		if ((w >> 24) == 1u) mean *= lds64(foi_a + ((w >> 15) & 0x1f8u));
@@ -938,12 +947,12 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		}
 		const unsigned bal = __ballot_sync(FULLMASK, act), balb = __ballot_sync(FULLMASK, big);
 		if (act) {
-			const int pos = big ? top - (nbig + __popc(balb & lt)) : nsmall + __popc(bal & ~balb & lt);
+			const int pos = big ? top - (int)((cnt2 >> 16) + __popc(balb & lt)) : (int)((cnt2 & 0xffffu) + __popc(bal & ~balb & lt));
 			sts16(ae_a + pos * 2, e); sts64(ns_a + e * 8, mean);
 		}
-		nbig += __popc(balb);
-		nsmall += __popc(bal & ~balb);
+		cnt2 += __popc(bal & ~balb) + (__popc(balb) << 16);
 	}
+	const int nsmall = (int)(cnt2 & 0xffffu), nbig = (int)(cnt2 >> 16);
 
 	/* 3. draws on the dense lists */
 	if (nsmall + nbig > 0) {
