@@ -52,6 +52,9 @@ struct alignas(16) Nbr { double val; unsigned off; int pad; };   /* off in BYTES
 #ifndef BEEP_TRAJ_MINB
 #define BEEP_TRAJ_MINB 4
 #endif
+#ifndef BEEP_TRAJ_NWARP
+#define BEEP_TRAJ_NWARP 8                /* warps per CTA (upper bound; the grid flavour uses exactly this many) */
+#endif
 struct TrajSm { int Gs, n0, ctab, common, JDe, JD32, ns, ae, foi, nmi, iv, nbr, work; };
 #if defined(__CUDACC__)
 __host__ __device__

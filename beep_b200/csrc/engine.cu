@@ -345,17 +345,17 @@ static int choose_launch(BeepEngine *eng)
 		const size_t ntsz = (m.nmm > 0) ? (size_t)m.G * L.Gs : 0;      /* the warp's copy of Ntime (k_traj) */
 		eng->smem_traj = (common + eng->nwarp * (CDp + work + even(2 * (size_t)m.S * m.G) + ntsz)) * sizeof(double);
 	} else {
-		eng->nwarp = std::min(8, m.A);
+		eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A);
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
 		else eng->sync_mode = SYNC_GRID;
 	}
 	if (force) {
 		int f = atoi(force);
 		if (f == SYNC_GRID) eng->sync_mode = SYNC_GRID;
-		else if (f == SYNC_CTA && m.M_nnz == 0) { eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(8, m.A); eng->smem_traj = cta_bytes(eng->nwarp); }
+		else if (f == SYNC_CTA && m.M_nnz == 0) { eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A); eng->smem_traj = cta_bytes(eng->nwarp); }
 	}
 	if (eng->sync_mode == SYNC_GRID) {
-		eng->nwarp = 8;
+		eng->nwarp = BEEP_TRAJ_NWARP;
 		eng->smem_traj = (common + eng->nwarp * (CDp + work)) * sizeof(double);
 	}
 	if ((long long)m.A * m.G >= (1ll << 28)) return fail(BEEP_ERR_UNSUPPORTED, "too many areas (A*G must be below 2^28)");

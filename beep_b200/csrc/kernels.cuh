@@ -1173,7 +1173,7 @@ __device__ __forceinline__ void work_ptrs(TileSm &ts, const TrajSm &L, double *w
 }
 
 template <int MODE, int SYNC, bool KEEP>
-__global__ void __launch_bounds__(256, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
+__global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(const __grid_constant__ TrajArgs a)
 {
 	extern __shared__ __align__(16) double smraw[];
 	const DevModel &m = a.m;

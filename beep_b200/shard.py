@@ -104,3 +104,135 @@ class ShardedFilter:
             loglik += inc
             self.ancestry.append(back)
         return loglik
+
+
+# ---------------------------------------------------------------------------
+# a12: the resampling decisions of PAS and MC3, and the particle mover
+# ---------------------------------------------------------------------------
+UNSET = 0xFFFFFFFF
+
+
+def _uniforms(seed, key, n):
+    """n uniforms from a counter-based stream that every rank can reproduce: the reference draws ran() on
+    rank 0 and broadcasts the decision; here the decision is replicated from a shared (seed, key)."""
+    return np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), int(key) & (2 ** 64 - 1)])).random(n)
+
+
+def pas_bootstrap(EF_all, invT, quench_factor, nrun, npart, seed, gen, invT_final=None):
+    """PAS::bootstrap (pas.cc:127-209), the decision part, on the all-gathered error functions.
+    The step in inverse temperature is 0.25 quench_factor / (median - lower quartile of EF) (:147-154),
+    limited by invT_final (:156-158); per run the particles are resampled in proportion to
+    exp(-DinvT (EF - mean)/2) (:160-176); a particle drawn k > 1 times is copied k-1 times over particles
+    drawn 0 times, handed out from the END of the list as the reference does (:178-193).
+    Returns (DinvT, EFmin, EFmax, partcopy) with partcopy[i] = source particle or UNSET (keep)."""
+    EF_all = np.asarray(EF_all, dtype=np.float64)
+    ntot = EF_all.size
+    if ntot != nrun * npart:
+        raise ValueError("EF_all must hold nrun*npart values")
+    srt = np.sort(EF_all, kind="stable")
+    EFmin, EFmax = srt[int(0.25 * ntot)], srt[int(0.75 * ntot)]
+    EF_range = srt[int(0.5 * ntot)] - srt[int(0.25 * ntot)]
+    muav = 0.0
+    for v in EF_all:
+        muav += v
+    muav /= ntot
+    DinvT = 0.25 * quench_factor / EF_range
+    if invT_final is not None and invT + DinvT > invT_final:
+        DinvT = invT_final - invT
+    partcopy = np.full(ntot, UNSET, dtype=np.uint32)
+    u = _uniforms(seed, 0x9A5000000 + gen, ntot)
+    for ru in range(nrun):
+        w = np.exp(-0.5 * DinvT * (EF_all[ru * npart:(ru + 1) * npart] - muav))
+        wsum = np.cumsum(w)
+        num = np.zeros(npart, dtype=np.int64)
+        for j in range(npart):
+            z = u[ru * npart + j] * wsum[-1]
+            sel = int(np.searchsorted(wsum, z, side="left"))      # first sel with z <= wsum[sel] (:170)
+            num[min(sel, npart - 1)] += 1
+        lst = [ru * npart + j for j in range(npart) for _ in range(max(num[j] - 1, 0))]
+        for j in range(npart):
+            if num[j] == 0:
+                partcopy[ru * npart + j] = lst.pop()
+        assert not lst
+    return float(DinvT), float(EFmin), float(EFmax), partcopy
+
+
+def mc3_swap(run_all, invT_all, EF_all, seed, sweep):
+    """MC3::swap_states (mc3.cc:153-217), the decision part: five passes over neighbouring chains of the same
+    run, swap accepted with probability exp((invT_i - invT_{i+1}) (EF_i - EF_{i+1}) / 2) (:178-190).
+    Returns (order, ntr_inc, nac_inc): chain position i continues with the particle that was at order[i]
+    (the argument of Mpi::copy_particles, :207) and the proposal / acceptance counts to add per position."""
+    run_all = np.asarray(run_all)
+    invT = np.asarray(invT_all, dtype=np.float64)
+    EF = np.array(EF_all, dtype=np.float64)
+    ntot = EF.size
+    order = np.arange(ntot, dtype=np.uint32)
+    ntr = np.zeros(ntot, dtype=np.int64)
+    nac = np.zeros(ntot, dtype=np.int64)
+    u = _uniforms(seed, 0x3C3000000 + sweep, 5 * max(ntot - 1, 1))
+    k = 0
+    for _ in range(5):
+        for i in range(ntot - 1):
+            if run_all[i] == run_all[i + 1]:
+                al = np.exp(0.5 * (invT[i] - invT[i + 1]) * (EF[i] - EF[i + 1]))
+                ntr[i] += 1
+                if u[k] < al:
+                    nac[i] += 1
+                    order[i], order[i + 1] = order[i + 1], order[i]
+                    EF[i], EF[i + 1] = EF[i + 1], EF[i]
+            k += 1
+    return order, ntr, nac
+
+
+def copy_particles(batch, src_of_all, rank=0, world=1, dist=None, device=None):
+    """Mpi::copy_particles (mpi.cc:81-165) over particle shards: global particle i becomes a copy of global
+    particle src_of_all[i] (UNSET = keep).  Copies within a rank are one permutation on the device
+    (beep_permute, out of place); a particle whose source lives on another rank travels as struct Particle
+    -- (paramval, transnum) -- point to point, and its state is rebuilt by replay
+    (State::initialise_from_particle, state.cc:294-322).  All sources are read before any destination is
+    written, as the reference's send-then-overwrite order guarantees."""
+    src_of_all = np.asarray(src_of_all, dtype=np.uint32)
+    N = batch.P
+    lo = rank * N
+    mine = src_of_all[lo:lo + N]
+    local = np.full(N, UNSET, dtype=np.uint32)
+    incoming = []                                        # (local slot, source rank, source slot)
+    for k, s in enumerate(mine):
+        if s == UNSET or int(s) == lo + k:
+            continue
+        if lo <= int(s) < lo + N:
+            local[k] = int(s) - lo
+        else:
+            incoming.append((k, int(s) // N, int(s) % N))
+    outgoing = []                                        # (destination rank, local source slot, global destination)
+    if world > 1:
+        for i, s in enumerate(src_of_all):
+            if s != UNSET and lo <= int(s) < lo + N and not (lo <= i < lo + N):
+                outgoing.append((i // N, int(s) - lo, i))
+    received = []
+    if world > 1 and (incoming or outgoing):
+        import torch
+        dev = device if device is not None else torch.device("cpu")
+        reqs, keep = [], []
+        for dst_rank, slot, gdst in outgoing:                # read every source first
+            th, tn = batch.export_particle(slot)
+            t = torch.from_numpy(np.concatenate([th.ravel(), tn.ravel()])).to(dev)
+            keep.append(t)
+            reqs.append(dist.isend(t, dst=dst_rank, tag=gdst))
+        m = batch.model
+        nth, ntn = int(m.nparam), int(np.prod(m.traj_shape))
+        for k, src_rank, _ in incoming:
+            t = torch.empty(nth + ntn, dtype=torch.float64, device=dev)
+            reqs.append(dist.irecv(t, src=src_rank, tag=lo + k))
+            received.append((k, t))
+        for r in reqs:
+            r.wait()
+    if np.any(local != UNSET):
+        batch.permute(local)
+    if received:
+        m = batch.model
+        nth = int(m.nparam)
+        for k, t in received:
+            v = t.cpu().numpy()
+            batch.import_particle(k, v[:nth], v[nth:].reshape(m.traj_shape))
+        batch.replay()

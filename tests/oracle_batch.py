@@ -26,6 +26,7 @@ class OracleBatch:
         th = np.asarray(theta, dtype=np.float64)
         if th.ndim == 1:
             th = np.broadcast_to(th, (self.P, th.size))
+        self.theta = np.array(th, dtype=np.float64)
         for k in range(self.P):
             self.st[k].set_param(th[k])
 
@@ -49,7 +50,24 @@ class OracleBatch:
             self.st[k].pop[cur_step] = pop[k]
         self.cur_t = cur_step
 
-    def permute(self, src_of, what):
-        pops = self.pop_all()
+    def permute(self, src_of, what=0):
         src = [k if s == 0xFFFFFFFF else int(s) for k, s in enumerate(src_of)]
+        if what == 0:                                   # PERMUTE_FULL: struct Particle = (paramval, transnum)
+            snap = [self.export_particle(k) for k in range(self.P)]
+            for k, s in enumerate(src):
+                if s != k:
+                    self.import_particle(k, *snap[s])
+            return
+        pops = self.pop_all()
         self.set_pop_all(pops[src], self.cur_t)
+
+    def export_particle(self, slot):
+        return self.theta[slot].copy(), self.st[slot].transnum.copy()
+
+    def import_particle(self, slot, theta, transnum):
+        self.theta[slot] = theta
+        self.st[slot].set_param(theta)
+        self.st[slot].init_from_particle(np.ascontiguousarray(transnum, dtype=np.float64))
+
+    def replay(self):
+        pass                                            # init_from_particle already rebuilt the state
