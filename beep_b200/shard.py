@@ -213,19 +213,21 @@ def copy_particles(batch, src_of_all, rank=0, world=1, dist=None, device=None):
     if world > 1 and (incoming or outgoing):
         import torch
         dev = device if device is not None else torch.device("cpu")
-        reqs, keep = [], []
+        ops, keep = [], []
         for dst_rank, slot, gdst in outgoing:                # read every source first
             th, tn = batch.export_particle(slot)
             t = torch.from_numpy(np.concatenate([th.ravel(), tn.ravel()])).to(dev)
             keep.append(t)
-            reqs.append(dist.isend(t, dst=dst_rank, tag=gdst))
+            ops.append(dist.P2POp(dist.isend, t, dst_rank, tag=gdst))
         m = batch.model
         nth, ntn = int(m.nparam), int(np.prod(m.traj_shape))
         for k, src_rank, _ in incoming:
             t = torch.empty(nth + ntn, dtype=torch.float64, device=dev)
-            reqs.append(dist.irecv(t, src=src_rank, tag=lo + k))
+            ops.append(dist.P2POp(dist.irecv, t, src_rank, tag=lo + k))
             received.append((k, t))
-        for r in reqs:
+        # one group: NCCL matches sends and receives of a pair in posting order (both sides list them by
+        # global destination) and would deadlock on send-before-receive outside a group
+        for r in dist.batch_isend_irecv(ops):
             r.wait()
     if np.any(local != UNSET):
         batch.permute(local)

@@ -132,8 +132,11 @@ def test_copy_particles_across_gpus():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+        p.join(120)
+    hung = [p for p in procs if p.exitcode is None]
+    for p in hung:
+        p.kill()
+    assert not hung and all(p.exitcode == 0 for p in procs)
     a, b = two[0] + two[1], one[0]
     for x, y in zip(a, b):
         assert x[0] == y[0] and x[1] == y[1]
