@@ -999,6 +999,104 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 /* PMCMC bootstrap, pmcmc.cc:211-268 (host, O(Ntot))                          */
 /* ------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------ */
+/* a12  resampling decisions of the particle methods (host arithmetic)      */
+/* ------------------------------------------------------------------------ */
+/* The reference gathers per-particle scalars on rank 0, decides there with the global ran() and
+ * broadcasts; here every rank holds the all-gathered scalars and computes the identical decision from a
+ * counter-based stream keyed by (seed, generation / sweep), so there is no root and no broadcast. */
+static void decision_stream(BeepStream *rs, uint64_t seed, uint32_t key, uint32_t tag) { beep_stream_init(rs, seed, key, tag, 0xFFFFFFFEu); }
+
+extern "C" int beep_test_uniforms(uint64_t seed, uint32_t key, uint32_t tag, int n, double *out)
+{
+	if (!out || n < 0) return fail(BEEP_ERR_INVALID, "bad argument to beep_test_uniforms");
+	BeepStream rs;
+	decision_stream(&rs, seed, key, tag);
+	for (int i = 0; i < n; i++) out[i] = beep_next_uniform(&rs);
+	return BEEP_OK;
+}
+
+/* ABCMBP::EF_cutoff, abcmbp.cc:135-217: cut-off = mean of the two middle error functions (:149-150); the
+ * j-th best particle is kept and overwrites the (j + Ntot/2)-th (:158-163) */
+extern "C" int beep_ef_cutoff(const double *EF, int ntot, double *EFcut, double *EFmin, double *EFmax, uint32_t *partcopy)
+{
+	if (!EF || ntot < 2 || !EFcut || !EFmin || !EFmax || !partcopy) return fail(BEEP_ERR_INVALID, "bad argument to beep_ef_cutoff");
+	std::vector<uint32_t> ord(ntot);
+	for (int i = 0; i < ntot; i++) ord[i] = (uint32_t)i;
+	std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return EF[a] < EF[b]; });
+	const int half = ntot / 2;
+	*EFcut = 0.5 * (EF[ord[half - 1]] + EF[ord[half]]);
+	*EFmin = EF[ord[(int)(0.025 * ntot)]]; *EFmax = EF[ord[(int)(0.975 * ntot)]];
+	for (int i = 0; i < ntot; i++) partcopy[i] = 0xFFFFFFFFu;
+	for (int j = 0; j < half; j++) partcopy[ord[j + half]] = ord[j];
+	return BEEP_OK;
+}
+
+/* PAS::bootstrap, pas.cc:127-209 */
+extern "C" int beep_pas_bootstrap(const double *EF, int nrun, int npart, double invT, double quench_factor, double invT_final,
+                                  uint64_t seed, int gen, double *DinvT_out, double *EFmin, double *EFmax, uint32_t *partcopy)
+{
+	if (!EF || nrun <= 0 || npart <= 0 || !DinvT_out || !EFmin || !EFmax || !partcopy) return fail(BEEP_ERR_INVALID, "bad argument to beep_pas_bootstrap");
+	const int ntot = nrun * npart;
+	std::vector<double> srt(EF, EF + ntot);
+	std::sort(srt.begin(), srt.end());
+	*EFmin = srt[(int)(0.25 * ntot)]; *EFmax = srt[(int)(0.75 * ntot)];              /* :143 */
+	const double EF_range = srt[(int)(0.5 * ntot)] - srt[(int)(0.25 * ntot)];         /* :147 */
+	double muav = 0;
+	for (int i = 0; i < ntot; i++) muav += EF[i];
+	muav /= ntot;
+	double DinvT = 0.25 * quench_factor / EF_range;                                   /* :154 */
+	if (invT_final >= 0 && invT + DinvT > invT_final) DinvT = invT_final - invT;      /* :156-158 */
+	*DinvT_out = DinvT;
+	BeepStream rs;
+	decision_stream(&rs, seed, (uint32_t)gen, 0x9A5u);
+	std::vector<double> wsum(npart);
+	std::vector<unsigned> num(npart);
+	std::vector<uint32_t> list;
+	for (int ru = 0; ru < nrun; ru++) {
+		double sum = 0;
+		for (int j = 0; j < npart; j++) { sum += exp(-0.5 * DinvT * (EF[ru * npart + j] - muav)); wsum[j] = sum; }
+		for (int j = 0; j < npart; j++) num[j] = 0;
+		for (int j = 0; j < npart; j++) {
+			const double z = beep_next_uniform(&rs) * sum;
+			int sel = 0;
+			while (sel < npart - 1 && z > wsum[sel]) sel++;                              /* :170 (the last particle absorbs rounding) */
+			num[sel]++;
+		}
+		list.clear();
+		for (int j = 0; j < npart; j++) for (unsigned k = 1; k < num[j]; k++) list.push_back((uint32_t)(ru * npart + j));
+		for (int j = 0; j < npart; j++) {
+			if (num[j] > 0) partcopy[ru * npart + j] = 0xFFFFFFFFu;
+			else { partcopy[ru * npart + j] = list.back(); list.pop_back(); }             /* :186-188: handed out from the end */
+		}
+	}
+	return BEEP_OK;
+}
+
+/* MC3::swap_states, mc3.cc:153-217: five passes of neighbour swaps inside each run */
+extern "C" int beep_mc3_swap(const uint32_t *run, const double *invT, const double *EF_in, int ntot, uint64_t seed, int sweep,
+                             uint32_t *order, uint32_t *ntr_inc, uint32_t *nac_inc)
+{
+	if (!run || !invT || !EF_in || ntot <= 0 || !order || !ntr_inc || !nac_inc) return fail(BEEP_ERR_INVALID, "bad argument to beep_mc3_swap");
+	std::vector<double> EF(EF_in, EF_in + ntot);
+	for (int i = 0; i < ntot; i++) { order[i] = (uint32_t)i; ntr_inc[i] = 0; nac_inc[i] = 0; }
+	BeepStream rs;
+	decision_stream(&rs, seed, (uint32_t)sweep, 0x3C3u);
+	for (int loop = 0; loop < 5; loop++)
+		for (int i = 0; i + 1 < ntot; i++) {
+			const double u = beep_next_uniform(&rs);                                     /* one per pair, used or not: position-stable */
+			if (run[i] != run[i + 1]) continue;
+			const double al = exp(0.5 * (invT[i] - invT[i + 1]) * (EF[i] - EF[i + 1]));   /* :179 */
+			ntr_inc[i]++;
+			if (u < al) {
+				nac_inc[i]++;
+				std::swap(order[i], order[i + 1]);
+				std::swap(EF[i], EF[i + 1]);
+			}
+		}
+	return BEEP_OK;
+}
+
+/* ------------------------------------------------------------------------ */
 /* K7  ABC-SMC importance weights                                            */
 /* ------------------------------------------------------------------------ */
 extern "C" int beep_mvn_kernel_sums(BeepEngine *eng, int nvar, int nparam, const int *var, const double *inv_M, double size,

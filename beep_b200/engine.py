@@ -55,6 +55,11 @@ _SIGNATURES = {
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
+    "beep_ef_cutoff": (ctypes.c_int, [_vp, ctypes.c_int, _c_dp, _c_dp, _c_dp, _vp]),
+    "beep_pas_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int,
+                                          _c_dp, _c_dp, _c_dp, _vp]),
+    "beep_mc3_swap": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, _vp, _vp, _vp]),
+    "beep_test_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp]),
     "beep_mvn_kernel_sums": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]),
     "beep_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _c_dp, _vp]),
     "beep_test_poisson": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_int, _vp]),

@@ -6,8 +6,9 @@ particles pairwise (``mpi.cc:81-165,215-327``).  Here every rank all-gathers the
 particle) and computes the IDENTICAL decision from a shared counter-based key, so no root and no
 broadcast exist; only the states of ancestors that live on another rank move.
 
-The simulate / MBP / likelihood path itself has no collective.  Everything here is host logic over
-``torch.distributed`` (backend nccl on the GPU box, gloo in the CPU tests).
+The simulate / MBP / likelihood path itself has no collective.  The decisions themselves (bootstrap, cut-off, PAS resampling, MC3 swaps) are host
+routines of the C-ABI library (C++); this module is the ``torch.distributed`` plumbing around them (backend nccl on
+the GPU box, gloo in the CPU tests).
 """
 import numpy as np
 
@@ -43,20 +44,17 @@ def allgather(local, dist=None, device=None):
 
 
 def ef_cutoff_copy(EF_all):
-    """ABCMBP::EF_cutoff (abcmbp.cc:135-217), the decision part: sort the error functions, the cut-off
-    is the mean of the two middle values (:149-150), the j-th best particle is kept and the
+    """ABCMBP::EF_cutoff (abcmbp.cc:135-217), the decision part (beep_ef_cutoff): sort the error functions,
+    the cut-off is the mean of the two middle values (:149-150), the j-th best particle is kept and the
     (j + Ntot/2)-th is overwritten by a copy of it (:158-163).
     Returns (EFcut, EFmin, EFmax, partcopy) with partcopy[i] = source particle or 0xFFFFFFFF (keep)."""
-    EF_all = np.asarray(EF_all, dtype=np.float64)
-    n = EF_all.size
-    order = np.argsort(EF_all, kind="stable")
-    half = n // 2
-    EFcut = 0.5 * (EF_all[order[half - 1]] + EF_all[order[half]])
-    EFmin, EFmax = EF_all[order[int(0.025 * n)]], EF_all[order[int(0.975 * n)]]
-    partcopy = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
-    for j in range(half):
-        partcopy[order[j + half]] = order[j]
-    return float(EFcut), float(EFmin), float(EFmax), partcopy
+    import ctypes
+    from . import engine as E
+    EF_all = np.ascontiguousarray(EF_all, dtype=np.float64)
+    pc = np.zeros(EF_all.size, dtype=np.uint32)
+    cut, lo, hi = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    E._check(E.lib().beep_ef_cutoff(EF_all.ctypes.data, EF_all.size, ctypes.byref(cut), ctypes.byref(lo), ctypes.byref(hi), pc.ctypes.data))
+    return cut.value, lo.value, hi.value, pc
 
 
 class ShardedFilter:
@@ -112,75 +110,45 @@ class ShardedFilter:
 UNSET = 0xFFFFFFFF
 
 
-def _uniforms(seed, key, n):
-    """n uniforms from a counter-based stream that every rank can reproduce: the reference draws ran() on
-    rank 0 and broadcasts the decision; here the decision is replicated from a shared (seed, key)."""
-    return np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), int(key) & (2 ** 64 - 1)])).random(n)
+def _uniforms(seed, key, tag, n):
+    """the uniforms a decision consumes (test hook of the library)"""
+    from . import engine as E
+    out = np.zeros(n)
+    E._check(E.lib().beep_test_uniforms(int(seed), int(key), int(tag), n, out.ctypes.data))
+    return out
 
 
 def pas_bootstrap(EF_all, invT, quench_factor, nrun, npart, seed, gen, invT_final=None):
-    """PAS::bootstrap (pas.cc:127-209), the decision part, on the all-gathered error functions.
-    The step in inverse temperature is 0.25 quench_factor / (median - lower quartile of EF) (:147-154),
-    limited by invT_final (:156-158); per run the particles are resampled in proportion to
+    """PAS::bootstrap (pas.cc:127-209), the decision part (beep_pas_bootstrap), on the all-gathered error
+    functions: the step in inverse temperature is 0.25 quench_factor / (median - lower quartile of EF)
+    (:147-154), limited by invT_final (:156-158); per run the particles are resampled in proportion to
     exp(-DinvT (EF - mean)/2) (:160-176); a particle drawn k > 1 times is copied k-1 times over particles
     drawn 0 times, handed out from the END of the list as the reference does (:178-193).
     Returns (DinvT, EFmin, EFmax, partcopy) with partcopy[i] = source particle or UNSET (keep)."""
-    EF_all = np.asarray(EF_all, dtype=np.float64)
-    ntot = EF_all.size
-    if ntot != nrun * npart:
+    import ctypes
+    from . import engine as E
+    EF_all = np.ascontiguousarray(EF_all, dtype=np.float64)
+    if EF_all.size != nrun * npart:
         raise ValueError("EF_all must hold nrun*npart values")
-    srt = np.sort(EF_all, kind="stable")
-    EFmin, EFmax = srt[int(0.25 * ntot)], srt[int(0.75 * ntot)]
-    EF_range = srt[int(0.5 * ntot)] - srt[int(0.25 * ntot)]
-    muav = 0.0
-    for v in EF_all:
-        muav += v
-    muav /= ntot
-    DinvT = 0.25 * quench_factor / EF_range
-    if invT_final is not None and invT + DinvT > invT_final:
-        DinvT = invT_final - invT
-    partcopy = np.full(ntot, UNSET, dtype=np.uint32)
-    u = _uniforms(seed, 0x9A5000000 + gen, ntot)
-    for ru in range(nrun):
-        w = np.exp(-0.5 * DinvT * (EF_all[ru * npart:(ru + 1) * npart] - muav))
-        wsum = np.cumsum(w)
-        num = np.zeros(npart, dtype=np.int64)
-        for j in range(npart):
-            z = u[ru * npart + j] * wsum[-1]
-            sel = int(np.searchsorted(wsum, z, side="left"))      # first sel with z <= wsum[sel] (:170)
-            num[min(sel, npart - 1)] += 1
-        lst = [ru * npart + j for j in range(npart) for _ in range(max(num[j] - 1, 0))]
-        for j in range(npart):
-            if num[j] == 0:
-                partcopy[ru * npart + j] = lst.pop()
-        assert not lst
-    return float(DinvT), float(EFmin), float(EFmax), partcopy
+    pc = np.zeros(EF_all.size, dtype=np.uint32)
+    d, lo, hi = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    E._check(E.lib().beep_pas_bootstrap(EF_all.ctypes.data, nrun, npart, float(invT), float(quench_factor), -1.0 if invT_final is None else float(invT_final),
+                                        int(seed), int(gen), ctypes.byref(d), ctypes.byref(lo), ctypes.byref(hi), pc.ctypes.data))
+    return d.value, lo.value, hi.value, pc
 
 
 def mc3_swap(run_all, invT_all, EF_all, seed, sweep):
-    """MC3::swap_states (mc3.cc:153-217), the decision part: five passes over neighbouring chains of the same
-    run, swap accepted with probability exp((invT_i - invT_{i+1}) (EF_i - EF_{i+1}) / 2) (:178-190).
-    Returns (order, ntr_inc, nac_inc): chain position i continues with the particle that was at order[i]
-    (the argument of Mpi::copy_particles, :207) and the proposal / acceptance counts to add per position."""
-    run_all = np.asarray(run_all)
-    invT = np.asarray(invT_all, dtype=np.float64)
-    EF = np.array(EF_all, dtype=np.float64)
-    ntot = EF.size
-    order = np.arange(ntot, dtype=np.uint32)
-    ntr = np.zeros(ntot, dtype=np.int64)
-    nac = np.zeros(ntot, dtype=np.int64)
-    u = _uniforms(seed, 0x3C3000000 + sweep, 5 * max(ntot - 1, 1))
-    k = 0
-    for _ in range(5):
-        for i in range(ntot - 1):
-            if run_all[i] == run_all[i + 1]:
-                al = np.exp(0.5 * (invT[i] - invT[i + 1]) * (EF[i] - EF[i + 1]))
-                ntr[i] += 1
-                if u[k] < al:
-                    nac[i] += 1
-                    order[i], order[i + 1] = order[i + 1], order[i]
-                    EF[i], EF[i + 1] = EF[i + 1], EF[i]
-            k += 1
+    """MC3::swap_states (mc3.cc:153-217), the decision part (beep_mc3_swap): five passes over neighbouring
+    chains of the same run, swap accepted with probability exp((invT_i - invT_{i+1}) (EF_i - EF_{i+1}) / 2)
+    (:178-190).  Returns (order, ntr_inc, nac_inc): chain position i continues with the particle that was
+    at order[i] (the argument of Mpi::copy_particles, :207) and the proposal / acceptance counts to add."""
+    from . import engine as E
+    run = np.ascontiguousarray(run_all, dtype=np.uint32)
+    invT = np.ascontiguousarray(invT_all, dtype=np.float64)
+    EF = np.ascontiguousarray(EF_all, dtype=np.float64)
+    n = EF.size
+    order, ntr, nac = (np.zeros(n, dtype=np.uint32) for _ in range(3))
+    E._check(E.lib().beep_mc3_swap(run.ctypes.data, invT.ctypes.data, EF.ctypes.data, n, int(seed), int(sweep), order.ctypes.data, ntr.ctypes.data, nac.ctypes.data))
     return order, ntr, nac
 
 

@@ -205,6 +205,23 @@ double beep_last_simulate_ms(const BeepBatch *batch);
 int beep_bootstrap(const double *L_all_host, int ntot, double invT, uint64_t seed, int section,
                    double *loglik_inc, uint32_t *backpart_host);
 
+/* Resampling decisions of the particle methods, on
+ * scalars that every rank has all-gathered: pure host arithmetic, replicated
+ * on every rank from a counter-based stream keyed by (seed, generation/sweep)
+ * -- the reference decides on rank 0 with ran() and broadcasts.  partcopy[i] /
+ * order[i] are the argument of Mpi::copy_particles (mpi.cc:81-165):
+ * the particle that position i continues with, 0xFFFFFFFF = keep.
+ *   beep_ef_cutoff      ABCMBP::EF_cutoff   abcmbp.cc:135-217
+ *   beep_pas_bootstrap  PAS::bootstrap      pas.cc:127-209   (invT_final < 0: unset)
+ *   beep_mc3_swap       MC3::swap_states    mc3.cc:153-217   (ntr/nac: counts to add per position) */
+int beep_ef_cutoff(const double *EF_all_host, int ntot, double *EFcut, double *EFmin, double *EFmax, uint32_t *partcopy_host);
+int beep_pas_bootstrap(const double *EF_all_host, int nrun, int npart, double invT, double quench_factor, double invT_final,
+                       uint64_t seed, int gen, double *DinvT, double *EFmin, double *EFmax, uint32_t *partcopy_host);
+int beep_mc3_swap(const uint32_t *run_all_host, const double *invT_all_host, const double *EF_all_host, int ntot, uint64_t seed, int sweep,
+                  uint32_t *order_host, uint32_t *ntr_inc_host, uint32_t *nac_inc_host);
+/* test hook: the uniforms the decisions above consume (key = generation/sweep, tag 0x9A5 PAS / 0x3C3 MC3) */
+int beep_test_uniforms(uint64_t seed, uint32_t key, uint32_t tag, int n, double *out_host);
+
 /* ABC-SMC importance weights.  Replaces the loop of
  * ABCSMC::calculate_particle_weight (abcsmc.cc:260-271) over the previous
  * generation, with MVN::probability (mvn.cc:185-196) inside, for ALL proposals

@@ -88,6 +88,35 @@ private:
 	BeepBatch *h_ = nullptr;
 };
 
+/// ABCMBP::EF_cutoff (abcmbp.cc:135-217): cut-off and copy list from the all-gathered error functions
+struct CutoffDecision { double EFcut, EFmin, EFmax; std::vector<uint32_t> partcopy; };
+inline CutoffDecision ef_cutoff(const std::vector<double> &EF_all)
+{
+	CutoffDecision d;
+	d.partcopy.resize(EF_all.size());
+	check(beep_ef_cutoff(EF_all.data(), (int)EF_all.size(), &d.EFcut, &d.EFmin, &d.EFmax, d.partcopy.data()));
+	return d;
+}
+/// PAS::bootstrap (pas.cc:127-209): inverse-temperature step and copy list; invT_final < 0 = unset
+struct PasDecision { double DinvT, EFmin, EFmax; std::vector<uint32_t> partcopy; };
+inline PasDecision pas_bootstrap(const std::vector<double> &EF_all, int nrun, int npart, double invT, double quench_factor, double invT_final, uint64_t seed, int gen)
+{
+	PasDecision d;
+	d.partcopy.resize(EF_all.size());
+	check(beep_pas_bootstrap(EF_all.data(), nrun, npart, invT, quench_factor, invT_final, seed, gen, &d.DinvT, &d.EFmin, &d.EFmax, d.partcopy.data()));
+	return d;
+}
+/// MC3::swap_states (mc3.cc:153-217): new chain order and the proposal / acceptance counts to add per position
+struct SwapDecision { std::vector<uint32_t> order, ntr, nac; };
+inline SwapDecision mc3_swap(const std::vector<uint32_t> &run_all, const std::vector<double> &invT_all, const std::vector<double> &EF_all, uint64_t seed, int sweep)
+{
+	SwapDecision d;
+	const int n = (int)EF_all.size();
+	d.order.resize(n); d.ntr.resize(n); d.nac.resize(n);
+	check(beep_mc3_swap(run_all.data(), invT_all.data(), EF_all.data(), n, seed, sweep, d.order.data(), d.ntr.data(), d.nac.data()));
+	return d;
+}
+
 /// PMCMC::obs_prob (pmcmc.cc:180-207) + bootstrap (:211-268) on one GPU: log marginal likelihood
 /// estimate of the bootstrap particle filter for one parameter vector shared by all particles.
 inline double particle_filter(Engine &eng, BatchState &particles, const std::vector<double> &theta_all, uint64_t seed, double invT = 1.0)

@@ -106,7 +106,7 @@ def test_pas_bootstrap_decision():
     n = EF.size
     assert DinvT == 0.25 * quench / (srt[int(0.5 * n)] - srt[int(0.25 * n)])
     assert (EFmin, EFmax) == (srt[int(0.25 * n)], srt[int(0.75 * n)])
-    u = _uniforms(9, 0x9A5000000 + 4, n)
+    u = _uniforms(9, 4, 0x9A5, n)
     muav = EF.sum() / n
     for ru in range(nrun):
         wsum, s = [], 0.0
@@ -117,7 +117,7 @@ def test_pas_bootstrap_decision():
         for j in range(npart):
             z = u[ru * npart + j] * s
             sel = 0
-            while sel < npart and z > wsum[sel]:
+            while sel < npart - 1 and z > wsum[sel]:
                 sel += 1
             num[sel] += 1
         lst = [ru * npart + j for j in range(npart) for _ in range(max(num[j] - 1, 0))]
