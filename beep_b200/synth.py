@@ -210,3 +210,83 @@ def jitter_params(theta, nparticle, rel=0.05, seed=1):
     th[:, 0] = 0.0
     th[:, 3] = 1.0
     return th
+
+
+def write_reference_inputs(workdir, A=256, G=20, T=365, seed=SEED, name="synthetic"):
+    """Writes the synthetic population of make_model(A, G, T) as input files in the REFERENCE's own
+    formats (TOML + CSV: ages / comps / trans / R_spline / efoi_spline / areas / mixing matrices / data_tables,
+    as in the reference's examples/EX_C2.toml and EX_C4.toml), so that the unmodified reference can run the
+    same shape: A areas x G ages x 12 compartments (Erlang-2 on E, A, I, H) x 13 transitions x T daily steps.
+    Same generator and seed as make_model: populations, age matrix, sparse geographic matrix (written dense,
+    zeros elsewhere), branching probabilities by age and the R(t) knots are identical; age-specific
+    susceptibility and the seeded infections are left at the reference's defaults (1 and none -- the
+    external force of infection starts the epidemic).  Returns the TOML path (relative names inside)."""
+    import os
+    m, theta = make_model(A=A, G=G, T=T, seed=seed)
+    ar = m.arrays
+    data = os.path.join(workdir, f"Data_{name}")
+    os.makedirs(data, exist_ok=True)
+    ages = [f"a{k}" for k in range(G)]
+    pop = np.asarray(ar["pop_init"]).reshape(A, -1, G).sum(axis=1)
+    with open(os.path.join(data, "population.csv"), "w") as f:
+        f.write("area," + ",".join(ages) + "\n")
+        for c in range(A):
+            f.write(f"R{c}," + ",".join(str(int(v)) for v in pop[c]) + "\n")
+    np.savetxt(os.path.join(data, "age_matrix.csv"), np.asarray(ar["N0"]).reshape(G, G), delimiter=",", fmt="%.10g")
+    geo = np.zeros((A, A))
+    off, to, val, diag = ar["M_off"], ar["M_to"], ar["M_val"], ar["M_diag"]
+    for c in range(A):
+        geo[c, c] = diag[c]
+        for k in range(off[c], off[c + 1]):
+            geo[c, to[k]] = val[k]
+    geo = 0.5 * (geo + geo.T) / geo.diagonal().mean()          # the reference wants a symmetric matrix and normalises it itself
+    np.savetxt(os.path.join(data, "geo_matrix.csv"), geo, delimiter=",", fmt="%.10g")
+    age = np.arange(G) / max(G - 1, 1)
+    pA, pC, pD = 0.6 - 0.35 * age, 0.02 + 0.25 * age ** 2, 0.02 + 0.4 * age ** 2
+    fmt = lambda v: " | ".join(f"{x:.6g}" for x in v)
+    nknot = 12
+    Rv = theta[9:9 + nknot]
+    bps = ["start"] + [str(int(round(x))) for x in np.linspace(0, T, nknot)[1:-1]] + ["end"]      # break points are whole days
+    toml = f'''description = "synthetic scale-up population ({A} areas x {G} ages), written by beep_b200/synth.py"
+time_format = "number"
+start = "0"
+end = "{T}"
+steps_per_unit_time = 1
+datadir = "Data_{name}"
+outputdir = "Output_{name}"
+ages = {{cats="{' | '.join(ages)}"}}
+age_mixing_matrix = "age_matrix.csv"
+geo_mixing_matrix = "geo_matrix.csv"
+comps = [
+{{name="S"}},
+{{name="E", dist="Erlang", k="2", mean_value="3"}},
+{{name="A", dist="Erlang", k="2", mean_value="5", inf_value="0.55"}},
+{{name="I", dist="Erlang", k="2", mean_value="4", inf_value="1"}},
+{{name="C", dist="Exp", mean_value="2"}},
+{{name="H", dist="Erlang", k="2", mean_value="8"}},
+{{name="R"}},
+{{name="D"}}
+]
+trans = [
+{{from="S", to="E", infection="yes"}},
+{{from="E", to="A", prob_value="age: {fmt(pA)}"}},
+{{from="E", to="I", prob_value="age: *"}},
+{{from="A", to="R"}},
+{{from="I", to="R", prob_value="age: {fmt(1 - pC)}"}},
+{{from="I", to="C", prob_value="age: *"}},
+{{from="C", to="H"}},
+{{from="H", to="R", prob_value="age: {fmt(1 - pD)}"}},
+{{from="H", to="D", prob_value="age: *"}}
+]
+R_spline = [{{ value="{' | '.join(f'{x:.6g}' for x in Rv)}", bp="{' | '.join(bps)}"}}]
+efoi_spline = [{{ value="10"}}]
+areas = "population.csv"
+data_tables = [
+{{type="transition", observation="S->E", timestep="7", obsmodel="normal 10%", geo_dep="area", file="S-E.csv"}},
+{{type="population", observation="H", timestep="7", obsmodel="normal 10%", geo_dep="area", file="H.csv"}}
+]
+'''
+    path = os.path.join(workdir, f"{name}.toml")
+    with open(path, "w") as f:
+        f.write(toml)
+    return path

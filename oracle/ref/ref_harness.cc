@@ -21,6 +21,7 @@
 // tests/golden/make_golden.py.
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -407,6 +408,29 @@ int main(int argc, char **argv)
 		pk.f64("theta",flat2(theta),{(long)theta.size(),(long)model.param.size()});
 		vector <double> pr; for(const auto &th : theta) pr.push_back(model.prior(th));
 		pk.f64("prior",pr);
+	}
+
+	// ---- CPU-baseline mode (bench.py --impl reference): the reference's own State::simulate(param)
+	// (set_param + tau-leap, state.cc:582-592) and ObservationModel::calculate (obsmodel.cc:22-35) with its
+	// own std:: samplers, repeated for BEEP_HARNESS_BENCH seconds; nothing else is written
+	if(getenv("BEEP_HARNESS_BENCH")){
+		double budget = atof(getenv("BEEP_HARNESS_BENCH"));
+		details.stochastic = true;
+		State st(details,data,model,obsmodel);
+		st.simulate(theta[0]);
+		volatile double sink = obsmodel.calculate(&st);
+		struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC,&t0);
+		long reps = 0; double el = 0;
+		do{
+			st.simulate(theta[0]);
+			sink = obsmodel.calculate(&st);
+			reps++;
+			clock_gettime(CLOCK_MONOTONIC,&t1); el = (t1.tv_sec-t0.tv_sec)+1e-9*(t1.tv_nsec-t0.tv_nsec);
+		}while(el < budget);
+		(void)sink;
+		printf("BENCH reps=%ld seconds=%.6f T=%u A=%u D=%u\n",reps,el,(unsigned)T,(unsigned)data.narea,(unsigned)data.ndemocatpos);
+		pk.close();
+		return 0;
 	}
 
 	const bool stoch0 = details.stochastic;
