@@ -98,6 +98,12 @@ def main():
         for old, new in subs:
             txt = txt.replace(old, new)
         open(os.path.join(work, toml), "w").write(txt)
+    # the synthetic scale-up shape (BASELINE.json configs[4]) at a size the reference dumps in seconds, written
+    # in the reference's own input formats by beep_b200/synth.py: 12 areas x 20 ages x 12 compartments x 140 steps
+    from beep_b200.synth import write_reference_inputs
+    write_reference_inputs(work, A=12, G=20, T=140, name="synthetic12")
+    CASES["SYN_A12"] = ("synthetic12.toml", ["mode=sim"], 1, 59)
+    BIG.add("SYN_A12")
     for name, (toml, args, ntheta, seed) in CASES.items():
         if only and name not in only:
             continue
