@@ -53,6 +53,7 @@ STAT = {
     "stat_EX": ("examples/EX.toml", ["mode=sim"], 1, 61, 10000),
     "stat_EX_C4": ("examples/EX_C4.toml", ["mode=sim"], 1, 67, 10000),
 }
+POSTERIOR = {"post_EX_A1": ("examples/EX_A1.toml", 2000)}      # BASELINE.json configs[1]: ~2.5 minutes of the reference
 MVN_CASES = {
     "mvn_small": (12, 7, 60, 16, 71),          # a handful of free parameters (EX_A1-like)
     "mvn_england": (180, 140, 400, 24, 73),    # England_AS-like: 180 parameters, most of them free
@@ -138,6 +139,24 @@ def main():
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: {reps} replicates, {os.path.getsize(path) / 1024:.0f} KiB")
+    # posterior fixtures: the reference's own MCMC-MBP run (mode=mcmcmbp, invT=1) -> Parameter_estimates.csv
+    for name, (toml, nsample) in POSTERIOR.items():
+        if only and name not in only:
+            continue
+        outdir = os.path.join(work, "out_" + name)
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "BEEP"), f"inputfile={toml}", "mode=mcmcmbp", f"nsample={nsample}", "invT=1", f"outputdir={outdir}"],
+                           cwd=work, capture_output=True, text=True)
+        est = os.path.join(outdir, "Parameter_estimates.csv")
+        if not os.path.exists(est):
+            print(f"{name}: reference run FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        import csv
+        import json
+        rows = list(csv.DictReader(open(est)))
+        out = {"command": f"BEEP inputfile={toml} mode=mcmcmbp nsample={nsample} invT=1", "parameters": [
+            {"name": x["Name"], "mean": float(x["Mean"]), "sd": float(x["SD"]), "ess": (float(x["ESS"]) if x["ESS"] not in ("---", "") else None), "prior": x["Prior"]} for x in rows]}
+        json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
+        print(f"{name}: {len(rows)} parameters")
     # ABC-SMC weight kernel: the reference's MVN::setup / propose / probability
     # (oracle/ref/ref_mvn.cc): name -> (nparam, nvar, Nlast, Nprop, seed)
     for name, (nparam, nvar, nl, npr, seed) in MVN_CASES.items():
