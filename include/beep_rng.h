@@ -276,6 +276,33 @@ static const double beep_inv_host[64] = {0.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 3.0, 1
 /* PTRS squeeze failed: the exact acceptance test (Hormann 1993, step 3) */
 BEEP_HD_COLD int beep_ptrs_accept(double lam, double a, double b, double us, double V, double kf)
 {
+#if defined(__CUDA_ARCH__)
+	/* Device pre-test with the hardware-assisted log (libdevice, <= 1 ulp, ~1/3 of the instructions of
+	 * the portable beep_log).  Both sides of the exact test below are sums of a few logarithms scaled
+	 * by at most kf; the two evaluations can differ by a few ulps of the largest term (beep_log is
+	 * itself within ~1 ulp of log, the Stirling tail is the same formula), i.e. by < 1e-14 * scale.
+	 * Whenever the pre-test separates the two sides by more than 1e-9 * scale its verdict IS the
+	 * exact test's verdict; otherwise (probability ~1e-6 per call) the exact test decides.  Results are
+	 * therefore bit-identical to the host oracle, which always runs the exact test. */
+	{
+		const double inva = BR_ADD(1.1239, BR_DIV(1.1328, BR_SUB(b, 3.4)));
+		const double tt = BR_ADD(BR_DIV(a, BR_MUL(us, us)), b);
+		const double ll = log(lam);
+		double lf;
+		if (kf < 16.0) lf = beep_lfact(kf);                 /* table */
+		else {
+			const double ik = 1.0 / kf, ik2 = ik * ik;
+			lf = (kf + 0.5) * log(kf) - kf + 9.189385332046727417803297364056e-01 +
+			     ik * (8.333333333333333333e-02 + ik2 * (-2.777777777777777778e-03 + ik2 * (7.936507936507936508e-04 + ik2 * -5.952380952380952381e-04)));
+		}
+		const double lhs = log(V) + log(inva) - log(tt);
+		const double klam = kf * ll;
+		const double rhs = klam - lam - lf;
+		const double scale = fabs(klam) + lam + fabs(lf) + fabs(lhs) + 1.0;
+		const double diff = lhs - rhs;
+		if (fabs(diff) > 1e-9 * scale) return diff <= 0.0;
+	}
+#endif
 	double invalpha = BR_ADD(1.1239, BR_DIV(1.1328, BR_SUB(b, 3.4)));
 	double loglam = beep_log(lam);
 	double lhs_c = beep_log(invalpha);
