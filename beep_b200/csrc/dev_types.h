@@ -59,7 +59,7 @@ struct TrajSm { int Gs, n0, ctab, common, JDe, JD32, ns, ae, foi, nmi, iv, nbr, 
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline TrajSm traj_sm_layout(int G, int J, int D)
+static inline TrajSm traj_sm_layout(int G, int J, int D, int nbr_doubles = 64)
 {
 	TrajSm L;
 	int gs = BEEP_EVEN(G);
@@ -73,7 +73,7 @@ static inline TrajSm traj_sm_layout(int G, int J, int D)
 	L.foi = L.ae + BEEP_EVEN((L.JDe + 3) >> 2);
 	L.iv = L.foi + BEEP_EVEN(D);
 	L.nbr = L.iv + gs;
-	L.nmi = L.nbr + 64;
+	L.nmi = L.nbr + BEEP_EVEN(nbr_doubles);   /* 32 staged Nbr entries; without neighbours only the staged spline values (if any) */
 	L.work = L.nmi + BEEP_EVEN(G);
 	return L;
 }

@@ -332,18 +332,35 @@ static const void *traj_fn(int mode, int sync, bool keep)
 }
 
 static size_t even(size_t x) { return (x + 1) & ~(size_t)1; }
+/* size of the per-warp neighbour staging area: 32 entries of 16 bytes when the mixing matrix has
+ * off-diagonal entries; otherwise only what ntime_refresh stages there (nspline + 1 spline values) */
+static int traj_nbr_doubles(const DevModel &m) { return m.M_nnz > 0 ? 64 : (m.nmm > 0 ? m.nspline + 1 : 0); }
 
 static int choose_launch(BeepEngine *eng)
 {
 	const DevModel &m = eng->dm;
-	const TrajSm L = traj_sm_layout(m.G, m.J, m.D);      /* the kernel computes the same layout */
+	const TrajSm L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));      /* handed to the kernel in its arguments */
 	const size_t CDp = (size_t)m.CDp, common = (size_t)L.common, work = (size_t)L.work;
 	const char *force = getenv("BEEP_FORCE_SYNC");      /* tests: exercise every flavour on small models */
 	auto cta_bytes = [&](int nwarp) { return (common + (size_t)m.A * CDp + even(2 * (size_t)m.S * m.A * m.G) + nwarp * work) * sizeof(double); };
 	if (m.M_nnz == 0) {
-		eng->sync_mode = SYNC_NONE; eng->nwarp = 4;
+		eng->sync_mode = SYNC_NONE;
 		const size_t ntsz = (m.nmm > 0) ? (size_t)m.G * L.Gs : 0;      /* the warp's copy of Ntime (k_traj) */
-		eng->smem_traj = (common + eng->nwarp * (CDp + work + even(2 * (size_t)m.S * m.G) + ntsz)) * sizeof(double);
+		auto none_bytes = [&](int nwarp) { return (common + nwarp * (CDp + work + even(2 * (size_t)m.S * m.G) + ntsz)) * sizeof(double); };
+		/* warps per CTA: the trajectory of a tile is one long dependent chain, so what counts is the number
+		 * of resident warps per SM -- take the CTA size (4..8 warps) that the occupancy calculator likes best
+		 * (the CTA-common tables and the per-CTA reservation are amortised differently) */
+		int best = 4, best_warps = -1;
+		for (int nw = 4; nw <= BEEP_TRAJ_NWARP; nw++) {
+			if (none_bytes(nw) > (size_t)eng->smem_optin) break;
+			const void *fn = traj_fn(MODE_SIM, SYNC_NONE, false);
+			if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)none_bytes(nw)) != cudaSuccess) break;
+			int nb = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nw * 32, none_bytes(nw)) != cudaSuccess) break;
+			if (nb * nw > best_warps) { best_warps = nb * nw; best = nw; }
+		}
+		eng->nwarp = best;
+		eng->smem_traj = none_bytes(best);
 	} else {
 		eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A);
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
@@ -536,7 +553,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
 	a.nwarp = eng->nwarp; a.chunk = 1;
-	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D);
+	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));
 	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
 	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && mode != MODE_REPLAY && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
 	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
