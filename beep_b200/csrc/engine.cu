@@ -58,7 +58,7 @@ struct BeepBatch {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool have_params = false, have_sim_time = false;
 	int cur_t = 0;
-	double *d_scratch = nullptr;    /* [P * max(K5_CHUNKS, OBS_CHUNKS*(1+ntable))] */
+	double *d_scratch = nullptr;    /* [P * max(k5_chunks, OBS_CHUNKS*(1+ntable))] */
 	double *h_pinned = nullptr; size_t h_pinned_n = 0;
 	unsigned *d_map = nullptr; unsigned char *d_flag = nullptr;
 	unsigned char *d_mask = nullptr; size_t d_mask_n = 0;
@@ -456,7 +456,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
 	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)P * 16);
-	BA(bt->d_scratch, (size_t)P * std::max<size_t>(K5_CHUNKS, (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
+	BA(bt->d_scratch, (size_t)P * std::max<size_t>(k5_chunks((size_t)m.T * m.A * m.J * m.D), (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
 		std::vector<unsigned long long> ids(P);
@@ -718,8 +718,9 @@ extern "C" int beep_latent_loglik(BeepBatch *bt, double *Li_host)
 	if (!bt->db.tm || (m.stochastic && !bt->db.tn)) return fail(BEEP_ERR_STATE, "beep_latent_loglik needs a batch that keeps transnum and transmean");
 	CU(cudaSetDevice(eng->device));
 	const int P = bt->db.P;
-	k_latent_partial<<<dim3(P, K5_CHUNKS), RED_THREADS, 0, bt->stream>>>(m, bt->db, bt->d_scratch);
-	k_latent_final<<<(P + 127) / 128, 128, 0, bt->stream>>>(P, bt->d_scratch, bt->db.Li);
+	const int nch = k5_chunks((size_t)m.T * m.A * m.J * m.D);
+	k_latent_partial<<<dim3(P, nch), RED_THREADS, 0, bt->stream>>>(m, bt->db, bt->d_scratch);
+	k_latent_final<<<(P + 127) / 128, 128, 0, bt->stream>>>(P, nch, bt->d_scratch, bt->db.Li);
 	eng->launches += 2;
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(Li_host, bt->db.Li, P * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));

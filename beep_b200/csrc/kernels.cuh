@@ -1516,28 +1516,44 @@ __global__ void k_obs_reduce(DevModel m, int P, int want_tables, int nch, const 
 /* ------------------------------------------------------------------------ */
 /* K5  latent-process likelihood, state.cc:812-826                           */
 /* ------------------------------------------------------------------------ */
-#define K5_CHUNKS 64
+/* The cells of a particle are cut into nch chunks (one CTA each, fixed reduction tree) that k_latent_final
+ * adds in chunk order.  nch depends on the model only (k5_chunks), never on the batch, so a particle's
+ * likelihood does not depend on the particles around it.  Most cells of an epidemic have no event:
+ * k = 0 gives exactly -lam (0 log(lam) = 0, lgamma(1) = 0) and k = 1 needs no lgamma -- the kernel then
+ * runs at the speed of its two input streams (4 + 8 bytes per cell). */
+#define K5_MAX_CHUNKS 1024
+static inline int k5_chunks(size_t ncell) { return (int)std::max<size_t>(1, std::min<size_t>(K5_MAX_CHUNKS, ncell / 65536)); }
+/* log(k!) for k < 32 (correctly rounded; lgamma(k+1) agrees to an ulp or two -- the contract on L is 1e-10) */
+__device__ const double d_lfact32[32] = {0.0, 0.0, 0.693147180559945, 1.7917594692280554, 3.178053830347945, 4.787491742782047, 6.579251212010102, 8.525161361065415, 10.604602902745249, 12.801827480081467, 15.104412573075514, 17.502307845873887, 19.987214495661885, 22.55216385312342, 25.191221182738683, 27.89927138384089, 30.671860106080672, 33.50507345013689, 36.39544520803305, 39.339884187199495, 42.335616460753485, 45.38013889847691, 48.47118135183522, 51.60667556776438, 54.78472939811232, 58.00360522298052, 61.26170176100201, 64.55753862700634, 67.88974313718153, 71.257038967168, 74.65823634883017, 78.0922235533153};
+__device__ __forceinline__ double d_poisson_probability_fast(int i, double lam)                  /* utils.cc:157-170 */
+{
+	if (lam == 0) return (i == 0) ? 0.0 : -BEEP_LARGE;
+	if (i < 0) return -BEEP_LARGE;
+	if (i == 0) return -lam;                            /* 0 log(lam) - lam - lgamma(1) with lam in (0, inf): exactly -lam */
+	if (i == 1) return log(lam) - lam;                  /* lgamma(2) = 0 */
+	return i * log(lam) - lam - (i < 32 ? d_lfact32[i] : lgamma((double)(i + 1)));
+}
 __global__ void __launch_bounds__(RED_THREADS) k_latent_partial(DevModel m, DevBatch b, double *partial)
 {
 	__shared__ double red[RED_THREADS / 32];
-	const int p = blockIdx.x, ch = blockIdx.y;
+	const int p = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
 	const size_t n = (size_t)m.T * m.A * m.J * m.D;
-	const size_t lo = n * ch / K5_CHUNKS, hi = n * (ch + 1) / K5_CHUNKS;
+	const size_t lo = n / nch * ch + min((size_t)ch, n % nch), hi = lo + n / nch + ((size_t)ch < n % nch ? 1 : 0);
 	const int *tn = b.tn + (size_t)p * n;
 	const double *tm = b.tm + (size_t)p * n;
 	double acc = 0;
 	for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
 		double lam = tm[i];
 		int k = m.stochastic ? tn[i] : (int)lam;
-		acc += d_poisson_probability(k, lam);
+		acc += d_poisson_probability_fast(k, lam);
 	}
 	double s = block_sum(acc, red);
-	if (threadIdx.x == 0) partial[(size_t)p * K5_CHUNKS + ch] = s;
+	if (threadIdx.x == 0) partial[(size_t)p * nch + ch] = s;
 }
-__global__ void k_latent_final(int P, const double *partial, double *Li)
+__global__ void k_latent_final(int P, int nch, const double *partial, double *Li)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p < P) { double s = 0; for (int i = 0; i < K5_CHUNKS; i++) s += partial[(size_t)p * K5_CHUNKS + i]; Li[p] = s; }
+	if (p < P) { double s = 0; for (int i = 0; i < nch; i++) s += partial[(size_t)p * nch + i]; Li[p] = s; }
 }
 
 /* ------------------------------------------------------------------------ */
