@@ -555,7 +555,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.nwarp = eng->nwarp; a.chunk = 1;
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));
 	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
-	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && mode != MODE_REPLAY && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
+	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
 	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;

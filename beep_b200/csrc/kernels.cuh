@@ -837,7 +837,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 }
 
 /* The same tile step for the common model structure -- one strain, dp == age (D == G > 1),
- * stochastic dynamics, MODE_SIM / MODE_MBP -- written against explicit shared addresses:
+ * stochastic dynamics, MODE_SIM / MODE_MBP / MODE_REPLAY -- written against explicit shared addresses:
  *   wb    the warp's work area (ns, ae, foi, Iv, nbr), pa the tile's population, ca the CTA tables.
  * Same operations in the same order as tile_step (hence as the oracle); the scan is branch-free:
  * the cell table is padded to a multiple of 32 with never-firing cells and crate[] holds the
@@ -928,6 +928,18 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		const int e = e0 + lane;
 		const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
 		const double popu = lds64(pa + ((w & 0xfffu) << 3));
+		if (MODE == MODE_REPLAY) {
+			/* the events are given (state.cc:294-322); only the means are recomputed */
+			if (e < JD) {
+				double mean = dt * popu * crate[e];
+				if ((w >> 24) == 1u) mean *= lds64(foi_a + ((w >> 15) & 0x1f8u));
+				if (!(popu > 0)) mean = 0;
+				const int num = b.tn[tbase + e];
+				if (keep_tm) b.tm[tbase + e] = mean;
+				if (num != 0) { sts64(ns_a + e * 8, (double)num); trbits |= 1u << ((w >> 12) & 63); }
+			}
+			continue;
+		}
 		if (!__any_sync(FULLMASK, popu > 0 && (w >> 25) == 0u)) {          /* kind 2 (and the padding) never fires */
 			if (KEEP && e < JD) {
 				if (keep_tm) b.tm[tbase + e] = 0;
@@ -955,7 +967,7 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 	const int nsmall = (int)(cnt2 & 0xffffu), nbig = (int)(cnt2 >> 16);
 
 	/* 3. draws on the dense lists */
-	if (nsmall + nbig > 0) {
+	if (MODE != MODE_REPLAY && nsmall + nbig > 0) {
 		__syncwarp();
 		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
 		const unsigned long long sid = b.stream_id[p];
@@ -1188,7 +1200,7 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 	}
 	__syncthreads();
 	const unsigned ca = launder(smem_addr(smraw));
-	const bool fast = MODE != MODE_REPLAY && a.fast != 0;
+	const bool fast = a.fast != 0;
 	double *sm = smraw + L.common;
 
 	if (SYNC == SYNC_NONE) {
