@@ -11,6 +11,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -1016,6 +1018,86 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 /* ------------------------------------------------------------------------ */
 /* PMCMC bootstrap, pmcmc.cc:211-268 (host, O(Ntot))                          */
 /* ------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------ */
+/* N4  posterior sample files, State::save / State::load (state.cc:709-790) */
+/* ------------------------------------------------------------------------ */
+/* Byte-compatible with the reference's Posterior/samples/sampleN_{parameter,transition}.csv: the same
+ * std::ostream default formatting of doubles (6 significant digits), the same row and column order
+ * [sett][area][trans][dp], the same mid-step times details.division_time (details.cc:102-105). */
+extern "C" int beep_save_sample(BeepBatch *bt, int slot, const char *file_prefix, const char *const *param_names, double EF, double start_time)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	if (!file_prefix || !param_names) return fail(BEEP_ERR_INVALID, "null argument");
+	const DevModel &m = bt->eng->dm;
+	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D, AJD = (size_t)m.A * m.J * m.D;
+	std::vector<double> theta(m.nparam), tn(TAJD);
+	rc = beep_export_particle(bt, slot, theta.data(), tn.data());
+	if (rc) return rc;
+	{
+		std::string name = std::string(file_prefix) + "_parameter.csv";
+		std::ofstream outp(name.c_str());
+		if (!outp) return fail(BEEP_ERR_INVALID, "cannot open the file '%s'", name.c_str());
+		outp << "Parameter,Value" << std::endl;
+		outp << "Error function," << EF << std::endl;
+		for (int th = 0; th < m.nparam; th++) outp << param_names[th] << "," << theta[th] << std::endl;
+	}
+	{
+		std::string name = std::string(file_prefix) + "_transition.csv";
+		std::ofstream outp(name.c_str());
+		if (!outp) return fail(BEEP_ERR_INVALID, "cannot open the file '%s'", name.c_str());
+		outp << "Time,Transitions (ordered by area x trans x democatpos)" << std::endl;
+		const int period = m.period;
+		for (int sett = 0; sett < m.T; sett++) {
+			outp << (double((sett + 0.5) * period) / m.T + start_time);
+			const double *row = tn.data() + (size_t)sett * AJD;
+			for (size_t k = 0; k < AJD; k++) outp << "," << row[k];
+			outp << std::endl;
+		}
+	}
+	return BEEP_OK;
+}
+
+extern "C" int beep_load_sample(BeepBatch *bt, int slot, const char *file_prefix, const char *const *param_names, double *EF_out)
+{
+	int rc = slot_ok(bt, slot);
+	if (rc) return rc;
+	if (!file_prefix) return fail(BEEP_ERR_INVALID, "null argument");
+	const DevModel &m = bt->eng->dm;
+	const size_t AJD = (size_t)m.A * m.J * m.D;
+	std::vector<double> theta(m.nparam), tn((size_t)m.T * AJD, 0.0);
+	auto split = [](const std::string &ln) { std::vector<std::string> v; std::stringstream ss(ln); std::string f; while (std::getline(ss, f, ',')) v.push_back(f); return v; };
+	{
+		std::string name = std::string(file_prefix) + "_parameter.csv", line;
+		std::ifstream inp(name.c_str());
+		if (!inp) return fail(BEEP_ERR_INVALID, "cannot open the file '%s'", name.c_str());
+		std::getline(inp, line);
+		std::getline(inp, line);
+		auto f = split(line);
+		if (f.size() != 2) return fail(BEEP_ERR_INVALID, "problem loading the file '%s'", name.c_str());
+		if (EF_out) *EF_out = atof(f[1].c_str());
+		for (int th = 0; th < m.nparam; th++) {
+			if (!std::getline(inp, line)) return fail(BEEP_ERR_INVALID, "the file '%s' is too short", name.c_str());
+			f = split(line);
+			if (f.size() != 2 || (param_names && f[0] != param_names[th])) return fail(BEEP_ERR_INVALID, "parameter %d of '%s' is not '%s'", th, name.c_str(), param_names ? param_names[th] : "?");
+			theta[th] = atof(f[1].c_str());
+		}
+	}
+	{
+		std::string name = std::string(file_prefix) + "_transition.csv", line;
+		std::ifstream inp(name.c_str());
+		if (!inp) return fail(BEEP_ERR_INVALID, "cannot open the file '%s'", name.c_str());
+		std::getline(inp, line);
+		for (int sett = 0; sett < m.T; sett++) {
+			if (!std::getline(inp, line)) break;                          /* a posterior shorter than the prediction period (simulate.cc:153) */
+			auto f = split(line);
+			if (f.size() != AJD + 1) return fail(BEEP_ERR_INVALID, "row %d of '%s' has %zu fields, not %zu", sett, name.c_str(), f.size(), AJD + 1);
+			for (size_t k = 0; k < AJD; k++) tn[(size_t)sett * AJD + k] = atof(f[k + 1].c_str());
+		}
+	}
+	return beep_import_particle(bt, slot, theta.data(), tn.data());
+}
+
 /* ------------------------------------------------------------------------ */
 /* a12  resampling decisions of the particle methods (host arithmetic)      */
 /* ------------------------------------------------------------------------ */

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
+    "beep_save_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_double, ctypes.c_double]),
+    "beep_load_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, _c_dp]),
     "beep_ef_cutoff": (ctypes.c_int, [_vp, ctypes.c_int, _c_dp, _c_dp, _c_dp, _vp]),
     "beep_pas_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int,
                                           _c_dp, _c_dp, _c_dp, _vp]),
@@ -244,6 +246,20 @@ class Batch:
     def import_particle(self, slot, theta, transnum):
         th, tn = _f64(theta), _f64(transnum)
         _check(self.L.beep_import_particle(self.h, slot, th.ctypes.data, tn.ctypes.data))
+
+    def save_sample(self, slot, prefix, param_names, EF, start_time=0.0):
+        """State::save (state.cc:709-739): <prefix>_parameter.csv and <prefix>_transition.csv"""
+        arr = (ctypes.c_char_p * len(param_names))(*[n.encode() for n in param_names])
+        _check(self.L.beep_save_sample(self.h, slot, prefix.encode(), ctypes.cast(arr, ctypes.c_void_p), float(EF), float(start_time)))
+
+    def load_sample(self, slot, prefix, param_names=None):
+        """State::load (state.cc:743-790); returns the stored error function.  Call replay() afterwards."""
+        ef = ctypes.c_double()
+        arr = None
+        if param_names is not None:
+            arr = ctypes.cast((ctypes.c_char_p * len(param_names))(*[n.encode() for n in param_names]), ctypes.c_void_p)
+        _check(self.L.beep_load_sample(self.h, slot, prefix.encode(), arr, ctypes.byref(ef)))
+        return ef.value
 
     # -- read-back ----------------------------------------------------------
     def derived(self, slot, which):

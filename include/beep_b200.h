@@ -205,6 +205,17 @@ double beep_last_simulate_ms(const BeepBatch *batch);
 int beep_bootstrap(const double *L_all_host, int ntot, double invT, uint64_t seed, int section,
                    double *loglik_inc, uint32_t *backpart_host);
 
+/* Posterior sample files: State::save / State::load
+ * (state.cc:709-790) straight from / into a slot of a batch.  Writes and reads
+ * <prefix>_parameter.csv and <prefix>_transition.csv byte-compatibly with the
+ * reference's Posterior/samples/sampleN_* files (same number formatting, same
+ * [sett][area][trans][dp] order, times = details.division_time).  param_names:
+ * model.param[th].name, [nparam]; start_time: details.start for
+ * time_format = "number", else 0.  After beep_load_sample call beep_replay to
+ * rebuild populations and means (State::initialise_from_particle).            */
+int beep_save_sample(BeepBatch *batch, int slot, const char *file_prefix, const char *const *param_names, double EF, double start_time);
+int beep_load_sample(BeepBatch *batch, int slot, const char *file_prefix, const char *const *param_names, double *EF_out);
+
 /* Resampling decisions of the particle methods, on
  * scalars that every rank has all-gathered: pure host arithmetic, replicated
  * on every rank from a counter-based stream keyed by (seed, generation/sweep)

@@ -157,6 +157,11 @@ def main():
             {"name": x["Name"], "mean": float(x["Mean"]), "sd": float(x["SD"]), "ess": (float(x["ESS"]) if x["ESS"] not in ("---", "") else None), "prior": x["Prior"]} for x in rows]}
         json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
         print(f"{name}: {len(rows)} parameters")
+        # one of the run's posterior sample files (State::save, state.cc:709-739) as the fixture of the sample-file round trip
+        sdir = os.path.join(ROOT, "tests", "golden", "samples_" + name[len("post_"):])
+        os.makedirs(sdir, exist_ok=True)
+        for suffix in ("_parameter.csv", "_transition.csv"):
+            shutil.copy(os.path.join(outdir, "Posterior", "samples", "sample7" + suffix), os.path.join(sdir, "sample7" + suffix))
     # ABC-SMC weight kernel: the reference's MVN::setup / propose / probability
     # (oracle/ref/ref_mvn.cc): name -> (nparam, nvar, Nlast, Nprop, seed)
     for name, (nparam, nvar, nl, npr, seed) in MVN_CASES.items():
