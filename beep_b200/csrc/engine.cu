@@ -59,6 +59,7 @@ struct BeepBatch {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool have_params = false, have_sim_time = false;
+	bool theta_dirty = false;       /* a slot's parameters were replaced (beep_import_particle): the derived tables are re-derived before the next launch that reads them */
 	int cur_t = 0;
 	double *d_scratch = nullptr;    /* [P * max(k5_chunks, OBS_CHUNKS*(1+ntable))] */
 	double *h_pinned = nullptr; size_t h_pinned_n = 0;
@@ -521,6 +522,7 @@ static int launch_set_param(BeepBatch *bt)
 	eng->launches += 4;
 	CU(cudaGetLastError());
 	bt->have_params = true;
+	bt->theta_dirty = false;
 	return BEEP_OK;
 }
 
@@ -551,6 +553,11 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 {
 	BeepEngine *eng = bt->eng;
 	const DevModel &m = eng->dm;
+	if (bt->theta_dirty) {
+		/* State::initialise_from_particle starts with set_param (state.cc:296): K0 from the parameters on the device */
+		int rc = launch_set_param(bt);
+		if (rc) return rc;
+	}
 	TrajArgs a;
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
@@ -998,7 +1005,10 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 	const DevModel &m = bt->eng->dm;
 	CU(cudaSetDevice(bt->eng->device));
 	CU(cudaStreamSynchronize(bt->stream));
-	if (theta_host) CU(cudaMemcpy(bt->db.theta + (size_t)slot * m.nparam, theta_host, m.nparam * sizeof(double), cudaMemcpyHostToDevice));
+	if (theta_host) {
+		CU(cudaMemcpy(bt->db.theta + (size_t)slot * m.nparam, theta_host, m.nparam * sizeof(double), cudaMemcpyHostToDevice));
+		bt->theta_dirty = true;
+	}
 	if (transnum_host) {
 		const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
 		if (m.stochastic) {

@@ -31,6 +31,16 @@ def test_sample_file_round_trip(tmp_path):
     b.replay()
     L = b.obs_loglik()
     assert abs(-2 * L[1] - EF) < 2e-3 * EF           # parameters and EF are stored with 6 significant digits
+    # the derived tables follow the loaded parameters (State::initialise_from_particle starts with set_param,
+    # state.cc:296): the latent-process likelihood of the loaded events equals the oracle's
+    from oracle_lib import OracleState
+    th1, tn1 = b.export_particle(1)
+    st = OracleState(ModelDesc(arrays), stochastic=1, keyed=True, imap_from_pop=True)
+    st.set_param(th1)
+    st.init_from_particle(tn1)
+    Li = b.latent_loglik()
+    assert abs(Li[1] - st.latent_loglik()) <= 1e-10 * abs(st.latent_loglik())
+    assert abs(L[1] - st.obs_loglik()) <= 1e-10 * abs(st.obs_loglik())
     out = str(tmp_path / "sample7")
     b.save_sample(1, out, NAMES, EF, start_time=0.0)
     for suffix in ("_parameter.csv", "_transition.csv"):

@@ -103,7 +103,8 @@ def _mover(rank, world, N, name, port, src_of_all, out):
     b.simulate(seed=5, stream_ids=np.arange(rank * N, (rank + 1) * N, dtype=np.uint64))
     copy_particles(b, src_of_all, rank, world, d_, dev)
     L = b.obs_loglik()
-    out[rank] = [(b.export_particle(k)[0].tolist(), b.export_particle(k)[1].ravel().tolist(), float(L[k])) for k in range(N)]
+    Li = b.latent_loglik()          # depends on the derived tables of the moved parameters
+    out[rank] = [(b.export_particle(k)[0].tolist(), b.export_particle(k)[1].ravel().tolist(), float(L[k]), float(Li[k])) for k in range(N)]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -141,3 +142,4 @@ def test_copy_particles_across_gpus():
     for x, y in zip(a, b):
         assert x[0] == y[0] and x[1] == y[1]
         assert abs(x[2] - y[2]) <= 1e-10 * abs(y[2])
+        assert abs(x[3] - y[3]) <= 1e-10 * abs(y[3])
