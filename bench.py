@@ -187,17 +187,23 @@ def reference_run(args, steps, budget_s=4.0, areas=256):
         toml = write_reference_inputs(work, A=areas)
         env = dict(os.environ, BEEP_HARNESS_BENCH=str(budget_s * max(steps, 1)))
         procs = [subprocess.Popen([REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim"],
-                                  cwd=work, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(nproc)]
-        units, secs = 0.0, 0.0
-        for p in procs:
-            out = p.communicate(timeout=600)[0]
-            ln = [l for l in out.splitlines() if l.startswith("BENCH ")]
-            if p.returncode != 0 or not ln:
-                return None
-            kv = dict(x.split("=") for x in ln[-1].split()[1:])
+                                  cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
+        units, secs, ok = 0.0, 0.0, 0
+        for i, p in enumerate(procs):
+            rc = p.wait(timeout=900)
+            res = os.path.join(work, f"o{i}.bpk.bench")
+            if rc != 0 or not os.path.exists(res):
+                print(f"bench.py: reference process {i} failed (rc={rc})", file=sys.stderr)
+                continue
+            kv = dict(x.split("=") for x in open(res).read().split()[1:])
             units += float(kv["reps"]) * float(kv["T"]) * float(kv["A"]) * float(kv["D"])
             secs = max(secs, float(kv["seconds"]))
-    except Exception:
+            ok += 1
+        if ok == 0:
+            return None
+        nproc = ok
+    except Exception as e:
+        print(f"bench.py: reference arm falls back to the CPU port: {e!r}", file=sys.stderr)
         return None
     finally:
         shutil.rmtree(work, ignore_errors=True)

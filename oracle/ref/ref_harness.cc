@@ -429,6 +429,8 @@ int main(int argc, char **argv)
 		}while(el < budget);
 		(void)sink;
 		printf("BENCH reps=%ld seconds=%.6f T=%u A=%u D=%u\n",reps,el,(unsigned)T,(unsigned)data.narea,(unsigned)data.ndemocatpos);
+		{ FILE *bf = fopen((outfile+".bench").c_str(),"w");                 // the reference prints its own progress on stdout: results go to a file
+			if(bf){ fprintf(bf,"BENCH reps=%ld seconds=%.6f T=%u A=%u D=%u\n",reps,el,(unsigned)T,(unsigned)data.narea,(unsigned)data.ndemocatpos); fclose(bf);} }
 		pk.close();
 		return 0;
 	}
