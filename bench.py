@@ -186,7 +186,7 @@ def reference_run(args, steps, budget_s=4.0, areas=256):
     try:
         toml = write_reference_inputs(work, A=areas)
         env = dict(os.environ, BEEP_HARNESS_BENCH=str(budget_s * max(steps, 1)))
-        procs = [subprocess.Popen([REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim"],
+        procs = [subprocess.Popen([REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim", f"outputdir=Output_{i}"],
                                   cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
         units, secs, ok = 0.0, 0.0, 0
         for i, p in enumerate(procs):
