@@ -892,7 +892,7 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 				const unsigned row = n0_a + lane * (L.Gs * 8);
 				if (!ntfly) {
 					const int h = L.Gs >> 1;
-#pragma unroll 2
+#pragma unroll 4
 					for (int k = 0; k < h; k++) { const double2 n2 = lds128(row + k * 16), v2 = lds128(iv_a + k * 16); sum += n2.x * v2.x; sum += n2.y * v2.y; }
 				} else {
 #pragma unroll 1
