@@ -920,6 +920,8 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 	 * A pass whose 32 cells all have an empty source compartment (most passes of an epidemic's
 	 * early and late phases) leaves after four instructions. */
 	unsigned cnt2 = 0;                                  /* nsmall | nbig << 16 (one register across the loop) */
+	int simu = 0;
+	if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
 	const int top = L.JDe - 1;
 	unsigned trbits = 0;
 	const double *crate = b.crate + (size_t)p * L.JD32;
@@ -951,12 +953,26 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		double mean = dt * popu * cr;
 		if ((w >> 24) == 1u) mean *= lds64(foi_a + ((w >> 15) & 0x1f8u));
 		if (!(popu > 0)) mean = 0;
-		const bool act = (mean != 0);
-		const bool big = mean >= BEEP_POISSON_INV_MAX;
+		bool act = (mean != 0);
 		if (KEEP && e < JD) {
 			if (keep_tm) b.tm[tbase + e] = mean;
 			if (keep_tn && !act) b.tn[tbase + e] = 0;
 		}
+		if (MODE == MODE_MBP && !DGLOB && act && !simu) {
+			/* mbp.cc:286-311: cells whose proposal needs no random number are settled here, from the
+			 * coalesced read of the initial state (which also brings its lines in for the draws):
+			 * equal means keep the count, a smaller mean thins a zero count to zero.  (Not in the
+			 * grid flavour, where the extra load latency in the scan costs more than it saves.) */
+			const int num_i = a.init_tn[tbase + e];
+			const double rate_i = a.init_tm[tbase + e];
+			if (mean == rate_i || (mean < rate_i && num_i == 0)) {
+				const int num = (mean == rate_i) ? num_i : 0;
+				if (keep_tn) b.tn[tbase + e] = num;
+				if (num != 0) { sts64(ns_a + e * 8, (double)num); trbits |= 1u << ((w >> 12) & 63); }
+				act = false;
+			}
+		}
+		const bool big = act && mean >= BEEP_POISSON_INV_MAX;
 		const unsigned bal = __ballot_sync(FULLMASK, act), balb = __ballot_sync(FULLMASK, big);
 		if (act) {
 			const int pos = big ? top - (int)((cnt2 >> 16) + __popc(balb & lt)) : (int)((cnt2 & 0xffffu) + __popc(bal & ~balb & lt));
@@ -971,8 +987,6 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		__syncwarp();
 		const unsigned long long cell0 = ((unsigned long long)t * A + c) * (unsigned long long)JD;
 		const unsigned long long sid = b.stream_id[p];
-		int simu = 0;
-		if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c];
 		/* one cell: the draw of MODE (state.cc:624-626 / mbp.cc:286-311) from the cell's own stream */
 		auto draw = [&](const int e, const double mean) -> int {
 			BeepStream rs;
