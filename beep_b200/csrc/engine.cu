@@ -589,10 +589,11 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	} else {
 		long long ntile = (long long)P * m.A;
 		int grid = (int)std::min<long long>(eng->coop_grid, (ntile + eng->nwarp - 1) / eng->nwarp);
-		/* dynamic tile scheduling: about 8 grabs per warp and sweep over the particles, at most 16 tiles
-		 * per grab and at least 4 grabs per particle-step */
+		/* dynamic tile scheduling: about 4 grabs per warp and sweep over the particles (measured: 8 tiles per
+		 * grab at 10 000 areas x 16 particles, 2 at x 4), at least 2 and at most 16 tiles per grab, and at
+		 * least 4 grabs per particle-step */
 		const long long nw = (long long)grid * eng->nwarp;
-		a.chunk = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, m.A / 4), ntile / (nw * 8)));
+		a.chunk = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, m.A / 4), std::max<long long>(mode == MODE_SIM ? 2 : 1, ntile / (nw * 4))));     /* MBP / replay tiles are heavier: finer grabs when tiles are scarce */
 		if (const char *ch = getenv("BEEP_TRAJ_CHUNK")) a.chunk = std::max(1, atoi(ch));
 		k_sched_init<<<(P + 127) / 128, 128, 0, bt->stream>>>(bt->db.sched, P, ti);
 		eng->launches++;
