@@ -48,6 +48,7 @@ struct BeepEngine {
 	int sync_mode = SYNC_NONE, nwarp = 4;
 	size_t smem_traj = 0;
 	int coop_grid = 0;
+	int none_resident = 1 << 30;   /* CTAs of the tile-resident flavour that are resident at once */
 	void *mvn_buf = nullptr; size_t mvn_cap = 0;   /* grow-only scratch of beep_mvn_kernel_sums */
 };
 
@@ -364,6 +365,7 @@ static int choose_launch(BeepEngine *eng)
 		}
 		eng->nwarp = best;
 		eng->smem_traj = none_bytes(best);
+		eng->none_resident = std::max(1, best_warps / best) * eng->nsm;
 	} else {
 		eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A);
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
@@ -459,6 +461,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
 	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)P * 16);
+	else if (eng->sync_mode == SYNC_NONE) BA(b.sched, 16);              /* the tile counter of the persistent warps */
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(k5_chunks((size_t)m.T * m.A * m.J * m.D), (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
 	{
@@ -581,8 +584,10 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	const void *fn = traj_fn(mode, eng->sync_mode, keep);
 	void *args[] = {(void *)&a};
 	if (eng->sync_mode == SYNC_NONE) {
+		/* persistent warps: as many CTAs as are resident at once (or fewer, if there are fewer tiles) */
 		long long ntile = (long long)P * m.A;
-		int grid = (int)((ntile + eng->nwarp - 1) / eng->nwarp);
+		int grid = (int)std::min<long long>((ntile + eng->nwarp - 1) / eng->nwarp, (long long)eng->none_resident);
+		CU(cudaMemsetAsync(bt->db.sched, 0, sizeof(unsigned long long), bt->stream));
 		CU(cudaLaunchKernel(fn, dim3(grid), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));
 	} else if (eng->sync_mode == SYNC_CTA) {
 		CU(cudaLaunchKernel(fn, dim3(P), dim3(eng->nwarp * 32), args, eng->smem_traj, bt->stream));

@@ -1230,8 +1230,17 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 			work_init(ts0, L, pop + CDp, lane);
 		}
 		double *dinf = pop + CDp + L.work;
-		const long long tile = (long long)blockIdx.x * nwarp + warp;
-		if (tile >= (long long)b.P * A) return;
+		/* Trajectories differ a lot in cost (an epidemic that takes off draws from the rejection samplers for
+		 * hundreds of steps, one that dies out touches almost nothing), so tiles are not bound to warps: a
+		 * persistent warp takes the next tile from a counter when it has finished one -- no CTA waits for its
+		 * slowest warp and no wave waits for its slowest CTA. */
+		const long long ntile = (long long)b.P * A;
+#pragma unroll 1
+		while (true) {
+		long long tile = 0;
+		if (lane == 0) tile = (long long)atomicAdd(b.sched, 1ull);
+		tile = __shfl_sync(FULLMASK, tile, 0);
+		if (tile >= ntile) break;
 		const int p = (int)(tile / A), c = (int)(tile % A);
 		double *gp = b.pop_cur + (size_t)tile * CDp;
 		for (int i = lane; i < CDp; i += 32) pop[i] = gp[i];
@@ -1259,6 +1268,8 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 			}
 		}
 		for (int i = lane; i < CDp; i += 32) gp[i] = pop[i];
+		__syncwarp();
+		}
 	} else if (SYNC == SYNC_CTA) {
 		const int p = blockIdx.x;
 		double *popA = sm, *dinf = popA + (size_t)A * CDp;
