@@ -1,12 +1,15 @@
 /* kernels.cuh -- hand-written sm_100a kernels of the BEEP latent-state engine.
  *
- *   k_set_param   K0   State::set_param                    reference src/state.cc:66-91
- *   k_traj<M,S>   K1-3 State::simulate / Mbp::mbp /        src/state.cc:596-638,
+ *   k_set_param, k_beta, k_areafactor_*
+ *                 K0   State::set_param                    reference src/state.cc:66-91, src/model.cc:1010-1362
+ *   k_traj<M,S,K> K1-3 State::simulate / Mbp::mbp /        src/state.cc:596-638,
  *                      State::initialise_from_particle     src/mbp.cc:252-330, src/state.cc:294-322
  *                      (+ obs accumulation, obsmodel.cc:74-109)
  *   k_obs_final   K4   ObservationModel::calculate*        src/obsmodel.cc:22-58,245-322
- *   k_latent      K5   State::likelihood                   src/state.cc:812-826
- *   k_permute..   K6   Mpi::copy_particles / end_sec_swap  src/mpi.cc:81-165,215-327
+ *   k_latent_*    K5   State::likelihood                   src/state.cc:812-826
+ *   k_gather_slab, k_copy_flagged
+ *                 K6   Mpi::copy_particles / end_sec_swap  src/mpi.cc:81-165,215-327
+ *   k_mvn_*       K7   ABCSMC::calculate_particle_weight   src/abcsmc.cc:260-271, src/mvn.cc:185-196
  *
  * Mapping of the trajectory kernel: ONE WARP PER (particle, area) TILE.  The
  * tile's population pop[C][D] lives in shared memory for the whole time loop
@@ -15,8 +18,11 @@
  * Philox stream per cell) and over dp / age for the population update and the
  * force of infection.  The per-step coupling between areas (Imap needs dinf of
  * every source area, state.cc:204-216) is a barrier whose scope is chosen by
- * the launcher: none (uncoupled areas), __syncthreads (a CTA owns a particle)
- * or a cooperative grid sync (a particle spans the grid).
+ * the launcher: none (uncoupled areas: persistent warps take trajectories from
+ * a counter), __syncthreads (a CTA owns a particle), or one step barrier PER
+ * PARTICLE kept in global memory (a particle spans the grid: warps take chunks
+ * of tiles from the particle's scheduler word and move on to another particle
+ * while a step's last tiles are in flight -- no grid-wide barrier).
  *
  * The translation unit is compiled with --fmad=false: every double operation
  * below is the same IEEE operation, in the same order, as in the CPU oracle
@@ -455,7 +461,6 @@ __device__ __forceinline__ void sts128(unsigned a, double2 v) { asm volatile("st
  * (CCTL.IVALL) and with it the read-only model tables. */
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ double ld_l2(const double *p) { double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
-__device__ __forceinline__ unsigned long long atom_add_release_u64(unsigned long long *p, unsigned long long x) { unsigned long long v; asm volatile("atom.add.release.gpu.global.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(x) : "memory"); return v; }
 __device__ __forceinline__ void red_add_release_u64(unsigned long long *p, unsigned long long x) { asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long x) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long x) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory"); }
@@ -1160,15 +1165,6 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 	}
 	__syncwarp();
 	return apply ? trmask : 0u;
-}
-
-/* tile index -> (particle, area): float reciprocal estimate (particle < 2^23) corrected by one */
-__device__ __forceinline__ void tile_split(int tile, int A, float invA, int &p, int &c)
-{
-	p = (int)((float)tile * invA);
-	c = tile - p * A;
-	if (c < 0) { p--; c += A; }
-	else if (c >= A) { p++; c -= A; }
 }
 
 /* CTA-shared tables at the front of dynamic shared memory */
