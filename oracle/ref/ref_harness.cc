@@ -299,7 +299,8 @@ static void export_desc(Pack &pk, const Details &details, const Data &data, cons
 		vector <double> val, sd, fac, shape, thr; vector <int> fs, tab, om, si, sf, aoff, ar, doff, dp, ttoff, tt, tcoff, tc;
 		aoff.push_back(0); doff.push_back(0); ttoff.push_back(0); tcoff.push_back(0);
 		for(const auto &ob : data.obs){
-			val.push_back(ob.value); sd.push_back(ob.sd); fac.push_back(ob.factor); shape.push_back(ob.shape);
+			val.push_back(ob.value); sd.push_back(ob.sd); fac.push_back(ob.factor);
+			shape.push_back(ob.obsmodel == NEGBINO_OBSMODEL ? ob.shape : UNSET);   // the reference leaves shape uninitialised for the other observation models
 			fs.push_back(u2i(ob.factor_spline)); tab.push_back(ob.datatable); om.push_back((int)ob.obsmodel);
 			si.push_back(ob.sett_i); sf.push_back(ob.sett_f);
 			for(auto c : ob.area) ar.push_back(c);
