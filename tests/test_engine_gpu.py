@@ -241,16 +241,21 @@ def test_sectioned_simulation(name):
     assert relerr(Ls[1], ref, floor=1e-9) < RTOL
 
 
+@pytest.mark.parametrize("sync", [None, 1, 2])
 @pytest.mark.parametrize("name", NAMES)
-def test_mbp(name):
+def test_mbp(name, sync):
     """K3 vs the oracle's Mbp::mbp (mbp.cc:252-330): pure MBP, mixed SIMU/MBP,
-    acceptance bookkeeping, and the fixed-event parameter proposal (mbp.cc:460-491)."""
+    acceptance bookkeeping, and the fixed-event parameter proposal (mbp.cc:460-491) --
+    in the flavour the launcher picks for the model and with the CTA- and grid-synchronised
+    flavours forced (k_traj<MBP|REPLAY, SYNC, KEEP>: every instantiation the bench reports)."""
     from beep_b200 import engine as E
     m, d = load_golden(name)
     if d["theta"].shape[0] < 2:
         pytest.skip("single parameter vector")
     ms = _variant(m, stochastic=1)
-    eng = _engine(ms)
+    eng = _engine(ms, force_sync=sync)
+    if sync == 2:
+        assert eng.sync_scope == "GRID"
     P = 4
     th0 = np.repeat(d["theta"][:1], P, axis=0)
     th1 = np.repeat(d["theta"][1:2], P, axis=0)

@@ -91,3 +91,56 @@ def test_largest_oracle_size_bit_exact():
     assert np.array_equal(obs[k], st.obs_values())
     assert np.array_equal(pops[k], st.pop[m.T - 1])
     assert relerr(L[k], st.obs_loglik()) < 1e-10
+
+
+def test_largest_oracle_size_mbp_replay_bit_exact():
+    """The grid-spanning MBP and replay kernels (k_traj<MBP,GRID>, k_traj<REPLAY,GRID> -- what
+    `bench.py --mode mbp` times) at 1 000 areas against the oracle: the FULL proposed transnum
+    (mbp.cc:252-330) bit for bit, transition means of the replay (state.cc:294-322) to 1e-10."""
+    from beep_b200 import engine as E
+    from beep_b200.synth import make_model, jitter_params
+    import os
+    m, theta = make_model(A=1000, G=20, T=120)
+    os.environ["BEEP_FORCE_SYNC"] = "2"
+    try:
+        eng = E.Engine(m)
+    finally:
+        os.environ.pop("BEEP_FORCE_SYNC", None)
+    assert eng.sync_scope == "GRID"
+    P = 3
+    th0 = jitter_params(theta, P, rel=0.05, seed=8)
+    th1 = th0 * (1 + 0.01 * (np.arange(th0.shape[1]) % 7 == 3))
+    ids = np.array([4, 1, 6], dtype=np.uint64)
+    flags = E.KEEP_TRANSNUM | E.KEEP_TRANSMEAN
+    init = eng.batch(P, flags)
+    prop = eng.batch(P, flags)
+    init.set_params(th0)
+    init.simulate(seed=33, stream_ids=ids)
+    k = 1
+    oi = OracleState(m, stochastic=1, keyed=True, imap_from_pop=True)
+    oi.set_param(th0[k])
+    oi.simulate(seed=33, stream_id=int(ids[k]))
+    assert np.array_equal(init.trajectory(k).astype(np.int64), oi.transnum.astype(np.int64))
+    mask = np.zeros((m.T, m.A), dtype=np.uint8)
+    mask[m.T // 2:, 1::3] = 1
+    for msk, seed in ((None, 34), (mask, 35)):
+        prop.set_params(th1)
+        prop.mbp(init, msk, seed=seed, stream_ids=ids)
+        op = OracleState(m, stochastic=1, keyed=True, imap_from_pop=True)
+        op.set_param(th1[k])
+        op.mbp(oi, msk, seed=seed, stream_id=int(ids[k]))
+        assert np.array_equal(prop.trajectory(k).astype(np.int64), op.transnum.astype(np.int64))
+        scale = float(np.max(np.abs(op.transmean)))
+        assert relerr(prop.trajectory(k, E.TRAJ_TRANSMEAN), op.transmean, floor=1e-9 * scale) < 1e-10
+        assert relerr(prop.obs_loglik()[k], op.obs_loglik()) < 1e-10
+    # replay of the initial events under the proposal's parameters
+    for s in range(P):
+        prop.import_particle(s, th1[s], init.trajectory(s))
+    prop.replay()
+    o3 = OracleState(m, stochastic=1, keyed=True, imap_from_pop=True)
+    o3.set_param(th1[k])
+    o3.init_from_particle(init.trajectory(k))
+    scale = float(np.max(np.abs(o3.transmean)))
+    assert relerr(prop.trajectory(k, E.TRAJ_TRANSMEAN), o3.transmean, floor=1e-9 * scale) < 1e-10
+    assert relerr(prop.latent_loglik()[k], o3.latent_loglik()) < 1e-10
+    assert np.array_equal(prop.pop(k), o3.pop[m.T - 1])
