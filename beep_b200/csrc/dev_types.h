@@ -78,8 +78,35 @@ static inline TrajSm traj_sm_layout(int G, int J, int D, int nbr_doubles = 64)
 	return L;
 }
 
+/* Shared-memory layout of the chunk kernel (traj_chunk.cuh): byte offsets inside a warp's area.
+ *   pop[NT][CDp4] int32 | lmean[cap] double (the infectivity vectors Iv[NT][Gs] during the force-of-infection
+ *   phase) | foi[NT][G] double | tinfo[NT] 32-byte records | lcell[cap] u16 | acc[NT][CHUNK_NEJ] int32 | mbarrier */
+#define CHUNK_NEJ 8                       /* observation entries per (sett, area) cell the chunk kernel accumulates */
+struct ChunkSm { int pop, lmean, foi, tinfo, lcell, acc, bar, per, cap; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline ChunkSm chunk_sm_layout(int NT, int G, int Gs, int JD32, int CDp4)
+{
+	ChunkSm s;
+	int o = 0;
+	s.cap = JD32 > 256 ? JD32 : 256;
+	s.pop = o; o += NT * CDp4 * 4;
+	s.lmean = o; o += (s.cap > NT * Gs ? s.cap : NT * Gs) * 8;
+	s.foi = o; o += ((NT * G + 1) & ~1) * 8;
+	s.tinfo = o; o += NT * 32;
+	s.lcell = o; o += ((s.cap * 2 + 15) & ~15);
+	s.acc = o; o += NT * CHUNK_NEJ * 4;
+	s.bar = o; o += 16;
+	s.per = (o + 15) & ~15;
+	return s;
+}
+
 struct DevModel {
 	int T, period, spu, A, C, J, D, G, S, Dq, nparam, nspline, nobs, ntable;
+	int CDp4;           /* C*D rounded up to a multiple of 4: tile stride of the int32 populations (16-byte bulk copies) */
+	unsigned obs_tr_any;            /* transitions that some observation counts */
+	const unsigned char *cell_npop; /* [T*A] entries of the (sett, area) cell's list that observe a population; they come first */
 	int stochastic, siminf, itr, geo_spline, nR, nefoi, ninf, nmm, ncovar, nlevel, ndir;
 	int nslot, nsection, has_region, has_area_eff, age_fast, M_nnz;
 	int CDp;            /* C*D rounded up to even: tile stride of pop_cur (16-byte async copies) */
@@ -126,6 +153,7 @@ struct DevBatch {
 	unsigned long long *sched;     /* [P][16] per particle, one 128-byte line: word 0 = (step << 32 | next tile) of the
 	                                  particle-step scheduler, word 1 = tiles of that step completed */
 	double *pop_cur, *dinf;
+	int *popi;                     /* [P][A][CDp4] int32 populations: batches the chunk kernel serves (then pop_cur is null) */
 	double *scratchA;              /* [P][A] K0 scratch (per-area averages) */
 	int *tn; double *tm; double *poptraj;
 	double *obs_partial, *obs_val, *L, *EFtab, *Li;
@@ -148,6 +176,8 @@ struct TrajArgs {
 	int fast;           /* the model has the common structure tile_step_fast handles */
 	float invA;         /* 1/A: tile index -> (particle, area) without an integer division */
 	TrajSm L;           /* shared-memory layout (traj_sm_layout), computed once by the launcher */
+	ChunkSm Ls;         /* chunk kernel: per-warp layout */
+	unsigned invG;      /* chunk kernel: ceil(2^16 / G), pair index -> (tile, age) without a division */
 	unsigned char tfrom[32], tto[32], tkind[32];   /* per transition: source, target, kind (0 ordinary, 1 infection, 2 never) */
 };
 

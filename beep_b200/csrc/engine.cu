@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "traj_chunk.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* errors                                                                    */
@@ -50,6 +51,11 @@ struct BeepEngine {
 	int coop_grid = 0;
 	int none_resident = 1 << 30;   /* CTAs of the tile-resident flavour that are resident at once */
 	void *mvn_buf = nullptr; size_t mvn_cap = 0;   /* grow-only scratch of beep_mvn_kernel_sums */
+	/* chunk kernel (traj_chunk.cuh): the model qualifies, tiles per chunk, launch shape */
+	bool chunk_model = false, chunk_ok = false;
+	int chunk_nt = 0, chunk_grid = 0;
+	size_t chunk_smem = 0;
+	ChunkSm chunk_ls;
 };
 
 struct BeepBatch {
@@ -239,6 +245,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
 	UP(pop_init, d->pop_init, (size_t)A * C * D);
 	m.CDp = (C * D + 1) & ~1;
+	m.CDp4 = (C * D + 3) & ~3;
 	{
 		/* packed per-cell table: population offset of the source compartment, transition, dp, kind
 		 * (0 = ordinary transition, 1 = the infection transition, 2 = always zero) */
@@ -287,12 +294,34 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		for (size_t i = 0; i < (size_t)T * A; i++) cell_cnt[i + 1] += cell_cnt[i];
 		std::vector<ObsEnt> ent(cell_cnt[(size_t)T * A]);
 		std::vector<int> fill(cell_cnt.begin(), cell_cnt.end() - 1);
-		for (int ob = 0; ob < O; ob++)
-			for (int k = d->obs_area_off[ob]; k < d->obs_area_off[ob + 1]; k++)
-				for (int t = d->obs_sett_i[ob]; t < d->obs_sett_f[ob]; t++) {
-					size_t cell = (size_t)t * A + d->obs_area[k];
-					ent[fill[cell]++] = ObsEnt{ob, slot_off[ob] + (k - d->obs_area_off[ob])};
-				}
+		/* a cell's entries that observe a population come first (the chunk kernel reads them before the step's
+		 * events are applied); cell_npop counts them */
+		std::vector<unsigned char> npop((size_t)T * A, 0);
+		int max_ent = 0;
+		bool npop_fits = true;
+		for (int pass = 0; pass < 2; pass++)
+			for (int ob = 0; ob < O; ob++) {
+				if ((cmask[ob] != 0) != (pass == 0)) continue;
+				for (int k = d->obs_area_off[ob]; k < d->obs_area_off[ob + 1]; k++)
+					for (int t = d->obs_sett_i[ob]; t < d->obs_sett_f[ob]; t++) {
+						size_t cell = (size_t)t * A + d->obs_area[k];
+						ent[fill[cell]++] = ObsEnt{ob, slot_off[ob] + (k - d->obs_area_off[ob])};
+						if (pass == 0) { if (npop[cell] == 255) npop_fits = false; else npop[cell]++; }
+					}
+			}
+		for (size_t i = 0; i < (size_t)T * A; i++) max_ent = std::max(max_ent, cell_cnt[i + 1] - cell_cnt[i]);
+		m.obs_tr_any = 0;
+		for (int ob = 0; ob < O; ob++) m.obs_tr_any |= tmask[ob];
+		UPV(cell_npop, npop);
+		/* the chunk kernel serves the common model structure (see launch_traj) with integer populations
+		 * and at most CHUNK_NEJ observation entries per (sett, area) cell */
+		eng->chunk_model = npop_fits && max_ent <= CHUNK_NEJ && m.S == 1 && m.Dq == m.G && m.G > 1 && m.stochastic && J * D < 4096 && C * D < 4096;
+		for (int i = 0; i < Dq && eng->chunk_model; i++) if (d->dp_age[i] != i % G) eng->chunk_model = false;
+		for (size_t i = 0; i < (size_t)A * C * D && eng->chunk_model; i++) {
+			const double v = d->pop_init[i];
+			if (!(std::fabs(v) < 2e9) || v != std::floor(v)) eng->chunk_model = false;
+		}
+		for (unsigned q = 0; q < 8u * 32u; q++) if (((q * ((65536u + G - 1) / G)) >> 16) != q / G) eng->chunk_model = false;
 		int per = d->pmcmc_obs_period > 0 ? d->pmcmc_obs_period : T;
 		m.nsection = (T + per - 1) / per;
 		for (int s = 0; s < m.nsection; s++) {
@@ -333,6 +362,23 @@ static const void *traj_fn(int mode, int sync, bool keep)
 	if (sync == SYNC_NONE) return keep ? traj_fn2<SYNC_NONE, true>(mode) : traj_fn2<SYNC_NONE, false>(mode);
 	if (sync == SYNC_CTA) return keep ? traj_fn2<SYNC_CTA, true>(mode) : traj_fn2<SYNC_CTA, false>(mode);
 	return keep ? traj_fn2<SYNC_GRID, true>(mode) : traj_fn2<SYNC_GRID, false>(mode);
+}
+
+/* chunk kernel instantiations (traj_chunk.cuh) */
+template <int NT, bool KEEP>
+static const void *chunk_fn2(int mode)
+{
+	switch (mode) {
+	case MODE_SIM: return (const void *)k_traj_chunk<MODE_SIM, KEEP, NT>;
+	case MODE_MBP: return (const void *)k_traj_chunk<MODE_MBP, true, NT>;
+	default: return (const void *)k_traj_chunk<MODE_REPLAY, true, NT>;
+	}
+}
+static const void *chunk_fn(int mode, int nt, bool keep)
+{
+	if (mode != MODE_SIM) keep = true;
+	if (nt == 4) return keep ? chunk_fn2<4, true>(mode) : chunk_fn2<4, false>(mode);
+	return keep ? chunk_fn2<8, true>(mode) : chunk_fn2<8, false>(mode);
 }
 
 static size_t even(size_t x) { return (x + 1) & ~(size_t)1; }
@@ -397,6 +443,27 @@ static int choose_launch(BeepEngine *eng)
 		}
 		if (nbmin < 1) return fail(BEEP_ERR_UNSUPPORTED, "trajectory kernel does not fit an SM");
 		eng->coop_grid = nbmin * eng->nsm;
+		/* the chunk kernel for models of the common structure: NT tiles per warp and grab */
+		eng->chunk_ok = false;
+		const char *off = getenv("BEEP_NO_CHUNK");
+		if (eng->chunk_model && !(off && atoi(off))) {
+			int nt = 4;                              /* measured: 4 tiles x 24 warps/SM beats 8 x 16 (profiles/README.md) */
+			if (const char *e = getenv("BEEP_CHUNK_NT")) nt = (atoi(e) == 8) ? 8 : 4;
+			if (m.A < 8) nt = 4;
+			eng->chunk_nt = nt;
+			eng->chunk_ls = chunk_sm_layout(nt, m.G, L.Gs, L.JD32, m.CDp4);
+			eng->chunk_smem = common * sizeof(double) + (size_t)CHUNK_NWARP * eng->chunk_ls.per;
+			if (eng->chunk_smem <= (size_t)eng->smem_optin) {
+				int nbc = 1 << 30;
+				for (int mode = 0; mode < 3; mode++) for (int keep = 0; keep < 2; keep++) {
+					const void *fn = chunk_fn(mode, nt, keep != 0);
+					CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eng->chunk_smem));
+					CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, CHUNK_NWARP * 32, eng->chunk_smem));
+					nbc = std::min(nbc, nb);
+				}
+				if (nbc >= 1) { eng->chunk_ok = true; eng->chunk_grid = nbc * eng->nsm; }
+			}
+		}
 	}
 	return BEEP_OK;
 }
@@ -450,7 +517,10 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.theta, (size_t)P * m.nparam); BA(b.pd, (size_t)P * m.nparam);
 	BA(b.transrate, (size_t)P * m.J * m.D); BA(b.disc_spline, (size_t)P * m.nspline * m.T); BA(b.sus, (size_t)P * m.D);
 	BA(b.areafactor, (size_t)P * m.period * m.A); BA(b.betaR, (size_t)P * m.S * m.nR * m.T); BA(b.infco, (size_t)P * m.C);
-	BA(b.pop_cur, (size_t)P * m.A * m.CDp); BA(b.scratchA, (size_t)P * m.A);
+	/* stochastic batches of chunk-kernel models keep integer populations (int32, half the per-step traffic) */
+	if (eng->chunk_ok && !(flags & BEEP_KEEP_POP)) BA(b.popi, (size_t)P * m.A * m.CDp4);
+	else BA(b.pop_cur, (size_t)P * m.A * m.CDp);
+	BA(b.scratchA, (size_t)P * m.A);
 	if (eng->sync_mode == SYNC_GRID) BA(b.dinf, 2 * (size_t)P * m.S * m.A * m.G);
 	if ((flags & BEEP_KEEP_TRANSNUM) && m.stochastic) BA(b.tn, (size_t)P * TAJD);
 	if ((flags & BEEP_KEEP_TRANSMEAN) || ((flags & BEEP_KEEP_TRANSNUM) && !m.stochastic)) { BA(b.tm, (size_t)P * TAJD); b.flags |= BEEP_KEEP_TRANSMEAN; }
@@ -483,6 +553,7 @@ extern "C" int64_t beep_batch_bytes(const BeepBatch *bt) { return bt ? bt->bytes
 extern "C" void *beep_batch_stream(BeepBatch *bt) { return bt ? (void *)bt->stream : nullptr; }
 extern "C" int64_t beep_launch_count(const BeepEngine *eng) { return eng ? eng->launches : 0; }
 extern "C" int beep_engine_sync_scope(const BeepEngine *eng) { return eng ? eng->sync_mode : -1; }
+extern "C" int beep_engine_chunk_tiles(const BeepEngine *eng) { return (eng && eng->chunk_ok) ? eng->chunk_nt : 0; }
 extern "C" int beep_sync(BeepBatch *bt)
 {
 	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
@@ -564,17 +635,19 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	TrajArgs a;
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
-	a.nwarp = eng->nwarp; a.chunk = 1;
+	a.nwarp = eng->nwarp; a.chunk = 1; a.invG = 0; memset(&a.Ls, 0, sizeof a.Ls);
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));
 	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
 	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
 	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;
+	const bool chunk = bt->db.popi != nullptr;
 	if (ti == 0) {
 		size_t n = (size_t)P * m.A * m.CDp;
 		int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)eng->nsm * 8);
-		k_pop_reset<<<nb, 256, 0, bt->stream>>>(m, bt->db);
+		if (chunk) k_pop_reset_i32<<<nb, 256, 0, bt->stream>>>(m, bt->db);
+		else k_pop_reset<<<nb, 256, 0, bt->stream>>>(m, bt->db);
 		size_t ns = (size_t)P * std::max(m.nslot, 1);
 		k_zero<<<(int)std::min<size_t>((ns + 255) / 256, (size_t)eng->nsm * 8), 256, 0, bt->stream>>>(bt->db.obs_partial, ns);
 		eng->launches += 2;
@@ -583,7 +656,14 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	const bool keep = (bt->db.flags & (BEEP_KEEP_TRANSNUM | BEEP_KEEP_TRANSMEAN | BEEP_KEEP_POP)) != 0;
 	const void *fn = traj_fn(mode, eng->sync_mode, keep);
 	void *args[] = {(void *)&a};
-	if (eng->sync_mode == SYNC_NONE) {
+	if (chunk) {
+		a.Ls = eng->chunk_ls; a.invG = (65536u + m.G - 1) / m.G; a.chunk = eng->chunk_nt;
+		long long nchunk = (long long)P * ((m.A + eng->chunk_nt - 1) / eng->chunk_nt);
+		int grid = (int)std::min<long long>(eng->chunk_grid, (nchunk + CHUNK_NWARP - 1) / CHUNK_NWARP);
+		k_sched_init<<<(P + 127) / 128, 128, 0, bt->stream>>>(bt->db.sched, P, ti);
+		eng->launches++;
+		CU(cudaLaunchCooperativeKernel(chunk_fn(mode, eng->chunk_nt, keep), dim3(grid), dim3(CHUNK_NWARP * 32), args, eng->chunk_smem, bt->stream));
+	} else if (eng->sync_mode == SYNC_NONE) {
 		/* persistent warps: as many CTAs as are resident at once (or fewer, if there are fewer tiles) */
 		long long ntile = (long long)P * m.A;
 		int grid = (int)std::min<long long>((ntile + eng->nwarp - 1) / eng->nwarp, (long long)eng->none_resident);
@@ -781,6 +861,7 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	int rc;
 	const DevBatch &b = bt->db;
 	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.CDp, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.popi, (size_t)m.A * m.CDp4, bt->d_map))) return rc;
 	if (what == BEEP_PERMUTE_SECTION_STATE) return BEEP_OK;      /* mpi.cc:286-288: pop (Imap/Idiag are re-derived from it) */
 	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
 	if ((rc = gather_inplace(bt, b.theta, m.nparam, bt->d_map))) return rc;
@@ -838,7 +919,9 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if ((rc = copy_flagged(init, a.etab, b.etab, (size_t)m.nefoi * m.T))) return rc;
 	if ((rc = copy_flagged(init, a.crate, b.crate, ((size_t)m.J * m.D + 31) & ~(size_t)31))) return rc;
 	if ((rc = copy_flagged(init, a.inflist, b.inflist, (size_t)m.C + 1))) return rc;
+	if ((a.popi != nullptr) != (b.popi != nullptr)) return fail(BEEP_ERR_INVALID, "init and prop batches were created with different flags (population storage differs)");
 	if ((rc = copy_flagged(init, a.pop_cur, b.pop_cur, (size_t)m.A * m.CDp))) return rc;
+	if ((rc = copy_flagged(init, a.popi, b.popi, (size_t)m.A * m.CDp4))) return rc;
 	if ((rc = copy_flagged(init, a.tn, b.tn, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.tm, b.tm, TAJD))) return rc;
 	if ((rc = copy_flagged(init, a.poptraj, b.poptraj, (size_t)m.T * m.A * m.C * m.D))) return rc;
@@ -894,6 +977,18 @@ extern "C" int beep_get_trajectory(BeepBatch *bt, int slot, int which, double *o
 	return fail(BEEP_ERR_INVALID, "unknown trajectory selector %d", which);
 }
 
+/* integer populations (batches of the chunk kernel) cross the boundary as doubles like the others */
+static int get_pop_i32(BeepBatch *bt, const int *src, size_t ntile, double *out)
+{
+	const DevModel &m = bt->eng->dm;
+	const size_t CD = (size_t)m.C * m.D;
+	std::vector<int> tmp(ntile * CD);
+	CU(cudaMemcpy2DAsync(tmp.data(), CD * sizeof(int), src, (size_t)m.CDp4 * sizeof(int), CD * sizeof(int), ntile, cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	for (size_t i = 0; i < tmp.size(); i++) out[i] = (double)tmp[i];
+	return BEEP_OK;
+}
+
 extern "C" int beep_get_pop(BeepBatch *bt, int slot, double *out, int64_t n)
 {
 	int rc = slot_ok(bt, slot);
@@ -903,6 +998,7 @@ extern "C" int beep_get_pop(BeepBatch *bt, int slot, double *out, int64_t n)
 	if (!out || (size_t)n != ACD) return fail(BEEP_ERR_INVALID, "pop has %zu elements", ACD);
 	CU(cudaSetDevice(bt->eng->device));
 	const size_t CD = (size_t)m.C * m.D;
+	if (bt->db.popi) return get_pop_i32(bt, bt->db.popi + (size_t)slot * m.A * m.CDp4, (size_t)m.A, out);
 	CU(cudaMemcpy2DAsync(out, CD * sizeof(double), bt->db.pop_cur + (size_t)slot * m.A * m.CDp, (size_t)m.CDp * sizeof(double),
 	                     CD * sizeof(double), m.A, cudaMemcpyDeviceToHost, bt->stream));
 	CU(cudaStreamSynchronize(bt->stream));
@@ -916,6 +1012,7 @@ extern "C" int beep_get_pop_all(BeepBatch *bt, double *out)
 	const DevModel &m = bt->eng->dm;
 	const size_t CD = (size_t)m.C * m.D;
 	CU(cudaSetDevice(bt->eng->device));
+	if (bt->db.popi) return get_pop_i32(bt, bt->db.popi, (size_t)bt->db.P * m.A, out);
 	CU(cudaMemcpy2DAsync(out, CD * sizeof(double), bt->db.pop_cur, (size_t)m.CDp * sizeof(double), CD * sizeof(double), (size_t)bt->db.P * m.A, cudaMemcpyDeviceToHost, bt->stream));
 	CU(cudaStreamSynchronize(bt->stream));
 	return BEEP_OK;
@@ -928,6 +1025,13 @@ extern "C" int beep_set_pop_all(BeepBatch *bt, const double *in, int cur_t)
 	const size_t CD = (size_t)m.C * m.D;
 	CU(cudaSetDevice(bt->eng->device));
 	CU(cudaStreamSynchronize(bt->stream));
+	if (bt->db.popi) {
+		std::vector<int> tmp((size_t)bt->db.P * m.A * CD);
+		for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (int)in[i];
+		CU(cudaMemcpy2D(bt->db.popi, (size_t)m.CDp4 * sizeof(int), tmp.data(), CD * sizeof(int), CD * sizeof(int), (size_t)bt->db.P * m.A, cudaMemcpyHostToDevice));
+		bt->cur_t = cur_t;
+		return BEEP_OK;
+	}
 	CU(cudaMemcpy2D(bt->db.pop_cur, (size_t)m.CDp * sizeof(double), in, CD * sizeof(double), CD * sizeof(double), (size_t)bt->db.P * m.A, cudaMemcpyHostToDevice));
 	bt->cur_t = cur_t;
 	return BEEP_OK;

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "beep_batch_stream": (_vp, [_vp]),
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
+    "beep_engine_chunk_tiles": (ctypes.c_int, [_vp]),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
     "beep_save_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_double, ctypes.c_double]),
     "beep_load_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, _c_dp]),
@@ -135,6 +136,10 @@ class Engine:
     @property
     def launch_count(self):
         return self.L.beep_launch_count(self.h)
+
+    @property
+    def chunk_tiles(self):
+        return self.L.beep_engine_chunk_tiles(self.h)
 
     @property
     def sync_scope(self):

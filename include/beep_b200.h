@@ -191,6 +191,10 @@ void *beep_batch_stream(BeepBatch *batch);
 /* scope of the per-step barrier the trajectory kernel uses for this model:
  * 0 = none (areas uncoupled), 1 = CTA (a CTA owns a particle), 2 = cooperative grid */
 int beep_engine_sync_scope(const BeepEngine *eng);
+/* tiles (consecutive areas of one particle-step) a warp of the grid-spanning trajectory kernel works at once:
+ * 4 or 8 when the chunk kernel (integer populations, pooled draws) serves the model, 0 when the
+ * one-tile-per-warp kernel does */
+int beep_engine_chunk_tiles(const BeepEngine *eng);
 /* number of engine kernel launches since creation (bench accounting)        */
 int64_t beep_launch_count(const BeepEngine *eng);
 /* last kernel-only duration of beep_simulate in ms (CUDA events on the
