@@ -66,6 +66,7 @@ struct BeepBatch {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool have_params = false, have_sim_time = false;
+	std::vector<unsigned char> slot_theta;   /* slots whose parameters were given (set_params: all; import_particle: one) */
 	bool theta_dirty = false;       /* a slot's parameters were replaced (beep_import_particle): the derived tables are re-derived before the next launch that reads them */
 	int cur_t = 0;
 	double *d_scratch = nullptr;    /* [P * max(k5_chunks, OBS_CHUNKS*(1+ntable))] */
@@ -150,6 +151,35 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	NEED(d->n_table_trans_off == m.ntable + 1 && d->n_table_comp_off == m.ntable + 1 && d->n_table_threshold == m.ntable, "datatable arrays inconsistent");
 	NEED(m.ncovar == 0 || d->n_covar_value == (int64_t)m.ncovar * A * m.period, "covar_value must be [ncovar][A][period]");
 	NEED(m.nlevel == 0 || d->n_level_map == (int64_t)m.period * A, "level_map must be [period][A]");
+	NEED(d->n_obs_sd == m.nobs && d->n_obs_factor == m.nobs && d->n_obs_shape == m.nobs && d->n_obs_model == m.nobs && d->n_obs_table == m.nobs &&
+	     d->n_obs_sett_i == m.nobs && d->n_obs_sett_f == m.nobs && d->n_obs_factor_spline == m.nobs, "per-observation arrays must have nobs entries");
+	NEED(m.nobs == 0 || (d->n_obs_area >= d->obs_area_off[m.nobs] && d->n_obs_dp >= d->obs_dp_off[m.nobs]), "obs_area / obs_dp shorter than their offsets say");
+	NEED(d->n_table_trans >= d->table_trans_off[m.ntable] && d->n_table_comp >= d->table_comp_off[m.ntable], "table_trans / table_comp shorter than their offsets say");
+	NEED(m.nR == 0 || d->n_R_area >= d->R_area_off[m.nR], "R_area shorter than R_area_off says");
+	NEED(d->n_spline_param >= d->spline_off[m.nspline] && d->n_spline_t >= d->spline_off[m.nspline] && d->n_spline_multfac >= d->spline_off[m.nspline], "spline knot arrays shorter than spline_off says");
+	NEED(d->n_sus_param >= d->sus_off[D], "sus_param shorter than sus_off says");
+	NEED(m.ndir == 0 || (d->n_dir_th >= d->dir_off[m.ndir] && d->n_dir_frac >= d->dir_off[m.ndir]), "dir_th / dir_frac shorter than dir_off says");
+	NEED(d->n_efoi_spline_ref == m.nefoi && d->n_matmod_spline == m.nmm, "efoi / matmod spline arrays inconsistent");
+	NEED(!m.has_region || d->n_region_effect_param == A, "region_effect_param must be [A]");
+	NEED(!m.has_area_eff || d->n_area_effect_param == A, "area_effect_param must be [A]");
+	{
+		/* every parameter / spline / compartment index the kernels dereference */
+		auto par_ok = [&](const int32_t *v, int64_t n, bool allow_neg) { for (int64_t i = 0; i < n; i++) if (v[i] >= m.nparam || (v[i] < 0 && !allow_neg)) return false; return true; };
+		NEED(par_ok(d->trans_prob_param, (int64_t)J * D, true), "trans_prob_param out of range");
+		for (int tr = 0; tr < J; tr++) if (!d->trans_inf[tr]) NEED(par_ok(d->trans_mean_param + (size_t)tr * D, D, false), "trans_mean_param of transition %d out of range", tr);
+		NEED(par_ok(d->comp_inf_param, C, false), "comp_inf_param out of range");
+		NEED(par_ok(d->spline_factor_param, m.nspline, false) && par_ok(d->spline_param, d->spline_off[m.nspline], false), "spline parameters out of range");
+		NEED(par_ok(d->sus_param, d->sus_off[D], false), "sus_param out of range");
+		NEED(m.ndir == 0 || par_ok(d->dir_th, d->dir_off[m.ndir], false), "dir_th out of range");
+		NEED(par_ok(d->covar_param, m.ncovar, false) && par_ok(d->level_param, m.nlevel, false), "covariate / level parameters out of range");
+		NEED(par_ok(d->strain_Rfactor_param, S, false), "strain_Rfactor_param out of range");
+		NEED(!m.has_region || par_ok(d->region_effect_param, A, false), "region_effect_param out of range");
+		NEED(!m.has_area_eff || par_ok(d->area_effect_param, A, false), "area_effect_param out of range");
+		for (int i = 0; i < m.nR; i++) NEED(d->R_spline_ref[i] >= 0 && d->R_spline_ref[i] < m.nspline, "R_spline_ref out of range");
+		for (int i = 0; i < m.nefoi; i++) NEED(d->efoi_spline_ref[i] >= 0 && d->efoi_spline_ref[i] < m.nspline, "efoi_spline_ref out of range");
+		for (int i = 0; i < m.nmm; i++) NEED(d->matmod_spline[i] >= 0 && d->matmod_spline[i] < m.nspline, "matmod_spline out of range");
+		for (int64_t i = 0; i < (m.nlevel > 0 ? d->n_level_map : 0); i++) NEED(d->level_map[i] >= 0 && d->level_map[i] < m.nlevel, "level_map out of range");
+	}
 	for (int tr = 0; tr < J; tr++) NEED(d->trans_from[tr] >= 0 && d->trans_from[tr] < C && d->trans_to[tr] >= 0 && d->trans_to[tr] < C, "transition %d endpoints out of range", tr);
 	for (int i = 0; i < Dq; i++) NEED(d->dp_age[i] >= 0 && d->dp_age[i] < G, "dp_age out of range");
 
@@ -595,16 +625,17 @@ static int launch_set_param(BeepBatch *bt)
 	k_areafactor_scale<<<dim3(P, (unsigned)std::min<size_t>((naf + 255) / 256, 1024)), 256, 0, bt->stream>>>(m, bt->db);
 	eng->launches += 4;
 	CU(cudaGetLastError());
-	bt->have_params = true;
 	bt->theta_dirty = false;
 	return BEEP_OK;
 }
+static void all_slots_have_theta(BeepBatch *bt) { bt->slot_theta.assign(bt->db.P, 1); bt->have_params = true; }
 
 extern "C" int beep_set_params_dev(BeepBatch *bt, const double *theta_dev)
 {
 	if (!bt || !theta_dev) return fail(BEEP_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(bt->eng->device));
 	CU(cudaMemcpyAsync(bt->db.theta, theta_dev, (size_t)bt->db.P * bt->eng->dm.nparam * sizeof(double), cudaMemcpyDeviceToDevice, bt->stream));
+	all_slots_have_theta(bt);
 	return launch_set_param(bt);
 }
 
@@ -617,6 +648,7 @@ extern "C" int beep_set_params(BeepBatch *bt, const double *theta_host)
 	CU(cudaStreamSynchronize(bt->stream));
 	memcpy(bt->h_pinned, theta_host, n * sizeof(double));
 	CU(cudaMemcpyAsync(bt->db.theta, bt->h_pinned, n * sizeof(double), cudaMemcpyHostToDevice, bt->stream));
+	all_slots_have_theta(bt);
 	return launch_set_param(bt);
 }
 
@@ -833,11 +865,20 @@ static int gather_inplace(BeepBatch *bt, Tp *arr, size_t n, const unsigned *d_ma
 	const int P = bt->db.P;
 	size_t need = (size_t)P * n * sizeof(Tp);
 	if (bt->d_tmp_n < need) {
-		/* scratch grows to the largest slab ever permuted; freed with the batch */
+		/* one scratch per batch, as large as the largest slab ever permuted: the smaller one is released first
+		 * (stream-ordered after the copies that used it) and the batch's byte count follows */
+		CU(cudaStreamSynchronize(bt->stream));
+		if (bt->d_tmp) {
+			cudaFree(bt->d_tmp);
+			bt->dev_allocs.erase(std::remove(bt->dev_allocs.begin(), bt->dev_allocs.end(), (void *)bt->d_tmp), bt->dev_allocs.end());
+			bt->bytes -= (long long)bt->d_tmp_n;
+			bt->d_tmp = nullptr; bt->d_tmp_n = 0;
+		}
 		double *t = nullptr;
 		cudaError_t e = cudaMalloc((void **)&t, need);
 		if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for permute scratch: %s", need, cudaGetErrorString(e));
 		bt->dev_allocs.push_back(t);
+		bt->bytes += (long long)need;
 		bt->d_tmp = t; bt->d_tmp_n = need;
 	}
 	Tp *tmp = (Tp *)bt->d_tmp;
@@ -856,9 +897,10 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	const int P = bt->db.P;
 	for (int p = 0; p < P; p++) if (src_of_host[p] != 0xFFFFFFFFu && src_of_host[p] >= (unsigned)P) return fail(BEEP_ERR_INVALID, "src_of[%d] = %u out of range", p, src_of_host[p]);
 	CU(cudaSetDevice(bt->eng->device));
+	int rc;
+	if (what != BEEP_PERMUTE_SECTION_STATE && bt->theta_dirty && (rc = launch_set_param(bt))) return rc;   /* derived tables move with the particles */
 	CU(cudaStreamSynchronize(bt->stream));
 	CU(cudaMemcpyAsync(bt->d_map, src_of_host, P * sizeof(unsigned), cudaMemcpyHostToDevice, bt->stream));
-	int rc;
 	const DevBatch &b = bt->db;
 	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.CDp, bt->d_map))) return rc;
 	if ((rc = gather_inplace(bt, b.popi, (size_t)m.A * m.CDp4, bt->d_map))) return rc;
@@ -901,6 +943,8 @@ extern "C" int beep_accept(BeepBatch *init, BeepBatch *prop, const uint8_t *acce
 	if (init->eng != prop->eng || init->db.P != prop->db.P) return fail(BEEP_ERR_INVALID, "init and prop batches differ in engine or size");
 	const DevModel &m = init->eng->dm;
 	CU(cudaSetDevice(init->eng->device));
+	if (prop->theta_dirty) { int rc0 = launch_set_param(prop); if (rc0) return rc0; }
+	if (init->theta_dirty && init->have_params) { int rc0 = launch_set_param(init); if (rc0) return rc0; }
 	CU(cudaStreamSynchronize(prop->stream));
 	CU(cudaStreamSynchronize(init->stream));
 	CU(cudaMemcpyAsync(init->d_flag, accept_host, init->db.P, cudaMemcpyHostToDevice, init->stream));
@@ -1046,6 +1090,7 @@ extern "C" int beep_get_derived(BeepBatch *bt, int slot, int which, double *out,
 	const DevModel &m = bt->eng->dm;
 	const DevBatch &b = bt->db;
 	CU(cudaSetDevice(bt->eng->device));
+	if (bt->theta_dirty) { rc = launch_set_param(bt); if (rc) return rc; }
 	const double *src = nullptr; size_t cnt = 0;
 	switch (which) {
 	case BEEP_DERIVED_TRANSRATE: cnt = (size_t)m.J * m.D; src = b.transrate + slot * cnt; break;
@@ -1118,6 +1163,10 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 	if (theta_host) {
 		CU(cudaMemcpy(bt->db.theta + (size_t)slot * m.nparam, theta_host, m.nparam * sizeof(double), cudaMemcpyHostToDevice));
 		bt->theta_dirty = true;
+		/* the batch has parameters once every slot was given some (State::load per particle, state.cc:743-790) */
+		if (bt->slot_theta.empty()) bt->slot_theta.assign(bt->db.P, 0);
+		bt->slot_theta[slot] = 1;
+		if (!bt->have_params) bt->have_params = std::find(bt->slot_theta.begin(), bt->slot_theta.end(), (unsigned char)0) == bt->slot_theta.end();
 	}
 	if (transnum_host) {
 		const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
@@ -1131,8 +1180,9 @@ extern "C" int beep_import_particle(BeepBatch *bt, int slot, const double *theta
 			CU(cudaMemcpy(bt->db.tm + (size_t)slot * TAJD, transnum_host, TAJD * sizeof(double), cudaMemcpyHostToDevice));
 		}
 	}
-	/* derived tables of every slot are refreshed from the stored parameters */
-	return launch_set_param(bt);
+	/* the derived tables are re-derived from the stored parameters before the next launch (or read-back)
+	 * that needs them: importing n particles costs one K0, not n */
+	return BEEP_OK;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1408,8 +1458,7 @@ extern "C" int beep_bootstrap(const double *L, int ntot, double invT, uint64_t s
 		if (!flag[lo]) { flag[lo] = 1; backpart[lo] = (uint32_t)lo; }      /* stay in place if chosen, pmcmc.cc:250-258 */
 		else extra.push_back((uint32_t)lo);
 	}
-	size_t k = 0;
-	for (int i = 0; i < ntot; i++) if (backpart[i] == 0xFFFFFFFFu) backpart[i] = extra[k++];
+	for (int i = 0; i < ntot; i++) if (backpart[i] == 0xFFFFFFFFu) { backpart[i] = extra.back(); extra.pop_back(); }   /* pmcmc.cc:256-260 */
 	return BEEP_OK;
 }
 

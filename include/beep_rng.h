@@ -361,28 +361,63 @@ static __device__ __noinline__ int beep_poisson_ptrs_fresh(uint32_t k0, uint32_t
 }
 #endif
 
+/* sequential-search inversion for 0 < lam < 10 from the uniform u */
+BEEP_HD int beep_poisson_inv_u(double u, double lam)
+{
+	/* exp(-lam) >= 1 - lam, and beep_exp is good to ~1 ulp: a uniform below
+	 * (1 - lam) - 4.5e-16 yields k = 0 whatever beep_exp rounds to, so the
+	 * shortcut never changes a draw (it only skips the exp) */
+	if (u <= BR_SUB(BR_SUB(1.0, lam), 4.5e-16)) return 0;
+	double p = beep_exp(BR_SUB(0.0, lam));
+	double cdf = p;
+	int k = 0;
+	double ik = BEEP_INV(1);                       /* 1/(k+1), fetched one step ahead of its use */
+	while (u > cdf && k < 1000) {
+		k++;
+		double ikn = BEEP_INV(k < 62 ? k + 1 : 63);
+		p = (k < 64) ? BR_MUL(BR_MUL(p, lam), ik) : BR_DIV(BR_MUL(p, lam), (double)k);
+		cdf = BR_ADD(cdf, p);
+		ik = ikn;
+	}
+	return k;
+}
+
+/* the first two uniforms of a fresh per-cell stream (one Philox block): what the first two calls of
+ * beep_next_uniform return after beep_stream_init_cell */
+BEEP_HD void beep_cell_uniforms(uint64_t seed, uint64_t stream_id, uint64_t cell, double *u1, double *u2)
+{
+	uint32_t key[2], ctr[4], buf[4];
+	key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+	ctr[0] = (uint32_t)(cell >> 32) << 16; ctr[1] = (uint32_t)cell;
+	ctr[2] = (uint32_t)stream_id; ctr[3] = (uint32_t)(stream_id >> 32);
+	beep_philox4x32_10(ctr, key, buf);
+	uint64_t x = (((uint64_t)buf[0] << 32) | (uint64_t)buf[1]) >> 12;
+	*u1 = BR_MUL(BR_ADD((double)x, 0.5), 2.220446049250313080847263336181640625e-16);
+	x = (((uint64_t)buf[2] << 32) | (uint64_t)buf[3]) >> 12;
+	*u2 = BR_MUL(BR_ADD((double)x, 0.5), 2.220446049250313080847263336181640625e-16);
+}
+
+/* the FIRST PTRS attempt from the stream's first two uniforms, squeeze only: returns 1 and the draw when the
+ * squeeze accepts (the value beep_poisson_ptrs returns from its first iteration), 0 when the attempt needs
+ * the exact test or is rejected */
+BEEP_HD int beep_poisson_ptrs_try_uv(double u1, double u2, double lam, int *out)
+{
+	double slam = BR_SQRT(lam);
+	double b = BR_ADD(0.931, BR_MUL(2.53, slam));
+	double a = BR_ADD(-0.059, BR_MUL(0.02483, b));
+	double vr = BR_SUB(0.9277, BR_DIV(3.6224, BR_SUB(b, 2.0)));
+	double U = BR_SUB(u1, 0.5);
+	double V = u2;
+	double us = BR_SUB(0.5, BR_FABS(U));
+	double kf = BR_FLOOR(BR_ADD(BR_ADD(BR_MUL(BR_ADD(BR_DIV(BR_MUL(2.0, a), us), b), U), lam), 0.43));
+	if (us >= 0.07 && V <= vr) { *out = (int)kf; return 1; }
+	return 0;
+}
+
 BEEP_HD int beep_poisson(BeepStream *s, double lam)
 {
 	if (!(lam > 0.0)) return 0;
-	if (lam < BEEP_POISSON_INV_MAX) {
-		double u = beep_next_uniform(s);
-		/* exp(-lam) >= 1 - lam, and beep_exp is good to ~1 ulp: a uniform below
-		 * (1 - lam) - 4.5e-16 yields k = 0 whatever beep_exp rounds to, so the
-		 * shortcut never changes a draw (it only skips the exp) */
-		if (u <= BR_SUB(BR_SUB(1.0, lam), 4.5e-16)) return 0;
-		double p = beep_exp(BR_SUB(0.0, lam));
-		double cdf = p;
-		int k = 0;
-		double ik = BEEP_INV(1);                       /* 1/(k+1), fetched one step ahead of its use */
-		while (u > cdf && k < 1000) {
-			k++;
-			double ikn = BEEP_INV(k < 62 ? k + 1 : 63);
-			p = (k < 64) ? BR_MUL(BR_MUL(p, lam), ik) : BR_DIV(BR_MUL(p, lam), (double)k);
-			cdf = BR_ADD(cdf, p);
-			ik = ikn;
-		}
-		return k;
-	}
+	if (lam < BEEP_POISSON_INV_MAX) return beep_poisson_inv_u(beep_next_uniform(s), lam);
 #if defined(__CUDA_ARCH__)
 	if (s->have == 0) return beep_poisson_ptrs_fresh(s->key[0], s->key[1], s->ctr[0], s->ctr[1], s->ctr[2], s->ctr[3], lam);
 #endif

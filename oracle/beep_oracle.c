@@ -808,8 +808,7 @@ int oracle_bootstrap(const double *L, int ntot, double invT, uint64_t seed, int 
 		if (!flag[lo]) { flag[lo] = 1; backpart[lo] = (uint32_t)lo; } /* stay in place if chosen, pmcmc.cc:250-258 */
 		else extra[nextra++] = (uint32_t)lo;
 	}
-	int k = 0;
-	for (int i = 0; i < ntot; i++) if (backpart[i] == 0xFFFFFFFFu) backpart[i] = extra[k++];
+	for (int i = 0; i < ntot; i++) if (backpart[i] == 0xFFFFFFFFu) backpart[i] = extra[--nextra];      /* pmcmc.cc:256-260: handed out from the back */
 	free(w); free(wsum); free(flag); free(extra);
 	return 0;
 }
