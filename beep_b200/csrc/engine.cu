@@ -1485,3 +1485,5 @@ extern "C" int beep_test_binomial(uint64_t seed, uint64_t stream_id, const doubl
 	cudaFree(dp); cudaFree(dn); cudaFree(dout);
 	return BEEP_OK;
 }
+
+#include "comm.cuh"

@@ -65,6 +65,18 @@ _SIGNATURES = {
     "beep_test_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp]),
     "beep_mvn_kernel_sums": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp]),
     "beep_bootstrap": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, _c_dp, _vp]),
+    "beep_comm_unique_id": (ctypes.c_int, [_vp]),
+    "beep_comm_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "beep_comm_destroy": (None, [_vp]),
+    "beep_comm_rank": (ctypes.c_int, [_vp]),
+    "beep_comm_size": (ctypes.c_int, [_vp]),
+    "beep_comm_bytes_moved": (ctypes.c_int64, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+    "beep_allgather_scalar": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "beep_allgather_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "beep_copy_particles": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "beep_end_sec_swap": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "beep_particle_sample": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "beep_test_move_plan": (ctypes.c_int, [ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_int), _vp, ctypes.POINTER(ctypes.c_int)]),
     "beep_test_poisson": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_int, _vp]),
     "beep_test_binomial": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, _vp, ctypes.c_int, _vp]),
 }
@@ -78,10 +90,26 @@ class BeepError(RuntimeError):
         self.code = code
 
 
+def _preload_nccl():
+    """The engine links libnccl.so.2.  In a process that also imports torch, the NCCL that torch bundles (newer
+    than the system one) must be the copy that gets loaded, whichever of the two libraries comes first."""
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            for f in glob.glob(os.path.join(d, "lib", "libnccl.so.2")):
+                ctypes.CDLL(f, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Load the engine library; raises if it has not been built (no fallback)."""
     global _LIB
     if _LIB is None:
+        _preload_nccl()
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(make -C beep_b200/csrc).  The BEEP engine has no CPU fallback.")
@@ -308,6 +336,90 @@ class Batch:
     @property
     def last_simulate_ms(self):
         return self.L.beep_last_simulate_ms(self.h)
+
+
+def comm_unique_id():
+    """128 bytes of an ncclUniqueId (create on one rank, hand to the others)."""
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().beep_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """The collectives of the particle methods inside the C-ABI library (NCCL, device to device): the
+    replacement of the reference's Mpi object for the hot path (src/mpi.cc:81-165,215-389)."""
+
+    def __init__(self, engine, unique_id, nranks, rank):
+        self.engine = engine
+        self.L = engine.L
+        self.nranks, self.rank = int(nranks), int(rank)
+        h = _vp()
+        idbuf = ctypes.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(self.L.beep_comm_create(engine.h, idbuf, self.nranks, self.rank, ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.beep_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def allgather(self, local):
+        """per-particle scalars (or rows) of every rank, in rank order"""
+        loc = _f64(local)
+        out = np.zeros((self.nranks,) + loc.shape).reshape((self.nranks * loc.shape[0],) + loc.shape[1:])
+        _check(self.L.beep_allgather_scalar(self.h, loc.ctypes.data, loc.size, out.ctypes.data))
+        return out
+
+    def copy_particles(self, batch, partcopy_all):
+        pc = np.ascontiguousarray(partcopy_all, dtype=np.uint32)
+        _check(self.L.beep_copy_particles(self.h, batch.h, pc.ctypes.data, pc.size))
+
+    def end_sec_swap(self, batch, backpart_all):
+        bp = np.ascontiguousarray(backpart_all, dtype=np.uint32)
+        _check(self.L.beep_end_sec_swap(self.h, batch.h, bp.ctypes.data, bp.size))
+
+    def particle_sample(self, batch, backpart):
+        """backpart: [nsec][Ntot].  Returns (theta, transnum) on rank 0, None elsewhere."""
+        bp = np.ascontiguousarray(backpart, dtype=np.uint32)
+        m = batch.model
+        th, tn = np.zeros(m.nparam), np.zeros(m.traj_shape)
+        _check(self.L.beep_particle_sample(self.h, batch.h, bp.ctypes.data, bp.shape[0], bp.shape[1], th.ctypes.data, tn.ctypes.data))
+        return (th, tn) if self.rank == 0 else None
+
+    @property
+    def bytes_moved(self):
+        r = ctypes.c_int64()
+        s = self.L.beep_comm_bytes_moved(self.h, ctypes.byref(r))
+        return s, r.value
+
+
+def particle_sample(batch, backpart):
+    """Mpi::particle_sample on one GPU (no communicator)."""
+    bp = np.ascontiguousarray(backpart, dtype=np.uint32)
+    m = batch.model
+    th, tn = np.zeros(m.nparam), np.zeros(m.traj_shape)
+    _check(lib().beep_particle_sample(None, batch.h, bp.ctypes.data, bp.shape[0], bp.shape[1], th.ctypes.data, tn.ctypes.data))
+    return th, tn
+
+
+def move_plan(kind, vec_all, N, rank):
+    """test hook: (local[N], out [(peer, slot)], in [(peer, [slots])]) of one rank; kind 0 copy_particles, 1 end_sec_swap"""
+    v = np.ascontiguousarray(vec_all, dtype=np.uint32)
+    local = np.zeros(N, dtype=np.uint32)
+    outp = np.zeros(2 * v.size + 2, dtype=np.int32)
+    inf = np.zeros(3 * v.size + 3, dtype=np.int32)
+    nout, nin = ctypes.c_int(), ctypes.c_int()
+    _check(lib().beep_test_move_plan(kind, v.ctypes.data, v.size, N, rank, local.ctypes.data, outp.ctypes.data, ctypes.byref(nout), inf.ctypes.data, ctypes.byref(nin)))
+    out = [(int(outp[2 * k]), int(outp[2 * k + 1])) for k in range(nout.value)]
+    ins, w = [], 0
+    while w < nin.value:
+        peer, n = int(inf[w]), int(inf[w + 1])
+        ins.append((peer, [int(x) for x in inf[w + 2:w + 2 + n]]))
+        w += 2 + n
+    return local, out, ins
 
 
 def mvn_kernel_sums(engine, var, inv_M, size, param_prop, param_last, w_last):

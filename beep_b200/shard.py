@@ -66,11 +66,12 @@ class ShardedFilter:
     likelihood estimate, identical on every rank.
     """
 
-    def __init__(self, batch, rank=0, world=1, dist=None, device=None):
+    def __init__(self, batch, rank=0, world=1, dist=None, device=None, comm=None):
         self.batch = batch
         self.rank, self.world = rank, world
         self.dist = dist
         self.device = device
+        self.comm = comm              # engine.Comm: the library's own NCCL collectives (device to device)
         self.ancestry = []
 
     def run(self, theta, seed, invT=1.0):
@@ -91,12 +92,16 @@ class ShardedFilter:
                 mine = back[lo:lo + N]
                 if self.world == 1:
                     b.permute(mine, E.PERMUTE_SECTION_STATE)
+                elif self.comm is not None:
+                    # Mpi::end_sec_swap (mpi.cc:215-327): only the distinct ancestors owned by another rank travel, HBM to HBM
+                    self.comm.end_sec_swap(b, back)
                 else:
+                    # CPU test path (gloo, oracle batches): the ancestors' states from the all-gathered section state
                     allpop = allgather(b.pop_all(), self.dist, self.device)      # [Ntot][A][C][D]
                     b.set_pop_all(allpop[mine], ti)
             b.simulate(ti, tf, seed=seed, stream_ids=ids if s == 0 else None)
             L = b.obs_loglik(section=s)
-            L_all = allgather(L, self.dist, self.device)
+            L_all = self.comm.allgather(L) if (self.comm is not None and self.world > 1) else allgather(L, self.dist, self.device)
             assert L_all.size == ntot
             inc, back = E.bootstrap(L_all, invT, seed, s)
             loglik += inc

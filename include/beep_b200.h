@@ -220,6 +220,43 @@ int beep_bootstrap(const double *L_all_host, int ntot, double invT, uint64_t see
 int beep_save_sample(BeepBatch *batch, int slot, const char *file_prefix, const char *const *param_names, double EF, double start_time);
 int beep_load_sample(BeepBatch *batch, int slot, const char *file_prefix, const char *const *param_names, double *EF_out);
 
+/* ------------------------------------------------------------------------ */
+/* Collectives of the particle methods: NCCL over NVLink, device to device   */
+/* ------------------------------------------------------------------------ */
+/* One BeepComm per GPU / rank replaces the reference's Mpi object (src/mpi.hh:16-60) for the hot path.  Global
+ * particle i lives on rank i / N (N = particles per rank), the reference's core = i/N (mpi.cc:98-101).
+ * beep_comm_unique_id writes the 128 bytes of an ncclUniqueId on ONE rank; the caller hands them to the other
+ * ranks by whatever it has (MPI_Bcast in the reference's host code, a file, torch.distributed in the bench).   */
+typedef struct BeepComm BeepComm;
+int beep_comm_unique_id(void *id128);
+int beep_comm_create(BeepEngine *eng, const void *id128, int nranks, int rank, BeepComm **out);
+void beep_comm_destroy(BeepComm *comm);
+int beep_comm_rank(const BeepComm *comm);
+int beep_comm_size(const BeepComm *comm);
+/* bytes this rank has sent (returned) and received (*recv) in particle movements so far */
+int64_t beep_comm_bytes_moved(const BeepComm *comm, int64_t *recv);
+/* Replaces mpi.gather + decision on rank 0 + mpi.bcast of per-particle scalars (abcmbp.cc:141, pas.cc:133,
+ * pmcmc.cc:219,263, mc3.cc:170-175; ABC-SMC's (theta, EF, w) exchange mpi.cc:169-211): every rank gets every
+ * rank's n_local values, in rank order.  _scalar: host arrays; _dev: device arrays on `stream` (NULL = the
+ * communicator's own).                                                                                         */
+int beep_allgather_scalar(BeepComm *comm, const double *local_host, int n_local, double *all_host);
+int beep_allgather_dev(BeepComm *comm, const double *local_dev, int n_local, double *all_dev, void *stream);
+/* Replaces Mpi::copy_particles (mpi.cc:81-165): global particle i continues as a copy of partcopy_all[i]
+ * (0xFFFFFFFF = keep; the output of beep_ef_cutoff / beep_pas_bootstrap / beep_mc3_swap).  Whole particles move
+ * HBM to HBM as their per-particle slabs (grouped ncclSend / ncclRecv); copies within a rank are one device
+ * permutation.  The state arrives complete: no replay is needed afterwards.                                    */
+int beep_copy_particles(BeepComm *comm, BeepBatch *batch, const uint32_t *partcopy_all_host, int ntot);
+/* Replaces Mpi::end_sec_swap (mpi.cc:215-327): particle p continues from the section state of backpart_all[p]
+ * (the output of beep_bootstrap).  Only the DISTINCT ancestors that live on another rank travel.               */
+int beep_end_sec_swap(BeepComm *comm, BeepBatch *batch, const uint32_t *backpart_all_host, int ntot);
+/* Replaces Mpi::particle_sample (mpi.cc:331-389): one filtered trajectory assembled backwards through the
+ * ancestry backpart_host[nsec][Ntot] (row s = beep_bootstrap's output after section s).  Rank 0 receives
+ * theta_host[nparam] and transnum_host[T][A][J][D]; comm may be NULL on a single GPU.                          */
+int beep_particle_sample(BeepComm *comm, BeepBatch *batch, const uint32_t *backpart_host, int nsec, int ntot, double *theta_host, double *transnum_host);
+/* test hook: the send / receive lists one rank derives (kind 0 = copy_particles, 1 = end_sec_swap)             */
+int beep_test_move_plan(int kind, const uint32_t *vec_all, int ntot, int N, int rank, uint32_t *local, int32_t *out_pairs, int *nout,
+                        int32_t *in_flat, int *nin_words);
+
 /* Resampling decisions of the particle methods, on
  * scalars that every rank has all-gathered: pure host arithmetic, replicated
  * on every rank from a counter-based stream keyed by (seed, generation/sweep)
