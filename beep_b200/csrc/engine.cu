@@ -583,6 +583,14 @@ extern "C" int64_t beep_batch_bytes(const BeepBatch *bt) { return bt ? bt->bytes
 extern "C" void *beep_batch_stream(BeepBatch *bt) { return bt ? (void *)bt->stream : nullptr; }
 extern "C" int64_t beep_launch_count(const BeepEngine *eng) { return eng ? eng->launches : 0; }
 extern "C" int beep_engine_sync_scope(const BeepEngine *eng) { return eng ? eng->sync_mode : -1; }
+extern "C" int beep_engine_dims(const BeepEngine *eng, int *T, int *A, int *C, int *J, int *D, int *nparam, int *nobs, int *ntable)
+{
+	if (!eng) return fail(BEEP_ERR_INVALID, "null engine");
+	const DevModel &m = eng->dm;
+	if (T) *T = m.T; if (A) *A = m.A; if (C) *C = m.C; if (J) *J = m.J; if (D) *D = m.D;
+	if (nparam) *nparam = m.nparam; if (nobs) *nobs = m.nobs; if (ntable) *ntable = m.ntable;
+	return BEEP_OK;
+}
 extern "C" int beep_engine_chunk_tiles(const BeepEngine *eng) { return (eng && eng->chunk_ok) ? eng->chunk_nt : 0; }
 extern "C" int beep_sync(BeepBatch *bt)
 {

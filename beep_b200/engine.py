@@ -55,6 +55,7 @@ _SIGNATURES = {
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_engine_chunk_tiles": (ctypes.c_int, [_vp]),
+    "beep_engine_dims": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 8),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
     "beep_save_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_double, ctypes.c_double]),
     "beep_load_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, _c_dp]),

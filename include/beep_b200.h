@@ -191,6 +191,8 @@ void *beep_batch_stream(BeepBatch *batch);
 /* scope of the per-step barrier the trajectory kernel uses for this model:
  * 0 = none (areas uncoupled), 1 = CTA (a CTA owns a particle), 2 = cooperative grid */
 int beep_engine_sync_scope(const BeepEngine *eng);
+/* the dimensions the engine was created with (any pointer may be NULL) */
+int beep_engine_dims(const BeepEngine *eng, int *T, int *A, int *C, int *J, int *D, int *nparam, int *nobs, int *ntable);
 /* tiles (consecutive areas of one particle-step) a warp of the grid-spanning trajectory kernel works at once:
  * 4 or 8 when the chunk kernel (integer populations, pooled draws) serves the model, 0 when the
  * one-tile-per-warp kernel does */

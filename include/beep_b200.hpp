@@ -32,6 +32,9 @@ public:
 	Engine &operator=(const Engine &) = delete;
 	BeepEngine *handle() const { return h_; }
 	int nsection() const { return beep_num_sections(h_); }
+	int ntable() const { int v = 0; check(beep_engine_dims(h_, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &v)); return v; }
+	/// A*J*D: entries of one time step of Particle::transnum
+	size_t cells_per_step() const { int A = 0, J = 0, D = 0; check(beep_engine_dims(h_, nullptr, &A, nullptr, &J, &D, nullptr, nullptr, nullptr)); return (size_t)A * J * D; }
 	void section_range(int s, int &ti, int &tf) const { check(beep_section_range(h_, s, &ti, &tf)); }
 	/// ABCSMC::calculate_particle_weight's sum over the previous generation (abcsmc.cc:264-268) for all proposals:
 	/// sums[i] = SUM_j w_last[j] exp(MVN::probability(prop_i, last_j)); parameters are rows of nparam doubles

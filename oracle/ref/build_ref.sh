@@ -17,7 +17,7 @@ OUT="$ROOT/oracle/_ref"
 OPT="${BEEP_REF_OPT:--O3}"
 if [ ! -d "$REF/src" ]; then echo "build_ref: $REF/src not found (reference absent) - nothing to do"; exit 0; fi
 mkdir -p "$OUT/obj"
-CXXFLAGS="$OPT -g0 -w -std=c++11 -mfma -I$HERE/mpi_shim -I$REF/toml11 -I$REF/src"
+CXXFLAGS="$OPT -g0 -w -std=c++11 -mfma -I$ROOT/host/ref_adapter/mpi_shim -I$REF/toml11 -I$REF/src"
 ls "$REF"/src/*.cc | grep -v -E "indbased_code|runtests|old_code" | \
   xargs -P "$(nproc)" -I{} sh -c 'f="{}"; b=$(basename "$f" .cc); o="'"$OUT"'/obj/$b.o"; if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then g++ '"$CXXFLAGS"' -c "$f" -o "$o"; fi'
 # utils.cc once more with the two integer samplers renamed, so that the harness can
