@@ -18,6 +18,17 @@ Other workloads (extra lines for DESIGN.md, not the driver's headline):
 One process per GPU (torchrun for N > 1); particles are sharded across ranks with no data-path
 collective (weak scaling).
 
+Every line also carries two extra objects measured AFTER the headline (they are not part of `value`):
+  "filter"   BASELINE configs[3]: the bootstrap particle filter of PMCMC::obs_prob (pmcmc.cc:180-268) on the
+             England_AS model, 4 096 particles in all sharded over the ranks (strong scaling) -- sections
+             simulated on the device, weights all-gathered (ncclAllGather), the distinct remote ancestors moved
+             HBM to HBM (beep_end_sec_swap), one trajectory drawn (beep_particle_sample); seconds per filter
+             pass and the collectives' share of it;
+  "abcsmc"   BASELINE's second metric: seconds per ABC-SMC generation (abcsmc.cc:26-131) of 16 384 England_AS
+             simulations in all, run by the reference's OWN host code on the engine (host/_ref/BEEP_b200:
+             TOML inputs, priors, MVN proposals of the reference; batched engine calls; one process per GPU,
+             samples exchanged by beep_allgather_scalar), with the reference's mode=abcsmc simulations/s beside it.
+
 `--impl reference` times the UNMODIFIED reference on all host cores (kind "reference"): oracle/_ref/ref_harness
 (the reference's own objects, built here from /root/reference and shipped as a binary) runs the synthetic
 population written in the reference's own TOML/CSV formats.  Where that is not possible (binary absent, or the
@@ -53,6 +64,8 @@ def parse():
     ap.add_argument("--particles", type=int, default=int(os.environ.get("BEEP_BENCH_PARTICLES", 0)), help="particles per GPU (0 = workload default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--keep-traj", action="store_true", help="store transnum (MBP chain initialisation)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)     # one launch under ncu (see measure_traffic)
+    ap.add_argument("--no-extras", action="store_true", help="skip the filter / abcsmc objects")
     a = ap.parse_args()
     if a.particles <= 0:
         a.particles = 16 if a.workload == "synthetic" else 16384
@@ -161,20 +174,36 @@ def cpu_run(args, steps, warmup, budget_s=12.0):
     what = "set_param+mbp+obs_loglik" if args.mode == "mbp" else "set_param+simulate+obs_loglik"
     shape = f"synthetic generator at A={m.A} areas x {m.D} ages x {m.T} steps" if args.workload == "synthetic" else "England_AS shape"
     sample = (f"oracle/liboracle.so (C restatement of state.cc/mbp.cc/obsmodel.cc), {shape}, {nthread} threads x {reps} particles per step, {what}")
-    return units / dt, nthread, sample, dt / steps * 1e3
+    return units / dt, nthread, sample, dt / steps * 1e3, int(m.A)
 
 
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
-def reference_run(args, steps, budget_s=4.0, areas=256):
+def reference_areas(nproc):
+    """The reference keeps pop / transnum / transmean for all T steps per State (about 2.3 MB per area at the
+    synthetic shape) and reads the geographic matrix only as a dense CSV (data_matrix.cc:206-229: A^2 numbers),
+    so the 10 000-area configuration itself cannot be loaded; the reference arm runs the same generator at the
+    largest area count that fits a third of the free host memory over `nproc` processes, at most 2 048."""
+    free = 64e9
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                free = float(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    a = int(free / 3 / nproc / 5.5e6)          # measured: about 4-5 MB of resident memory per area and process
+    return int(max(256, min(2048, a // 64 * 64)))
+
+
+def reference_run(args, steps, budget_s=4.0, areas=None):
     """Times the UNMODIFIED reference (oracle/_ref/ref_harness: the reference's own objects, built from the
     sources under /root/reference by oracle/ref/build_ref.sh and shipped as a binary) on the synthetic
     population written in the reference's own TOML/CSV formats (beep_b200.synth.write_reference_inputs):
     one single-rank process per host core -- what the reference's MPI ranks do between collectives -- each
     looping State::simulate(param) + ObservationModel::calculate with the reference's own samplers.
-    Returns (units/s, cores, sample, ms_per_step) or None when the binary is absent or the workload has no
-    reference input files (England_AS needs the reference's data directory)."""
+    Returns (units/s, cores, sample, ms_per_step, areas) or None when the binary is absent or the workload has no
+    reference input files."""
     if args.workload != "synthetic" or args.mode != "simulate" or not os.access(REF_HARNESS, os.X_OK):
         return None
     import tempfile
@@ -182,15 +211,17 @@ def reference_run(args, steps, budget_s=4.0, areas=256):
     from beep_b200.synth import write_reference_inputs
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nproc = max(1, min(cores, 64))
+    if areas is None:
+        areas = reference_areas(nproc)
     work = tempfile.mkdtemp(prefix="beep_ref_")
     try:
         toml = write_reference_inputs(work, A=areas)
         env = dict(os.environ, BEEP_HARNESS_BENCH=str(budget_s * max(steps, 1)))
-        procs = [subprocess.Popen([REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim", f"outputdir=Output_{i}"],
+        procs = [subprocess.Popen(["timeout", "-s", "KILL", "900", REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim", f"outputdir=Output_{i}"],
                                   cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
         units, secs, ok = 0.0, 0.0, 0
         for i, p in enumerate(procs):
-            rc = p.wait(timeout=900)
+            rc = p.wait(timeout=1000)
             res = os.path.join(work, f"o{i}.bpk.bench")
             if rc != 0 or not os.path.exists(res):
                 print(f"bench.py: reference process {i} failed (rc={rc})", file=sys.stderr)
@@ -208,8 +239,9 @@ def reference_run(args, steps, budget_s=4.0, areas=256):
     finally:
         shutil.rmtree(work, ignore_errors=True)
     sample = (f"oracle/_ref/ref_harness (the unmodified reference's State::simulate + ObservationModel::calculate, its own std:: samplers), "
-              f"synthetic population in the reference's TOML/CSV formats at A={areas} areas x 20 ages x 365 steps, {nproc} single-rank processes x {secs:.1f} s")
-    return units / secs, nproc, sample, secs / max(steps, 1) * 1e3
+              f"synthetic population in the reference's TOML/CSV formats at A={areas} areas x 20 ages x 365 steps (the largest the reference's dense "
+              f"geographic-matrix loader and per-State trajectory storage allow on this host), {nproc} single-rank processes x {secs:.1f} s")
+    return units / secs, nproc, sample, secs / max(steps, 1) * 1e3, areas
 
 
 def main_reference(args):
@@ -220,10 +252,11 @@ def main_reference(args):
     if r is None:
         kind = "port"
         r = cpu_run(args, args.steps, args.warmup)
-    v, cores, sample, ms = r
-    m, theta = load_workload(args, areas=256)
+    v, cores, sample, ms, areas = r
+    m, theta = load_workload(args, areas=areas)
     cfg = workload_config(args, m, theta.size)
-    cfg["areas"] = args.areas if args.workload == "synthetic" else int(m.A)
+    cfg["areas"] = int(m.A)                         # what the reference arm actually ran (see reference_areas)
+    cfg["workload"] += f" [reference arm: {int(m.A)} areas, not {args.areas}: the reference cannot load the dense geographic matrix of the full size]"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -234,6 +267,187 @@ def main_reference(args):
     }
     print(json.dumps(line))
 
+
+
+# ---------------------------------------------------------------------------
+# DRAM traffic of the dominant kernel, measured in this run
+# ---------------------------------------------------------------------------
+def traffic_child(args):
+    """One launch of the bench's trajectory kernel (run under ncu by measure_traffic)."""
+    from beep_b200 import engine as E
+    m, theta = load_workload(args)
+    eng = E.Engine(m, 0)
+    mbp = args.mode == "mbp"
+    flags = (E.KEEP_TRANSNUM | E.KEEP_TRANSMEAN) if mbp else (E.KEEP_TRANSNUM if args.keep_traj else 0)
+    b = eng.batch(args.particles, flags)
+    b.set_params(particle_params(args, theta, args.particles, seed=100))
+    b.simulate(seed=7)
+    b.sync()
+
+
+def measure_traffic(args, local):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the trajectory kernel at the bench configuration:
+    a child process of this script under `ncu --metrics ... -k regex:k_traj -c 1` on this rank's GPU.  None when
+    ncu is not there or fails (the traffic is reported as measured or not at all)."""
+    import shutil
+    ncu = shutil.which("ncu")
+    if ncu is None or args.mode != "simulate":
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_traj", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--traffic-child", "--workload", args.workload, "--mode", args.mode, "--areas", str(args.areas),
+           "--particles", str(args.particles)] + (["--keep-traj"] if args.keep_traj else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = str(local) if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout
+        import csv
+        import io
+        tot, seen = 0.0, 0
+        lines = out.splitlines()
+        start = next(i for i, ln in enumerate(lines) if ln.startswith('"ID"'))
+        for row in csv.DictReader(io.StringIO("\n".join(lines[start:]))):
+            if row.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(row["Metric Value"].replace(",", ""))
+                unit = row.get("Metric Unit", "byte").lower()
+                tot += v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
+                seen += 1
+        return tot if seen == 2 else None
+    except Exception as e:
+        print(f"bench.py: traffic measurement failed: {e!r}", file=sys.stderr)
+        return None
+
+
+# ---------------------------------------------------------------------------
+# extra objects: the sharded particle filter (configs[3]) and ABC-SMC seconds per generation (the second metric)
+# ---------------------------------------------------------------------------
+ADAPTER = os.path.join(ROOT, "host", "_ref", "BEEP_b200")
+REF_BEEP = os.path.join(ROOT, "oracle", "_ref", "BEEP")
+REF_INPUTS = os.path.join(ROOT, "tests", "golden", "ref_inputs")
+
+
+def filter_extra(rank, world, local, dist, ntot=4096, reps=3):
+    """PMCMC::obs_prob (pmcmc.cc:180-268) on England_AS, ntot particles over `world` GPUs (strong scaling)."""
+    import torch
+    from beep_b200 import engine as E
+    from beep_b200.model import ModelDesc
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "England_AS.npz")))
+    arrays = dict(ModelDesc.from_prefixed(d).arrays)
+    arrays["stochastic"] = 1
+    m = ModelDesc(arrays)
+    eng = E.Engine(m, local)
+    uid = None
+    if world > 1:
+        box = [E.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    cm = E.Comm(eng, uid, world, rank)
+    N = ntot // world
+    b = eng.batch(N, E.KEEP_TRANSNUM)
+    theta = np.repeat(d["theta"][:1], N, axis=0)
+    ids = np.arange(rank * N, (rank + 1) * N, dtype=np.uint64)
+    nsec = eng.nsection
+
+    def one(seed):
+        tcomm = 0.0
+        b.set_params(theta)
+        back = np.zeros((nsec, ntot), dtype=np.uint32)
+        ll = 0.0
+        for s in range(nsec):
+            ti, tf = eng.section_range(s)
+            if s > 0:
+                t0 = time.perf_counter()
+                if world > 1:
+                    cm.end_sec_swap(b, back[s - 1])
+                else:
+                    b.permute(back[s - 1], E.PERMUTE_SECTION_STATE)
+                tcomm += time.perf_counter() - t0
+            b.simulate(ti, tf, seed=seed, stream_ids=ids if s == 0 else None)
+            L = b.obs_loglik(section=s)
+            t0 = time.perf_counter()
+            Lall = cm.allgather(L)
+            tcomm += time.perf_counter() - t0
+            inc, back[s] = E.bootstrap(Lall, 1.0, seed, s)
+            ll += inc
+        t0 = time.perf_counter()
+        cm.particle_sample(b, back)
+        tcomm += time.perf_counter() - t0
+        return ll, tcomm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    one(1)
+    barrier()
+    t0 = time.perf_counter()
+    tc = 0.0
+    for r in range(reps):
+        ll, c = one(2 + r)
+        tc += c
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt, tc], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, tc = float(t[0]), float(t[1])
+    sent, recv = cm.bytes_moved
+    out = {"workload": f"bootstrap particle filter (PMCMC::obs_prob) on England_AS, {ntot} particles in all over {world} GPU(s), {nsec} sections, resampling after each, one trajectory sampled",
+           "seconds_per_filter": dt / reps, "particle_steps_per_s": ntot * m.T * m.D * reps / dt, "collectives_share": tc / dt,
+           "collectives": "ncclAllGather of section log-likelihoods + beep_end_sec_swap (distinct remote ancestors, HBM to HBM) + beep_particle_sample" if world > 1 else "one GPU: device permutation only",
+           "bytes_sent_per_rank_per_filter": sent / (reps + 1), "log_likelihood": ll, "scaling": "strong"}
+    cm.close()
+    b.close()
+    eng.close()
+    return out
+
+
+def abcsmc_extra(rank, world, local, nonce, ntot=16384):
+    """Seconds per ABC-SMC generation (abcsmc.cc:26-131) of ntot England_AS simulations in all, by the reference's own
+    host code on the engine (host/_ref/BEEP_b200), one process per GPU.  Generation 0 (prior samples): with the
+    reference's proposal kernel over all 170 free parameters next to none of the later generations' proposals fall
+    inside the prior bounds -- in the reference itself as well -- so they measure the host's rejection loop."""
+    if not os.access(ADAPTER, os.X_OK):
+        return None
+    env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local), BEEP_BATCH=str(ntot // world),
+               BEEP_NCCL_ID_FILE=f"/tmp/beep_nccl_id_{os.environ.get('MASTER_PORT', '0')}_{nonce}")
+    cmd = ["timeout", "-s", "KILL", "300", ADAPTER, "inputfile=COVID 19 England/England_AS.toml", "mode=abcsmc", f"nsample={ntot // 2}", "ngeneration=1",
+           "cutoff_frac=0.5", f"outputdir=/tmp/beep_b200_abcsmc_{rank}"]
+    r = subprocess.run(cmd, cwd=REF_INPUTS, capture_output=True, text=True, env=env)
+    if rank != 0:
+        return None
+    gen = [ln for ln in r.stdout.splitlines() if ln.startswith("generation 0:")]
+    if r.returncode != 0 or not gen:
+        print(f"bench.py: ABC-SMC adapter failed: {r.stdout[-500:]} {r.stderr[-500:]}", file=sys.stderr)
+        return None
+    kv = dict(x.split("=") for x in gen[0].split(":", 1)[1].split())
+    return {"workload": f"ABC-SMC generation 0 on England_AS (obsmodel scale -> normal 10%): {int(float(kv['simulations']))} simulations in all over {world} GPU(s): prior samples, "
+                        "State::simulate, error function, cut-off at cutoff_frac = 0.5, samples exchanged over the ranks; host code = the reference's own objects (host/_ref/BEEP_b200)",
+            "s_per_generation": float(kv["seconds"]), "simulations_per_s": float(kv["simulations/s"]), "EFcut": float(kv["EFcut"])}
+
+
+def abcsmc_reference(nsample=24):
+    """The reference's own mode=abcsmc generation 0 on the host cores: one single-rank process per core, each 2 nsample
+    simulations; start-up (input parsing) measured by a run of 2 simulations and subtracted."""
+    if not os.access(REF_BEEP, os.X_OK):
+        return None
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nproc = max(1, min(cores, 64))
+
+    def run(ns, n):
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(["timeout", "-s", "KILL", "600", REF_BEEP, "inputfile=COVID 19 England/England_AS.toml", "mode=abcsmc", f"nsample={ns}", "ngeneration=1", "cutoff_frac=0.5",
+                                f"outputdir=/tmp/beep_ref_abcsmc_{i}", f"seed={i}"], cwd=REF_INPUTS, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(n)]
+        ok = all(p.wait() == 0 for p in ps)
+        return time.perf_counter() - t0, ok
+
+    t_start, ok0 = run(1, nproc)
+    t_full, ok1 = run(nsample, nproc)
+    if not (ok0 and ok1) or t_full <= t_start:
+        return None
+    sims = nproc * 2 * (nsample - 1)
+    return {"simulations_per_s": sims / (t_full - t_start), "cores": nproc, "kind": "reference",
+            "sample": f"oracle/_ref/BEEP mode=abcsmc generation 0 on England_AS, {nproc} single-rank processes x {2 * nsample} simulations, start-up ({t_start:.1f} s) subtracted"}
 
 # ---------------------------------------------------------------------------
 # clocks sampler
@@ -375,6 +589,21 @@ def main_gpu(args):
 
     value = units * world * args.steps / (ms_dev * 1e-3)
     e2e = units * world * args.steps / (ms_e2e * 1e-3)
+    extra_filter = extra_abcsmc = None
+    if not args.no_extras and args.workload == "synthetic" and args.mode == "simulate":
+        try:
+            extra_filter = filter_extra(rank, world, local, dist)
+        except Exception as e:
+            print(f"bench.py: filter extra failed on rank {rank}: {e!r}", file=sys.stderr)
+        try:
+            box = [os.urandom(6).hex()]
+            if dist is not None:
+                dist.broadcast_object_list(box, src=0)          # a fresh name for the ncclUniqueId hand-over file
+            extra_abcsmc = abcsmc_extra(rank, world, local, box[0])
+        except Exception as e:
+            print(f"bench.py: abcsmc extra failed on rank {rank}: {e!r}", file=sys.stderr)
+        if dist is not None:
+            dist.barrier()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -390,15 +619,7 @@ def main_gpu(args):
     bpu = float(bytes_per_unit(m, args.mode, keep))
     kms = float(np.mean(traj_ms))
     achieved = units * bpu / (kms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath) and args.workload == "synthetic" and args.mode == "simulate":
-        try:
-            t = json.load(open(tpath))
-            # DRAM bytes of one k_traj launch measured by ncu --set full at P = t["particles"]; per launch it scales with P
-            traffic = t["k_traj_dram_bytes_per_launch"] * (P * m.A) / float(t["particles"] * t["areas"])
-        except Exception:
-            traffic = None
+    traffic = measure_traffic(args, local)
     sync = eng.sync_scope
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -408,7 +629,8 @@ def main_gpu(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": f"k_traj<{'MBP' if mbp else 'SIM'},{sync}>", "kernel_ms": kms, "bytes_per_unit": bpu, "units_per_launch": units,
+                     "kernel": (f"k_traj_chunk<{'MBP' if mbp else 'SIM'},NT={eng.chunk_tiles}>" if eng.chunk_tiles else f"k_traj<{'MBP' if mbp else 'SIM'},{sync}>"),
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, measured in this run" if traffic is not None else None, "kernel_ms": kms, "bytes_per_unit": bpu, "units_per_launch": units,
                      "peak_source": peak_src},
         "clocks": clk,
     }
@@ -418,8 +640,14 @@ def main_gpu(args):
         if r is None:
             kind = "port"
             r = cpu_run(args, 2, 1, budget_s=10.0)
-        v, cores, sample, _ = r
+        v, cores, sample, _, _ = r
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    if extra_filter is not None:
+        line["filter"] = extra_filter
+    if extra_abcsmc is not None:
+        if not args.no_cpu and world == 1:
+            extra_abcsmc["cpu_baseline"] = abcsmc_reference()
+        line["abcsmc"] = extra_abcsmc
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -427,7 +655,9 @@ def main_gpu(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.traffic_child:
+        traffic_child(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_gpu(a)

@@ -54,6 +54,7 @@ STAT = {
     "stat_EX_C4": ("examples/EX_C4.toml", ["mode=sim"], 1, 67, 10000),
 }
 POSTERIOR = {"post_EX_A1": ("examples/EX_A1.toml", 2000)}      # BASELINE.json configs[1]: ~2.5 minutes of the reference
+ABCSMC = {"abcsmc_EX_A1": ("examples/EX_A1.toml", 2000, 6)}     # ~3 minutes of the reference
 MVN_CASES = {
     "mvn_small": (12, 7, 60, 16, 71),          # a handful of free parameters (EX_A1-like)
     "mvn_england": (180, 140, 400, 24, 73),    # England_AS-like: 180 parameters, most of them free
@@ -162,6 +163,36 @@ def main():
         os.makedirs(sdir, exist_ok=True)
         for suffix in ("_parameter.csv", "_transition.csv"):
             shutil.copy(os.path.join(outdir, "Posterior", "samples", "sample7" + suffix), os.path.join(sdir, "sample7" + suffix))
+    # ABC-SMC end to end (BASELINE's second metric; abcsmc.cc:26-131): the reference's own run on EX_A1 -- cut-off and
+    # posterior means per generation (Diagnostics/Generation.csv), final estimates, the final samples' error functions
+    for name, (toml, nsample, ngen) in ABCSMC.items():
+        if only and name not in only:
+            continue
+        import csv
+        import json
+        outdir = os.path.join(work, "out_" + name)
+        args = [f"inputfile={toml}", "mode=abcsmc", f"nsample={nsample}", f"ngeneration={ngen}", "cutoff_frac=0.5", f"outputdir={outdir}"]
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "BEEP")] + args, cwd=work, capture_output=True, text=True)
+        gfile = os.path.join(outdir, "Diagnostics", "Generation.csv")
+        if not os.path.exists(gfile):
+            print(f"{name}: reference run FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        lines = [ln for ln in open(gfile) if not ln.startswith("#")]
+        gens = list(csv.DictReader(lines))
+        est = list(csv.DictReader(open(os.path.join(outdir, "Parameter_estimates.csv"))))
+        ef = []
+        sdir = os.path.join(outdir, "Posterior", "samples")
+        for f in sorted(os.listdir(sdir)):
+            if f.endswith("_parameter.csv"):
+                ef.append(float(open(os.path.join(sdir, f)).read().split("Error function,")[1].split()[0]))
+        gen0 = [ln for ln in r.stdout.splitlines() if ln.startswith("Generation 0")]
+        out = {"command": "BEEP " + " ".join(args[:-1]),
+               "EFcut0": float(gen0[0].split("EF Cut-off:")[1].split()[0]) if gen0 else None,
+               "generations": [{k: (float(v) if v not in ("UNSET", "") else None) for k, v in g.items() if k.endswith("(mean)") or k in ("Generation", "EF cut-off", "Model evidence")} for g in gens],
+               "estimates": [{"name": x["Name"], "mean": float(x["Mean"]), "sd": float(x["SD"]), "prior": x["Prior"]} for x in est],
+               "final_EF": sorted(ef)}
+        json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
+        print(f"{name}: {len(gens)} generations, {len(ef)} samples")
     # ABC-SMC weight kernel: the reference's MVN::setup / propose / probability
     # (oracle/ref/ref_mvn.cc): name -> (nparam, nvar, Nlast, Nprop, seed)
     for name, (nparam, nvar, nl, npr, seed) in MVN_CASES.items():

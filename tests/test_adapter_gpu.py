@@ -1,0 +1,64 @@
+"""The reference's own host code on the engine (host/_ref/BEEP_b200, built by host/ref_adapter/build.sh from
+the unmodified reference objects + host/ref_adapter/beep_b200_main.cc) against the reference's own runs.
+
+ABC-SMC (BASELINE's second metric, abcsmc.cc:26-131) on EX_A1: same TOML, same nsample / ngeneration /
+cutoff_frac; the fixture tests/golden/abcsmc_EX_A1.json holds the reference's cut-off and posterior means per
+generation and the error functions of its final samples (tests/golden/make_golden.py).  Stochastic parity:
+cut-offs within 12 %, posterior means within a quarter of the posterior sd, two-sample KS test on the final
+error functions relative to the cut-off (p > 0.001).  Needs the prebuilt binary (it travels with the repo)."""
+import csv
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "host", "_ref", "BEEP_b200")
+INPUTS = os.path.join(GOLDEN, "ref_inputs")
+
+
+def _run(args, env=None, timeout=600):
+    if not os.path.exists(EXE):
+        pytest.skip("host/_ref/BEEP_b200 has not been built (needs the reference sources: host/ref_adapter/build.sh)")
+    r = subprocess.run(["timeout", "-s", "KILL", str(timeout), EXE] + args, cwd=INPUTS, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_abcsmc_matches_reference_run(tmp_path):
+    from scipy import stats
+    ref = json.load(open(os.path.join(GOLDEN, "abcsmc_EX_A1.json")))
+    out = str(tmp_path / "out")
+    _run(["inputfile=examples/EX_A1.toml", "mode=abcsmc", "nsample=2000", "ngeneration=6", "cutoff_frac=0.5", f"outputdir={out}", "seed=3"])
+    gens = list(csv.DictReader(open(os.path.join(out, "b200_generations.csv"))))
+    assert len(gens) == 6
+    cut = [float(g["EFcut"]) for g in gens]
+    ref_cut = [ref["EFcut0"]] + [g["EF cut-off"] for g in ref["generations"]]
+    for a, b in zip(cut, ref_cut):
+        assert abs(a - b) <= 0.12 * b, (cut, ref_cut)
+    rows = list(csv.DictReader(open(os.path.join(out, "b200_posterior_parameters.csv"))))
+    w = np.array([float(r["weight"]) for r in rows])
+    ef = np.array([float(r["EF"]) for r in rows])
+    assert np.all(ef < cut[-1])
+    for est in ref["estimates"]:
+        x = np.array([float(r[est["name"]]) for r in rows])
+        mean = float(np.sum(w * x) / np.sum(w))
+        if est["sd"] == 0:
+            assert mean == est["mean"]
+        else:
+            assert abs(mean - est["mean"]) < 0.25 * est["sd"], (est, mean)
+    ks = stats.ks_2samp(ef / cut[-1], np.array(ref["final_EF"]) / ref_cut[-1])
+    assert ks.pvalue > 1e-3, ks
+
+
+def test_filter_runs_through_the_adapter():
+    out = _run(["inputfile=examples/EX_A1.toml", "mode=pmcmc", "nparticle=512", "nsample=10", "outputdir=/tmp/beep_b200_filter_out"], env={"BEEP_FILTER_REPS": "2"})
+    lines = [ln for ln in out.splitlines() if ln.startswith("filter ")]
+    assert len(lines) == 2
+    ll = [float(ln.split("log-likelihood=")[1].split()[0]) for ln in lines]
+    assert all(np.isfinite(ll)) and abs(ll[0] - ll[1]) < 10          # two seeds of the same filter
+    assert all(float(ln.split("sampled_events=")[1]) > 0 for ln in lines)
