@@ -169,15 +169,19 @@ static void plan_section_swap(const uint32_t *backpart, int ntot, int N, int ran
 		else need[pp].push_back(k);
 	}
 	for (auto &kv : need) pl.in.push_back(MovePlan::In{kv.first / N, kv.second});
-	for (int p = lo; p < lo + N; p++) {
-		std::vector<char> sent(ntot / N, 0);
-		for (int pp = 0; pp < ntot; pp++) {
-			if ((int)backpart[pp] != p) continue;
-			const int cor = pp / N;
-			if (cor != rank && !sent[cor]) { sent[cor] = 1; }
-		}
-		for (int cor = 0; cor < ntot / N; cor++) if (sent[cor]) pl.out.push_back(MovePlan::Out{cor, p - lo});
+	/* one pass over the ancestry (the reference scans all Ntot particles for each of its own, mpi.cc:264-287):
+	 * the ranks that need each local particle */
+	const int nranks = ntot / N;
+	std::vector<std::vector<unsigned char>> want(N);
+	for (int pp = 0; pp < ntot; pp++) {
+		const int p = (int)backpart[pp], cor = pp / N;
+		if (backpart[pp] == 0xFFFFFFFFu || p < lo || p >= lo + N || cor == rank) continue;
+		if (want[p - lo].empty()) want[p - lo].assign(nranks, 0);
+		want[p - lo][cor] = 1;
 	}
+	for (int k = 0; k < N; k++)
+		if (!want[k].empty())
+			for (int cor = 0; cor < nranks; cor++) if (want[k][cor]) pl.out.push_back(MovePlan::Out{cor, k});
 }
 
 /* test hook: the plan of one rank as flat arrays (tests/test_comm_plan_cpu.py replays the exchange of every rank)

@@ -206,6 +206,29 @@ int main(int argc, char **argv)
 		details.pmcmc_obs_period = details.division_per_time*max_dt*int(details.period/(max_dt*10.0));
 		if(details.pmcmc_obs_period == 0) details.pmcmc_obs_period = details.ndivision;
 	}
+	if(getenv("BEEP_HARNESS_OBSPATCH") != NULL){
+		// No example of the reference uses a plain-normal or negative-binomial observation model, censored
+		// ("thresh") or unknown data (negbin cannot even be selected from a TOML file,
+		// inputs.cc:455-460).  To pin ObservationModel::obs_prob's remaining branches (obsmodel.cc:245-305) the
+		// loaded observations are re-labelled in memory, cycling through every (model, datum kind) pair; the
+		// golden likelihoods are then the reference's own obs_prob on them.
+		for(auto tb = 0u; tb < data.datatable.size(); tb++){               // threshold = the table's largest datum: the censored sums stay representable
+			vector <double> vals; for(const auto &ob : data.obs) if(ob.datatable == tb && ob.value < UNKNOWN) vals.push_back(ob.value);
+			sort(vals.begin(),vals.end());
+			data.datatable[tb].threshold = vals.size() ? (unsigned int)(vals[vals.size()-1]+1) : 6;
+		}
+		for(auto i = 0u; i < data.obs.size(); i++){
+			auto &ob = data.obs[i];
+			switch(i%4){
+			case 0: ob.obsmodel = NORMAL_OBSMODEL; if(!(ob.sd > 0)) ob.sd = 2.5; break;
+			case 1: ob.obsmodel = NORMAL_PERCENT_OBSMODEL; if(!(ob.sd > 0)) ob.sd = 1.5; break;
+			case 2: ob.obsmodel = POISSON_OBSMODEL; break;
+			case 3: ob.obsmodel = NEGBINO_OBSMODEL; ob.shape = 3.5 + (i%5); break;
+			}
+			if((i/4)%3 == 1) ob.value = THRESH;
+			if((i/4)%5 == 2) ob.value = UNKNOWN;
+		}
+	}
 	ObservationModel obsmodel(details,data,model);
 	if(details.mode != PMCMC_INF) obsmodel.split_observations();       // obsmodel.cc:326-348
 	Output output(details,data,model,inputs,obsmodel,mpi);

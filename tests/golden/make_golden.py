@@ -59,6 +59,10 @@ MVN_CASES = {
     "mvn_small": (12, 7, 60, 16, 71),          # a handful of free parameters (EX_A1-like)
     "mvn_england": (180, 140, 400, 24, 73),    # England_AS-like: 180 parameters, most of them free
 }
+# observation-model branches no example exercises (plain normal, negative binomial, censored and unknown data):
+# the loaded observations of these cases are re-labelled by the harness (BEEP_HARNESS_OBSPATCH, ref_harness.cc)
+OBSPATCH = {"OBS_C4": ("examples/EX_C4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 83),
+            "OBS_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 89)}
 SUBST = {"England_AS": [('obsmodel="scale"', 'obsmodel="normal 10%"')]}
 BIG = {"England_AS"}
 
@@ -106,12 +110,15 @@ def main():
     write_reference_inputs(work, A=12, G=20, T=140, name="synthetic12")
     CASES["SYN_A12"] = ("synthetic12.toml", ["mode=sim"], 1, 59)
     BIG.add("SYN_A12")
+    CASES.update(OBSPATCH)
     for name, (toml, args, ntheta, seed) in CASES.items():
         if only and name not in only:
             continue
         bpk = os.path.join(work, name + ".bpk")
         cmd = [HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
         env = dict(os.environ)
+        if name in OBSPATCH:
+            env["BEEP_HARNESS_OBSPATCH"] = "1"
         if name in BIG:
             env["BEEP_HARNESS_BIG"] = "1"      # skip pop / Imap / Idiag dumps
         r = subprocess.run(cmd, cwd=work, capture_output=True, text=True, env=env)
