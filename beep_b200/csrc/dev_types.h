@@ -131,6 +131,7 @@ struct DevModel {
 	const int *R_spline_ref, *area_rgrp; const double *R_dist; const int *strain_Rfactor_param;
 	const int *efoi_spline_ref, *efoi_ref; const double *efoi_agedist;
 	const int *Min_off, *Min_src; const double *Min_val; const double *M_diag, *M_factor;
+	const double *Mt_dense;     /* [A][A] transposed mixing matrix, dense (zero diagonal), or null: the DMMA flavour of the contraction */
 	const AreaInfo *area_info;  /* [A] */
 	const Nbr *nbr;             /* [nnz] transposed mixing matrix, sources ascending per destination */
 	const double *pop_init;
@@ -153,6 +154,7 @@ struct DevBatch {
 	unsigned long long *sched;     /* [P][16] per particle, one 128-byte line: word 0 = (step << 32 | next tile) of the
 	                                  particle-step scheduler, word 1 = tiles of that step completed */
 	double *pop_cur, *dinf;
+	double *imap;                  /* [P][S][A][G] Imap of the current step, computed by k_imap_dmma (dense mixing matrix only) */
 	int *popi;                     /* [P][A][CDp4] int32 populations: batches the chunk kernel serves (then pop_cur is null) */
 	double *scratchA;              /* [P][A] K0 scratch (per-area averages) */
 	int *tn; double *tm; double *poptraj;
@@ -171,6 +173,7 @@ struct TrajArgs {
 	unsigned long long seed;
 	/* MBP: the coupled initial state (same slot of the `init` batch) */
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
+	const double *imap_pre;       /* non-null: Imap of this step for every (particle, strain, area, age), from k_imap_dmma */
 	int nwarp;          /* warps per CTA */
 	int chunk;          /* SYNC_GRID: tiles a warp takes per grab of the step's tile counter */
 	int fast;           /* the model has the common structure tile_step_fast handles */

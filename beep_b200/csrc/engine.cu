@@ -18,6 +18,7 @@
 
 #include "kernels.cuh"
 #include "traj_chunk.cuh"
+#include "imap_dense.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* errors                                                                    */
@@ -52,6 +53,7 @@ struct BeepEngine {
 	int none_resident = 1 << 30;   /* CTAs of the tile-resident flavour that are resident at once */
 	void *mvn_buf = nullptr; size_t mvn_cap = 0;   /* grow-only scratch of beep_mvn_kernel_sums */
 	/* chunk kernel (traj_chunk.cuh): the model qualifies, tiles per chunk, launch shape */
+	bool dense_m = false;              /* the mixing matrix is dense: Imap of a step by one DMMA GEMM for the whole batch (imap_dense.cuh) */
 	bool chunk_model = false, chunk_ok = false;
 	int chunk_nt = 0, chunk_grid = 0;
 	size_t chunk_smem = 0;
@@ -271,6 +273,14 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 			ai[c].rg = eng->h_rgrp[c]; ai[c].ie0 = d->efoi_ref[c];
 		}
 		UPV(nbr, nb); UPV(area_info, ai);
+		/* dense mixing matrix (every area mixes with most others): the contraction becomes a GEMM over the batch */
+		eng->dense_m = (A >= 64 && A <= 8192 && (long long)nnz >= 64ll * A);
+		if (const char *e = getenv("BEEP_DENSE_M")) eng->dense_m = atoi(e) != 0 && A <= 8192 && nnz > 0;
+		if (eng->dense_m) {
+			std::vector<double> mt((size_t)A * A, 0.0);
+			for (int c = 0; c < A; c++) for (int k = off[c]; k < off[c + 1]; k++) mt[(size_t)c * A + src[k]] = val[k];
+			UPV(Mt_dense, mt);
+		}
 	}
 	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
 	UP(pop_init, d->pop_init, (size_t)A * C * D);
@@ -447,7 +457,8 @@ static int choose_launch(BeepEngine *eng)
 		if (cta_bytes(eng->nwarp) <= 96 * 1024) { eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp); }
 		else eng->sync_mode = SYNC_GRID;
 	}
-	if (force) {
+	if (eng->dense_m) eng->sync_mode = SYNC_GRID;           /* one launch per step, between the GEMMs */
+	if (force && !eng->dense_m) {
 		int f = atoi(force);
 		if (f == SYNC_GRID) eng->sync_mode = SYNC_GRID;
 		else if (f == SYNC_CTA && m.M_nnz == 0) { eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A); eng->smem_traj = cta_bytes(eng->nwarp); }
@@ -476,7 +487,7 @@ static int choose_launch(BeepEngine *eng)
 		/* the chunk kernel for models of the common structure: NT tiles per warp and grab */
 		eng->chunk_ok = false;
 		const char *off = getenv("BEEP_NO_CHUNK");
-		if (eng->chunk_model && !(off && atoi(off))) {
+		if (eng->chunk_model && !eng->dense_m && !(off && atoi(off))) {
 			int nt = 4;                              /* measured: 4 tiles x 24 warps/SM beats 8 x 16 (profiles/README.md) */
 			if (const char *e = getenv("BEEP_CHUNK_NT")) nt = (atoi(e) == 8) ? 8 : 4;
 			if (m.A < 8) nt = 4;
@@ -552,6 +563,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	else BA(b.pop_cur, (size_t)P * m.A * m.CDp);
 	BA(b.scratchA, (size_t)P * m.A);
 	if (eng->sync_mode == SYNC_GRID) BA(b.dinf, 2 * (size_t)P * m.S * m.A * m.G);
+	if (eng->dense_m) BA(b.imap, (size_t)P * m.S * m.A * m.G);
 	if ((flags & BEEP_KEEP_TRANSNUM) && m.stochastic) BA(b.tn, (size_t)P * TAJD);
 	if ((flags & BEEP_KEEP_TRANSMEAN) || ((flags & BEEP_KEEP_TRANSNUM) && !m.stochastic)) { BA(b.tm, (size_t)P * TAJD); b.flags |= BEEP_KEEP_TRANSMEAN; }
 	if (flags & BEEP_KEEP_POP) BA(b.poptraj, (size_t)P * m.T * m.A * m.C * m.D);
@@ -560,7 +572,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.stream_id, P); BA(b.infmask, P);
 	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
-	if (eng->sync_mode == SYNC_GRID) BA(b.sched, (size_t)P * 16);
+	if (eng->sync_mode == SYNC_GRID) BA(b.sched, ((size_t)P + 1) * 16);
 	else if (eng->sync_mode == SYNC_NONE) BA(b.sched, 16);              /* the tile counter of the persistent warps */
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(k5_chunks((size_t)m.T * m.A * m.J * m.D), (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
 	BA(bt->d_map, P); BA(bt->d_flag, P);
@@ -591,6 +603,7 @@ extern "C" int beep_engine_dims(const BeepEngine *eng, int *T, int *A, int *C, i
 	if (nparam) *nparam = m.nparam; if (nobs) *nobs = m.nobs; if (ntable) *ntable = m.ntable;
 	return BEEP_OK;
 }
+extern "C" int beep_engine_dense_mixing(const BeepEngine *eng) { return (eng && eng->dense_m) ? 1 : 0; }
 extern "C" int beep_engine_chunk_tiles(const BeepEngine *eng) { return (eng && eng->chunk_ok) ? eng->chunk_nt : 0; }
 extern "C" int beep_sync(BeepBatch *bt)
 {
@@ -694,6 +707,56 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	}
 	CU(cudaEventRecord(bt->ev0, bt->stream));
 	const bool keep = (bt->db.flags & (BEEP_KEEP_TRANSNUM | BEEP_KEEP_TRANSMEAN | BEEP_KEEP_POP)) != 0;
+	a.imap_pre = nullptr;
+	if (eng->dense_m) {
+		/* dense mixing matrix: per step, Imap of ALL particles by one DMMA GEMM (the matrix streams once per step
+		 * for the whole batch), then one step of the grid-spanning kernel that reads it */
+		const void *fn1 = traj_fn(mode, SYNC_GRID, keep);
+		void *args1[] = {(void *)&a};
+		const long long ntile = (long long)P * m.A;
+		const int grid = (int)std::min<long long>(eng->coop_grid, (ntile + eng->nwarp - 1) / eng->nwarp);
+		const long long nw = (long long)grid * eng->nwarp;
+		a.chunk = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16, m.A / 4), std::max<long long>(mode == MODE_SIM ? 2 : 1, ntile / (nw * 4))));
+		const size_t dsz = (size_t)P * m.S * m.A * m.G;
+		const int NB = P * m.S, N = NB * m.G;
+		k_dinf_init<<<(int)std::min<size_t>((dsz + 255) / 256, (size_t)eng->nsm * 8), 256, 0, bt->stream>>>(m, bt->db, bt->db.dinf + (ti & 1) * dsz);
+		eng->launches++;
+		a.imap_pre = bt->db.imap;
+		/* the launch-bound step loop (three launches per step) is captured into a CUDA graph and replayed as one
+		 * submission; if the capture is refused the launches go out one by one */
+		auto enqueue = [&](cudaStream_t st) -> cudaError_t {
+			for (int t = ti; t < tf; t++) {
+				k_imap_dmma<<<dim3((N + IMD_TN - 1) / IMD_TN, (m.A + IMD_TM - 1) / IMD_TM), 128, 0, st>>>(m.Mt_dense, bt->db.dinf + (t & 1) * dsz, bt->db.imap, m.A, m.G, NB);
+				k_sched_init<<<(P + 127) / 128, 128, 0, st>>>(bt->db.sched, P, t);
+				a.ti = t; a.tf = t + 1;
+				cudaError_t e = cudaLaunchCooperativeKernel(fn1, dim3(grid), dim3(eng->nwarp * 32), args1, eng->smem_traj, st);
+				if (e != cudaSuccess) return e;
+			}
+			return cudaGetLastError();
+		};
+		bool graphed = false;
+		if (tf - ti > 1 && !getenv("BEEP_NO_GRAPH")) {
+			cudaGraph_t graph = nullptr;
+			cudaGraphExec_t exec = nullptr;
+			if (cudaStreamBeginCapture(bt->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+				cudaError_t e1 = enqueue(bt->stream);
+				cudaError_t e2 = cudaStreamEndCapture(bt->stream, &graph);
+				if (e1 == cudaSuccess && e2 == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+					graphed = cudaGraphLaunch(exec, bt->stream) == cudaSuccess;
+					CU(cudaStreamSynchronize(bt->stream));         /* the graph's argument copies live until it has run */
+				}
+				if (exec) cudaGraphExecDestroy(exec);
+				if (graph) cudaGraphDestroy(graph);
+			}
+			cudaGetLastError();
+		}
+		if (!graphed) CU(enqueue(bt->stream));
+		eng->launches += 3ll * (tf - ti);
+		CU(cudaEventRecord(bt->ev1, bt->stream));
+		bt->have_sim_time = true;
+		bt->cur_t = tf;
+		return BEEP_OK;
+	}
 	const void *fn = traj_fn(mode, eng->sync_mode, keep);
 	void *args[] = {(void *)&a};
 	if (chunk) {

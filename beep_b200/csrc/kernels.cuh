@@ -424,6 +424,7 @@ __global__ void k_sched_init(unsigned long long *sched, int P, int ti)
 {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p < P) { sched[(size_t)p * 16] = (unsigned long long)(unsigned)ti << 32; sched[(size_t)p * 16 + 1] = 0; }
+	if (p == 0) sched[(size_t)P * 16] = 0;            /* particles that have closed their last step */
 }
 
 __global__ void k_zero(double *x, size_t n)
@@ -599,7 +600,8 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 			 * staged through shared memory, 32 at a time, and read back as one 16-byte broadcast each;
 			 * sources ascending = the reference's accumulation order */
 			double Imap = 0;
-			for (int jb = 0; jb < tc.nn; jb += 32) {
+			if (a.imap_pre) Imap = a.imap_pre[(((size_t)tc.p * S + st) * Ad + ci) * G + ll];      /* dense mixing matrix: one GEMM per step for the whole batch */
+			else for (int jb = 0; jb < tc.nn; jb += 32) {
 				const int cnt = (tc.nn - jb < 32) ? tc.nn - jb : 32;
 				if (!staged) {
 					__syncwarp();
@@ -873,6 +875,8 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		const int ll = lane < G ? lane : G - 1;        /* idle lanes repeat the last age: every load stays in range */
 		const char *dcl = (const char *)(dinf_cur + ll);
 		double Imap = 0;
+		if (a.imap_pre) Imap = a.imap_pre[((size_t)p * A + c) * G + ll];           /* dense mixing matrix: one GEMM per step for the whole batch (S == 1 here) */
+		else
 #pragma unroll 1
 		for (int jb = 0; jb < tc.nn; jb += 32) {
 			const int cnt = (tc.nn - jb < 32) ? tc.nn - jb : 32;
@@ -1372,6 +1376,8 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 				/* nothing to take here: finished, or the step's last tiles are still in flight */
 				nmiss++;
 				if (t >= a.tf) nfin++;
+				/* every particle has closed its last step (counted by the closers): nothing is left anywhere */
+				if ((nmiss & 3) == 0 && ld_relaxed_u64(b.sched + (size_t)P * 16) >= (unsigned long long)P) break;
 				if (nmiss >= P) {
 					if (nfin >= P) break;                   /* a full round of finished particles */
 					nmiss = 0; nfin = 0;
@@ -1434,6 +1440,7 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 					while (ld_relaxed_u64(sp + 1) != (unsigned long long)A) { if (++spin > 20000000) __trap(); __nanosleep(64); }
 					st_relaxed_u64(sp + 1, 0ull);
 					st_release_u64(sp, (unsigned long long)(unsigned)(t + 1) << 32);
+					if (t + 1 >= a.tf) red_add_release_u64(b.sched + (size_t)P * 16, 1ull);
 				}
 			}
 			v = vn;

@@ -470,6 +470,8 @@ __global__ void __launch_bounds__(CHUNK_NWARP * 32, ChunkCfg<NT>::MINB) k_traj_c
 		if (t >= a.tf || idx >= (unsigned)A) {
 			nmiss++;
 			if (t >= a.tf) nfin++;
+			/* every particle has closed its last step (counted by the closers): nothing is left anywhere */
+			if ((nmiss & 3) == 0 && ld_relaxed_u64(b.sched + (size_t)P * 16) >= (unsigned long long)P) break;
 			if (nmiss >= P) {
 				if (nfin >= P) break;
 				nmiss = 0; nfin = 0;
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(CHUNK_NWARP * 32, ChunkCfg<NT>::MINB) k_traj_c
 				while (ld_relaxed_u64(sp + 1) != (unsigned long long)A) { if (++spin > 20000000) __trap(); __nanosleep(64); }
 				st_relaxed_u64(sp + 1, 0ull);
 				st_release_u64(sp, (unsigned long long)(unsigned)(t + 1) << 32);
+					if (t + 1 >= a.tf) red_add_release_u64(b.sched + (size_t)P * 16, 1ull);
 			}
 		}
 		v = vn;

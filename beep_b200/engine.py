@@ -55,6 +55,7 @@ _SIGNATURES = {
     "beep_launch_count": (ctypes.c_int64, [_vp]),
     "beep_engine_sync_scope": (ctypes.c_int, [_vp]),
     "beep_engine_chunk_tiles": (ctypes.c_int, [_vp]),
+    "beep_engine_dense_mixing": (ctypes.c_int, [_vp]),
     "beep_engine_dims": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 8),
     "beep_last_simulate_ms": (ctypes.c_double, [_vp]),
     "beep_save_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, _vp, ctypes.c_double, ctypes.c_double]),
@@ -165,6 +166,10 @@ class Engine:
     @property
     def launch_count(self):
         return self.L.beep_launch_count(self.h)
+
+    @property
+    def dense_mixing(self):
+        return bool(self.L.beep_engine_dense_mixing(self.h))
 
     @property
     def chunk_tiles(self):

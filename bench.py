@@ -82,7 +82,8 @@ def load_workload(args, areas=None):
     from beep_b200.synth import make_model
     if args.workload == "synthetic":
         A = areas if areas is not None else args.areas
-        m, theta = make_model(A=A, G=20, T=365)
+        nn = int(os.environ.get("BEEP_BENCH_NNEIGH", 8))      # neighbours per area (8: the sparse matrix of SURVEY 8d; A-1: a dense one)
+        m, theta = make_model(A=A, G=20, T=365, nneigh=min(nn, A - 1))
         return m, theta
     from beep_b200.model import ModelDesc
     d = dict(np.load(os.path.join(ROOT, "tests", "golden", "England_AS.npz")))

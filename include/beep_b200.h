@@ -197,6 +197,9 @@ int beep_engine_dims(const BeepEngine *eng, int *T, int *A, int *C, int *J, int 
  * 4 or 8 when the chunk kernel (integer populations, pooled draws) serves the model, 0 when the
  * one-tile-per-warp kernel does */
 int beep_engine_chunk_tiles(const BeepEngine *eng);
+/* 1 when the area-mixing contraction (state.cc:204-216) runs as a batched FP64 tensor-core GEMM per step (dense
+ * mixing matrix: at least 64 off-diagonal entries per area, or BEEP_DENSE_M=1), 0 when it is the sparse gather */
+int beep_engine_dense_mixing(const BeepEngine *eng);
 /* number of engine kernel launches since creation (bench accounting)        */
 int64_t beep_launch_count(const BeepEngine *eng);
 /* last kernel-only duration of beep_simulate in ms (CUDA events on the
