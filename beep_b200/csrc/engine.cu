@@ -1363,7 +1363,9 @@ extern "C" int beep_ef_cutoff(const double *EF, int ntot, double *EFcut, double 
 	if (!EF || ntot < 2 || !EFcut || !EFmin || !EFmax || !partcopy) return fail(BEEP_ERR_INVALID, "bad argument to beep_ef_cutoff");
 	std::vector<uint32_t> ord(ntot);
 	for (int i = 0; i < ntot; i++) ord[i] = (uint32_t)i;
-	std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return EF[a] < EF[b]; });
+	/* std::sort with the reference's comparator (abcmbp.cc:130-131,148): ties come out in the order the
+	 * reference's own sort leaves them (tests/golden/decisions.npz holds a tie) */
+	std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return EF[a] < EF[b]; });
 	const int half = ntot / 2;
 	*EFcut = 0.5 * (EF[ord[half - 1]] + EF[ord[half]]);
 	*EFmin = EF[ord[(int)(0.025 * ntot)]]; *EFmax = EF[ord[(int)(0.975 * ntot)]];
@@ -1424,8 +1426,8 @@ extern "C" int beep_mc3_swap(const uint32_t *run, const double *invT, const doub
 	decision_stream(&rs, seed, (uint32_t)sweep, 0x3C3u);
 	for (int loop = 0; loop < 5; loop++)
 		for (int i = 0; i + 1 < ntot; i++) {
-			const double u = beep_next_uniform(&rs);                                     /* one per pair, used or not: position-stable */
 			if (run[i] != run[i + 1]) continue;
+			const double u = beep_next_uniform(&rs);                                     /* one per pair of the same run, as the reference's ran() (:180) */
 			const double al = exp(0.5 * (invT[i] - invT[i + 1]) * (EF[i] - EF[i + 1]));   /* :179 */
 			ntr_inc[i]++;
 			if (u < al) {

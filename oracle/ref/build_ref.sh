@@ -7,6 +7,7 @@
 #   oracle/_ref/BEEP         the reference executable (single-rank MPI shim)
 #   oracle/_ref/ref_harness  adapter + golden-vector generator (ref_harness.cc)
 #   oracle/_ref/ref_mvn      golden vectors of the ABC-SMC weight kernel (ref_mvn.cc)
+#   oracle/_ref/ref_decisions golden vectors of the resampling decisions (ref_decisions.cc)
 # The reference's CMake cannot be used here (find_package(MPI REQUIRED) and a
 # network FetchContent); nothing is copied into the repo.  TEST INFRASTRUCTURE.
 set -e
@@ -30,4 +31,8 @@ g++ $CXXFLAGS -ffp-contract=off -I"$ROOT/include" -c "$HERE/ref_harness.cc" -o "
 g++ -o "$OUT/ref_harness" "$OUT/ref_harness.oo" $OBJS "$OUT/obj/utils_renamed.oo"
 g++ $CXXFLAGS -ffp-contract=off -c "$HERE/ref_mvn.cc" -o "$OUT/ref_mvn.oo"
 g++ -o "$OUT/ref_mvn" "$OUT/ref_mvn.oo" $OBJS "$OUT/obj/utils.o"
+# the decisions harness: utils.cc once more with ran() renamed, so that the harness supplies it (link-time injection)
+g++ $CXXFLAGS -Dran=beepref_ran -c "$REF/src/utils.cc" -o "$OUT/obj/utils_ran.oo"
+g++ $CXXFLAGS -ffp-contract=off -I"$ROOT/include" -c "$HERE/ref_decisions.cc" -o "$OUT/ref_decisions.oo"
+g++ -o "$OUT/ref_decisions" "$OUT/ref_decisions.oo" $OBJS "$OUT/obj/utils_ran.oo"
 echo "build_ref: built $OUT/BEEP, $OUT/ref_harness and $OUT/ref_mvn"

@@ -33,6 +33,9 @@ CASES = {
     "EX_A1": ("examples/EX_A1.toml", ["mode=mcmcmbp", "nsample=10"], 3, 11),
     # EX_B1 (marginal + population-fraction data) cannot be used: the reference itself aborts on it at this
     # commit, in inference mode ("Cannot have zero variance", data.cc:1113) and in mode=sim (Utils error 2)
+    "EX_A5": ("examples/EX_A5.toml", ["mode=mcmcmbp", "nsample=10"], 2, 13),   # a second demographic classification (sex) with susceptibility
+    "EX_C3": ("examples/EX_C3.toml", ["mode=mcmcmbp", "nsample=10"], 2, 27),   # areas x a demographic classification
+    "EX_G3": ("examples/EX_G3.toml", ["mode=sim"], 1, 47),   # the England model structure in small (smoothed-spline priors: simulation mode, as EX_E2)
     "EX_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 17),   # Poisson observation model
     "EX_B6": ("examples/EX_B6.toml", ["mode=mcmcmbp", "nsample=10"], 2, 19),   # observation factor spline
     "EX_C2": ("examples/EX_C2.toml", ["mode=mcmcmbp", "nsample=10"], 3, 23),   # 10 areas, covariates, area effects, Dirichlet
@@ -55,6 +58,8 @@ STAT = {
 }
 POSTERIOR = {"post_EX_A1": ("examples/EX_A1.toml", 2000)}      # BASELINE.json configs[1]: ~2.5 minutes of the reference
 ABCSMC = {"abcsmc_EX_A1": ("examples/EX_A1.toml", 2000, 6)}     # ~3 minutes of the reference
+DECISIONS = {"pmcmc": ["mode=pmcmc", "nparticle=24", "nsample=1000"], "abcmbp": ["mode=abcmbp", "nparticle=24", "ngeneration=3"],
+             "pas": ["mode=pas", "nparticle=12", "nrun=2", "invT_final=1"], "mc3": ["mode=mc3", "nchain=6", "nrun=2", "invT_final=1", "nsample=1000"]}
 MVN_CASES = {
     "mvn_small": (12, 7, 60, 16, 71),          # a handful of free parameters (EX_A1-like)
     "mvn_england": (180, 140, 400, 24, 73),    # England_AS-like: 180 parameters, most of them free
@@ -200,6 +205,22 @@ def main():
                "final_EF": sorted(ef)}
         json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
         print(f"{name}: {len(gens)} generations, {len(ef)} samples")
+    # resampling decisions by the reference's own PMCMC::bootstrap, ABCMBP::EF_cutoff,
+    # PAS::bootstrap and MC3::swap_states with ran() injected at link time (oracle/ref/ref_decisions.cc)
+    if not only or "decisions" in only:
+        dec = {}
+        for which, args in DECISIONS.items():
+            bpk = os.path.join(work, f"dec_{which}.bpk")
+            r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_decisions"), which, bpk, "5", "inputfile=examples/EX_A1.toml", f"outputdir={work}/dec_out"] + args,
+                               cwd=work, capture_output=True, text=True)
+            if r.returncode != 0 or not os.path.exists(bpk):
+                print(f"decisions/{which}: FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+                continue
+            for k, v in read_bpk(bpk).items():
+                dec[f"{which}.{k}"] = v
+        path = os.path.join(ROOT, "tests", "golden", "decisions.npz")
+        np.savez_compressed(path, **dec)
+        print(f"decisions: {len(dec)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
     # ABC-SMC weight kernel: the reference's MVN::setup / propose / probability
     # (oracle/ref/ref_mvn.cc): name -> (nparam, nvar, Nlast, Nprop, seed)
     for name, (nparam, nvar, nl, npr, seed) in MVN_CASES.items():
