@@ -80,9 +80,10 @@ static inline TrajSm traj_sm_layout(int G, int J, int D, int nbr_doubles = 64)
 
 /* Shared-memory layout of the chunk kernel (traj_chunk.cuh): byte offsets inside a warp's area.
  *   pop[NT][CDp4] int32 | lmean[cap] double (the infectivity vectors Iv[NT][Gs] during the force-of-infection
- *   phase) | foi[NT][G] double | tinfo[NT] 32-byte records | lcell[cap] u16 | acc[NT][CHUNK_NEJ] int32 | mbarrier */
+ *   phase) | foi[NT][G] double | tinfo[NT] 32-byte records | lcell[cap] u16 | acc[NT][CHUNK_NEJ] int32 | mbarrier |
+ *   lu: 8 doubles + 8 ints */
 #define CHUNK_NEJ 8                       /* observation entries per (sett, area) cell the chunk kernel accumulates */
-struct ChunkSm { int pop, lmean, foi, tinfo, lcell, acc, bar, per, cap; };
+struct ChunkSm { int pop, lmean, foi, tinfo, lcell, acc, bar, lu, per, cap; };
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
@@ -98,6 +99,7 @@ static inline ChunkSm chunk_sm_layout(int NT, int G, int Gs, int JD32, int CDp4)
 	s.lcell = o; o += ((s.cap * 2 + 15) & ~15);
 	s.acc = o; o += NT * CHUNK_NEJ * 4;
 	s.bar = o; o += 16;
+	s.lu = o; o += 96;                        /* (coefficient, byte offset) of up to 8 infectious compartments, staged for the close phase */
 	s.per = (o + 15) & ~15;
 	return s;
 }

@@ -361,7 +361,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 			const double v = d->pop_init[i];
 			if (!(std::fabs(v) < 2e9) || v != std::floor(v)) eng->chunk_model = false;
 		}
-		for (unsigned q = 0; q < 8u * 32u; q++) if (((q * ((65536u + G - 1) / G)) >> 16) != q / G) eng->chunk_model = false;
+		for (unsigned q = 0; q < std::max(8u * 32u, (unsigned)(J * D)); q++) if (((q * ((65536u + G - 1) / G)) >> 16) != q / G) eng->chunk_model = false;
 		int per = d->pmcmc_obs_period > 0 ? d->pmcmc_obs_period : T;
 		m.nsection = (T + per - 1) / per;
 		for (int s = 0; s < m.nsection; s++) {

@@ -37,7 +37,13 @@
 
 #include "kernels.cuh"
 
+#ifndef CHUNK_NWARP
 #define CHUNK_NWARP 4
+#endif
+#ifndef CHUNK_GUNROLL
+#define CHUNK_GUNROLL 4
+#endif
+static constexpr int GUNROLL = CHUNK_GUNROLL;
 
 __device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_shared_add(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -67,6 +73,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #define TI_K0 24     /* int     first entry of the tile's (sett, area) observation list   */
 #define TI_NENT 28   /* int     entries in that list                                      */
 
+
+
 template <int MODE, bool KEEP, int NT>
 __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const int t, const int c0, const int nt, const int lane,
                                            const unsigned wb, const unsigned ca, unsigned &phase)
@@ -87,12 +95,22 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 	const int GsB = L.Gs * 8;
 
 	/* 1a. state.cc:204-216, 547-553: the infectivity vector I of every (tile, age) pair */
-	if (lane < NT) sts32(ti_a + lane * 32 + TI_NZ, 0u);
 	for (int x = lane; x < nt * (L.Gs - G); x += 32) { const int i = x / (L.Gs - G), k = x - i * (L.Gs - G); sts64(lm_a + i * GsB + (G + k) * 8, 0.0); }
+	if (lane < nt) {
+		/* per-tile scalars, one lane per tile: beta * area factor (state.cc:410-411), external force (:423) */
+		const int c = c0 + lane;
+		const AreaInfo ai = m.area_info[c];
+		double be = b.betaR[((size_t)p * m.nR + ai.rg) * T + t];
+		be *= b.areafactor[((size_t)p * m.period + t / m.spu) * A + c];
+		const unsigned tia = ti_a + lane * 32;
+		sts64(tia + TI_BEAF, be);
+		sts64(tia + TI_ET, b.etab[((size_t)p * m.nefoi + ai.ie0) * T + t]);
+		sts32(tia + TI_IE0G, (unsigned)(ai.ie0 * G));
+		sts32(tia + TI_NZ, 0u);
+	}
 	__syncwarp();
 	{
 		const double d = ds[m.geo_spline * T + t], omd = 1 - d;
-		const int tday = t / m.spu;
 #pragma unroll 1
 		for (int q0 = 0; q0 < npair; q0 += 32) {
 			int q = q0 + lane;
@@ -103,7 +121,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 			const char *dcl = (const char *)(dinf_cur + ag);
 			const Nbr *nb = m.nbr + ai.j0;
 			double Imap = 0;
-#pragma unroll 4
+#pragma unroll (GUNROLL)
 			for (int j = 0; j < ai.nn; j++) {
 				const double2 raw = __ldg((const double2 *)(nb + j));        /* (weight, byte offset of the source area) */
 				Imap += ld_l2((const double *)(dcl + (unsigned)__double2loint(raw.y))) * raw.x;
@@ -113,13 +131,6 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 			if (valid) {
 				sts64(lm_a + i * GsB + ag * 8, Iv);
 				if (Iv != 0) sts32(ti_a + i * 32 + TI_NZ, 1u);
-				if (ag == 0) {
-					double be = b.betaR[((size_t)p * m.nR + ai.rg) * T + t];
-					be *= b.areafactor[((size_t)p * m.period + tday) * A + c];
-					sts64(ti_a + i * 32 + TI_BEAF, be);
-					sts64(ti_a + i * 32 + TI_ET, b.etab[((size_t)p * m.nefoi + ai.ie0) * T + t]);
-					sts32(ti_a + i * 32 + TI_IE0G, (unsigned)(ai.ie0 * G));
-				}
 			}
 		}
 	}
@@ -211,147 +222,149 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 	const unsigned long long sid = b.stream_id[p];
 	const int top = Ls.cap - 1;
 	unsigned dirty = 0;
-	int itile = 0;
+	{
+		int itile = 0;
 #pragma unroll 1
-	while (true) {
-		unsigned cnt2 = 0;                                  /* nsmall | nbig << 16 */
+		while (true) {
+			unsigned cnt2 = 0;                                  /* nsmall | nbig << 16 */
 #pragma unroll 1
-		for (; itile < nt && (int)((cnt2 & 0xffffu) + (cnt2 >> 16)) + JD <= Ls.cap; itile++) {
-			const unsigned pa = pop_a + itile * (CDp4 * 4), fa = foi_a + itile * (G * 8);
-			const size_t tbase = tbase0 + (size_t)itile * JD;
-			int simu = 0;
-			if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c0 + itile];
+			for (; itile < nt && (int)((cnt2 & 0xffffu) + (cnt2 >> 16)) + JD <= Ls.cap; itile++) {
+				const unsigned pa = pop_a + itile * (CDp4 * 4), fa = foi_a + itile * (G * 8);
+				const size_t tbase = tbase0 + (size_t)itile * JD;
+				int simu = 0;
+				if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c0 + itile];
 #pragma unroll 1
-			for (int e0 = 0; e0 < JD; e0 += 32) {
-				const int e = e0 + lane;
-				const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
-				const int popi = (int)lds32(pa + ((w & 0xfffu) << 2));
-				if (MODE == MODE_REPLAY) {
-					/* the events are given (state.cc:294-322); only the means are recomputed */
-					int num = 0;
-					if (e < JD) {
-						double mean = dt * (double)popi * crate[e];
-						if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
-						if (!(popi > 0)) mean = 0;
-						num = b.tn[tbase + e];
-						if (keep_tm) b.tm[tbase + e] = mean;
+				for (int e0 = 0; e0 < JD; e0 += 32) {
+					const int e = e0 + lane;
+					const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
+					const int popi = (int)lds32(pa + ((w & 0xfffu) << 2));
+					if (MODE == MODE_REPLAY) {
+						/* the events are given (state.cc:294-322); only the means are recomputed */
+						int num = 0;
+						if (e < JD) {
+							double mean = dt * (double)popi * crate[e];
+							if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
+							if (!(popi > 0)) mean = 0;
+							num = b.tn[tbase + e];
+							if (keep_tm) b.tm[tbase + e] = mean;
+						}
+						const unsigned bal = __ballot_sync(FULLMASK, num != 0);
+						if (num != 0) {
+							const int pos = (int)(cnt2 & 0xffffu) + __popc(bal & lt);
+							sts16(lc_a + pos * 2, (unsigned)((itile << 12) | e)); sts64(lm_a + pos * 8, (double)num);
+						}
+						cnt2 += __popc(bal);
+						continue;
 					}
-					const unsigned bal = __ballot_sync(FULLMASK, num != 0);
-					if (num != 0) {
-						const int pos = (int)(cnt2 & 0xffffu) + __popc(bal & lt);
-						sts16(lc_a + pos * 2, (unsigned)((itile << 12) | e)); sts64(lm_a + pos * 8, (double)num);
+					if (!__any_sync(FULLMASK, popi > 0 && (w >> 25) == 0u)) {          /* kind 2 (and the padding) never fires */
+						if (KEEP && e < JD) {
+							if (keep_tm) b.tm[tbase + e] = 0;
+							if (keep_tn) b.tn[tbase + e] = 0;
+						}
+						continue;
 					}
-					cnt2 += __popc(bal);
-					continue;
-				}
-				if (!__any_sync(FULLMASK, popi > 0 && (w >> 25) == 0u)) {          /* kind 2 (and the padding) never fires */
+					double mean = dt * (double)popi * crate[e];
+					if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
+					if (!(popi > 0)) mean = 0;
+					const bool act = (mean != 0);
 					if (KEEP && e < JD) {
-						if (keep_tm) b.tm[tbase + e] = 0;
-						if (keep_tn) b.tn[tbase + e] = 0;
+						if (keep_tm) b.tm[tbase + e] = mean;
+						if (keep_tn && !act) b.tn[tbase + e] = 0;
 					}
-					continue;
+					const bool big = act && (mean >= BEEP_POISSON_INV_MAX) && !(MODE == MODE_MBP && !simu);
+					const unsigned bal = __ballot_sync(FULLMASK, act), balb = __ballot_sync(FULLMASK, big);
+					if (act) {
+						const int pos = big ? top - (int)((cnt2 >> 16) + __popc(balb & lt)) : (int)((cnt2 & 0xffffu) + __popc(bal & ~balb & lt));
+						sts16(lc_a + pos * 2, (unsigned)((itile << 12) | e)); sts64(lm_a + pos * 8, mean);
+					}
+					cnt2 += __popc(bal & ~balb) + (__popc(balb) << 16);
 				}
-				double mean = dt * (double)popi * crate[e];
-				if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
-				if (!(popi > 0)) mean = 0;
-				const bool act = (mean != 0);
-				if (KEEP && e < JD) {
-					if (keep_tm) b.tm[tbase + e] = mean;
-					if (keep_tn && !act) b.tn[tbase + e] = 0;
-				}
-				const bool big = act && (mean >= BEEP_POISSON_INV_MAX) && !(MODE == MODE_MBP && !simu);
-				const unsigned bal = __ballot_sync(FULLMASK, act), balb = __ballot_sync(FULLMASK, big);
-				if (act) {
-					const int pos = big ? top - (int)((cnt2 >> 16) + __popc(balb & lt)) : (int)((cnt2 & 0xffffu) + __popc(bal & ~balb & lt));
-					sts16(lc_a + pos * 2, (unsigned)((itile << 12) | e)); sts64(lm_a + pos * 8, mean);
-				}
-				cnt2 += __popc(bal & ~balb) + (__popc(balb) << 16);
 			}
-		}
-		const int nsmall = (int)(cnt2 & 0xffffu), nbig = (int)(cnt2 >> 16);
-		__syncwarp();
+			const int nsmall = (int)(cnt2 & 0xffffu), nbig = (int)(cnt2 >> 16);
+			__syncwarp();
 
-		/* draws on the pooled list: one cell, one stream (state.cc:624-626 / mbp.cc:286-311) */
-		auto draw = [&](const int cid, const double mean) -> int {
-			const int i = cid >> 12, e = cid & 0xfff;
-			BeepStream rs;
-			beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)(i * JD + e));
-			if (MODE == MODE_SIM) return beep_poisson(&rs, mean);
-			const size_t g = tbase0 + (size_t)(i * JD + e);
-			const int num_i = a.init_tn[g];
-			if (a.simu_mask && a.simu_mask[((size_t)p * T + t) * A + c0 + i]) return beep_poisson(&rs, mean);
-			const double rate_i = a.init_tm[g];
-			if (mean > rate_i) return num_i + beep_poisson(&rs, mean - rate_i);
-			if (mean == rate_i) return num_i;
-			if (num_i == 0) return 0;
-			return beep_binomial(&rs, mean / rate_i, num_i);
-		};
-		/* one settled cell: trajectory store, population update (state.cc:460-485; the last step's events are
-		 * never applied) and the integer event sums of the observations that list the cell (obsmodel.cc:81-97) */
-		auto finish = [&](const int cid, const int num) {
-			const int i = cid >> 12, e = cid & 0xfff;
-			if (MODE != MODE_REPLAY && keep_tn) b.tn[tbase0 + (size_t)(i * JD + e)] = num;
-			if (num != 0) {
-				const unsigned w = lds32(ctab_a + e * 4);
-				const int tr = (w >> 12) & 63, dp = (w >> 18) & 63;
-				if (apply) {
-					const unsigned pa = pop_a + i * (CDp4 * 4);
-					red_shared_add(pa + (a.tfrom[tr] * G + dp) * 4, -num);
-					red_shared_add(pa + (a.tto[tr] * G + dp) * 4, num);
-					dirty |= 1u << i;
-				}
-				if ((m.obs_tr_any >> tr) & 1u) {
-					const int k0 = (int)lds32(ti_a + i * 32 + TI_K0), nent = (int)lds32(ti_a + i * 32 + TI_NENT);
+			/* draws on the pooled list: one cell, one stream (state.cc:624-626 / mbp.cc:286-311) */
+			auto draw = [&](const int cid, const double mean) -> int {
+				const int i = cid >> 12, e = cid & 0xfff;
+				BeepStream rs;
+				beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)(i * JD + e));
+				if (MODE == MODE_SIM) return beep_poisson(&rs, mean);
+				const size_t g = tbase0 + (size_t)(i * JD + e);
+				const int num_i = a.init_tn[g];
+				if (a.simu_mask && a.simu_mask[((size_t)p * T + t) * A + c0 + i]) return beep_poisson(&rs, mean);
+				const double rate_i = a.init_tm[g];
+				if (mean > rate_i) return num_i + beep_poisson(&rs, mean - rate_i);
+				if (mean == rate_i) return num_i;
+				if (num_i == 0) return 0;
+				return beep_binomial(&rs, mean / rate_i, num_i);
+			};
+			/* one settled cell: trajectory store, population update (state.cc:460-485; the last step's events are
+			 * never applied) and the integer event sums of the observations that list the cell (obsmodel.cc:81-97) */
+			auto finish = [&](const int cid, const int num) {
+				const int i = cid >> 12, e = cid & 0xfff;
+				if (MODE != MODE_REPLAY && keep_tn) b.tn[tbase0 + (size_t)(i * JD + e)] = num;
+				if (num != 0) {
+					const unsigned w = lds32(ctab_a + e * 4);
+					const int tr = (w >> 12) & 63, dp = (w >> 18) & 63;
+					if (apply) {
+						const unsigned pa = pop_a + i * (CDp4 * 4);
+						red_shared_add(pa + (a.tfrom[tr] * G + dp) * 4, -num);
+						red_shared_add(pa + (a.tto[tr] * G + dp) * 4, num);
+						dirty |= 1u << i;
+					}
+					if ((m.obs_tr_any >> tr) & 1u) {
+						const int k0 = (int)lds32(ti_a + i * 32 + TI_K0), nent = (int)lds32(ti_a + i * 32 + TI_NENT);
 #pragma unroll 1
-					for (int j = 0; j < nent; j++) {
-						const int ob = m.cell_ent[k0 + j].ob;
-						if (((m.obs_tmask[ob] >> tr) & 1u) && ((m.obs_dmask[ob] >> dp) & 1ull)) red_shared_add(acc_a + (i * CHUNK_NEJ + j) * 4, num);
+						for (int j = 0; j < nent; j++) {
+							const int ob = m.cell_ent[k0 + j].ob;
+							if (((m.obs_tmask[ob] >> tr) & 1u) && ((m.obs_dmask[ob] >> dp) & 1ull)) red_shared_add(acc_a + (i * CHUNK_NEJ + j) * 4, num);
+						}
+					}
+				}
+			};
+			if (MODE == MODE_REPLAY) {
+#pragma unroll 1
+				for (int x = lane; x < nsmall; x += 32) finish((int)lds16(lc_a + x * 2), (int)lds64(lm_a + x * 8));
+			} else {
+#pragma unroll 1
+				for (int x = lane; x < nsmall; x += 32) {
+					const int cid = (int)lds16(lc_a + x * 2);
+					finish(cid, draw(cid, lds64(lm_a + x * 8)));
+				}
+				if (nbig > 0) {
+					/* MODE_SIM only (MBP keeps a single list): first the squeeze of every cell's first attempt; the cells
+					 * it does not settle are collected (over the slots already read) and run the full sampler together */
+					int ndef = 0;
+#pragma unroll 1
+					for (int x0 = 0; x0 < nbig; x0 += 32) {
+						const int x = x0 + lane;
+						bool defer = false;
+						int cid = 0;
+						double mean = 0;
+						if (x < nbig) {
+							cid = (int)lds16(lc_a + (top - x) * 2);
+							mean = lds64(lm_a + (top - x) * 8);
+							BeepStream rs;
+							beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)((cid >> 12) * JD + (cid & 0xfff)));
+							int num;
+							if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num)) finish(cid, num);
+							else defer = true;
+						}
+						const unsigned bd = __ballot_sync(FULLMASK, defer);
+						if (defer) { const int pos = top - (ndef + __popc(bd & lt)); sts16(lc_a + pos * 2, (unsigned)cid); sts64(lm_a + pos * 8, mean); }
+						ndef += __popc(bd);
+					}
+					__syncwarp();
+#pragma unroll 1
+					for (int x = lane; x < ndef; x += 32) {
+						const int cid = (int)lds16(lc_a + (top - x) * 2);
+						finish(cid, draw(cid, lds64(lm_a + (top - x) * 8)));
 					}
 				}
 			}
-		};
-		if (MODE == MODE_REPLAY) {
-#pragma unroll 1
-			for (int x = lane; x < nsmall; x += 32) finish((int)lds16(lc_a + x * 2), (int)lds64(lm_a + x * 8));
-		} else {
-#pragma unroll 1
-			for (int x = lane; x < nsmall; x += 32) {
-				const int cid = (int)lds16(lc_a + x * 2);
-				finish(cid, draw(cid, lds64(lm_a + x * 8)));
-			}
-			if (nbig > 0) {
-				/* MODE_SIM only (MBP keeps a single list): first the squeeze of every cell's first attempt; the cells
-				 * it does not settle are collected (over the slots already read) and run the full sampler together */
-				int ndef = 0;
-#pragma unroll 1
-				for (int x0 = 0; x0 < nbig; x0 += 32) {
-					const int x = x0 + lane;
-					bool defer = false;
-					int cid = 0;
-					double mean = 0;
-					if (x < nbig) {
-						cid = (int)lds16(lc_a + (top - x) * 2);
-						mean = lds64(lm_a + (top - x) * 8);
-						BeepStream rs;
-						beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)((cid >> 12) * JD + (cid & 0xfff)));
-						int num;
-						if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num)) finish(cid, num);
-						else defer = true;
-					}
-					const unsigned bd = __ballot_sync(FULLMASK, defer);
-					if (defer) { const int pos = top - (ndef + __popc(bd & lt)); sts16(lc_a + pos * 2, (unsigned)cid); sts64(lm_a + pos * 8, mean); }
-					ndef += __popc(bd);
-				}
-				__syncwarp();
-#pragma unroll 1
-				for (int x = lane; x < ndef; x += 32) {
-					const int cid = (int)lds16(lc_a + (top - x) * 2);
-					finish(cid, draw(cid, lds64(lm_a + (top - x) * 8)));
-				}
-			}
+			__syncwarp();
+			if (itile >= nt) break;
 		}
-		__syncwarp();
-		if (itile >= nt) break;
 	}
 
 	/* 4a. obsmodel.cc:74-97: the transition observations of the chunk's (sett, area) cells */
@@ -373,15 +386,17 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 		dirty = __reduce_or_sync(FULLMASK, dirty);
 		double *dinf_nxt = b.dinf + ((t + 1) & 1) * dsz + (size_t)p * A * G + (size_t)c0 * G;
 		const int *il = b.inflist + (size_t)p * (m.C + 1);
-		const double *infco = b.infco + (size_t)p * m.C;
 		const int ninf = il[0];
+		const unsigned lu_a = wb + Ls.lu;                   /* free here: (coefficient, byte offset) of the infectious compartments */
+		if (lane < ninf) { const int co = il[1 + lane]; sts64(lu_a + lane * 8, b.infco[(size_t)p * m.C + co]); sts32(lu_a + 64 + lane * 4, (unsigned)(co * G * 4)); }
+		__syncwarp();
 #pragma unroll 1
 		for (int q = lane; q < npair; q += 32) {
 			const int i = (int)(((unsigned)q * invG) >> 16), ag = q - i * G;
 			const unsigned pa = pop_a + i * (CDp4 * 4) + ag * 4;
 			double sum = 0;
-#pragma unroll 1
-			for (int k = 1; k <= ninf; k++) { const int co = il[k]; sum += infco[co] * (double)(int)lds32(pa + co * (G * 4)); }
+#pragma unroll 2
+			for (int k = 0; k < ninf; k++) sum += lds64(lu_a + k * 8) * (double)(int)lds32(pa + lds32(lu_a + 64 + k * 4));
 			dinf_nxt[q] = sum;
 		}
 		const int n16 = CDp4 >> 2;                          /* 16-byte pieces per tile */
@@ -395,7 +410,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 	__syncwarp();
 }
 
-template <int NT> struct ChunkCfg { static constexpr int MINB = (NT <= 4) ? 6 : 4; };
+template <int NT> struct ChunkCfg { static constexpr int MINB = ((NT <= 4) ? 24 : 16) / CHUNK_NWARP; };
 
 template <int MODE, bool KEEP, int NT>
 __global__ void __launch_bounds__(CHUNK_NWARP * 32, ChunkCfg<NT>::MINB) k_traj_chunk(const __grid_constant__ TrajArgs a)
