@@ -233,16 +233,21 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 				const size_t tbase = tbase0 + (size_t)itile * JD;
 				int simu = 0;
 				if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c0 + itile];
+				/* the per-cell rate multipliers come through L1/L2 (the shared-memory carve-out leaves little L1): the
+				 * next pass's value is requested while this pass is worked */
+				double crn = crate[lane];
 #pragma unroll 1
 				for (int e0 = 0; e0 < JD; e0 += 32) {
 					const int e = e0 + lane;
+					const double cr = crn;
+					if (e0 + 32 < JD) crn = crate[e + 32];
 					const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
 					const int popi = (int)lds32(pa + ((w & 0xfffu) << 2));
 					if (MODE == MODE_REPLAY) {
 						/* the events are given (state.cc:294-322); only the means are recomputed */
 						int num = 0;
 						if (e < JD) {
-							double mean = dt * (double)popi * crate[e];
+							double mean = dt * (double)popi * cr;
 							if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
 							if (!(popi > 0)) mean = 0;
 							num = b.tn[tbase + e];
@@ -263,7 +268,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 						}
 						continue;
 					}
-					double mean = dt * (double)popi * crate[e];
+					double mean = dt * (double)popi * cr;
 					if ((w >> 24) == 1u) mean *= lds64(fa + ((w >> 15) & 0x1f8u));
 					if (!(popi > 0)) mean = 0;
 					const bool act = (mean != 0);

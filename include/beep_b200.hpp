@@ -5,6 +5,7 @@
 // mbp.cc:99-133).  These RAII classes are the batched counterparts a driver holds instead:
 //   beep::Engine      <- Details + Data + Model tables on one GPU   (main.cc:125-151)
 //   beep::BatchState  <- vector<State>                              (state.hh:11-133)
+//   beep::Comm        <- Mpi, for the particle plumbing of the hot path (mpi.hh:16-60): one per GPU / rank
 // Errors become exceptions carrying beep_last_error() (the reference exits, utils.cc:296-316).
 #ifndef BEEP_B200_HPP
 #define BEEP_B200_HPP
@@ -120,22 +121,64 @@ inline SwapDecision mc3_swap(const std::vector<uint32_t> &run_all, const std::ve
 	return d;
 }
 
-/// PMCMC::obs_prob (pmcmc.cc:180-207) + bootstrap (:211-268) on one GPU: log marginal likelihood
-/// estimate of the bootstrap particle filter for one parameter vector shared by all particles.
-inline double particle_filter(Engine &eng, BatchState &particles, const std::vector<double> &theta_all, uint64_t seed, double invT = 1.0)
+/// One communicator per GPU / rank (NCCL inside the library, particles move HBM to HBM).  Global particle i lives
+/// on rank i / N, the reference's core = i/N (mpi.cc:98-101).  `id128` are the 128 bytes of an ncclUniqueId written
+/// by Comm::unique_id() on one rank and handed to the others by whatever the host has (MPI_Bcast, a file, ...).
+class Comm {
+public:
+	static std::vector<unsigned char> unique_id() { std::vector<unsigned char> id(128); check(beep_comm_unique_id(id.data())); return id; }
+	Comm(Engine &eng, const std::vector<unsigned char> &id128, int nranks, int rank) { check(beep_comm_create(eng.handle(), id128.data(), nranks, rank, &h_)); }
+	~Comm() { beep_comm_destroy(h_); }
+	Comm(const Comm &) = delete;
+	Comm &operator=(const Comm &) = delete;
+	BeepComm *handle() const { return h_; }
+	int rank() const { return beep_comm_rank(h_); }
+	int size() const { return beep_comm_size(h_); }
+	/// mpi.gather + bcast of per-particle scalars (abcmbp.cc:141, pas.cc:133, pmcmc.cc:219,263, mc3.cc:170-175)
+	std::vector<double> allgather(const std::vector<double> &local)
+	{
+		std::vector<double> all(local.size() * (size_t)size());
+		check(beep_allgather_scalar(h_, local.data(), (int)local.size(), all.data()));
+		return all;
+	}
+	/// Mpi::copy_particles (mpi.cc:81-165): global particle i continues as a copy of partcopy_all[i] (0xFFFFFFFF = keep)
+	void copy_particles(BatchState &batch, const std::vector<uint32_t> &partcopy_all) { check(beep_copy_particles(h_, batch.handle(), partcopy_all.data(), (int)partcopy_all.size())); }
+	/// Mpi::end_sec_swap (mpi.cc:215-327): particle p continues from the section state of backpart_all[p]
+	void end_sec_swap(BatchState &batch, const std::vector<uint32_t> &backpart_all) { check(beep_end_sec_swap(h_, batch.handle(), backpart_all.data(), (int)backpart_all.size())); }
+private:
+	BeepComm *h_ = nullptr;
+};
+
+/// PMCMC::obs_prob (pmcmc.cc:180-207) + bootstrap (:211-268) + Mpi::end_sec_swap (mpi.cc:215-327): log marginal
+/// likelihood estimate of the bootstrap particle filter for one parameter vector shared by all particles.
+/// comm == nullptr: all particles on this GPU.  Otherwise `particles` holds this rank's shard; the weights are
+/// all-gathered, every rank takes the identical resampling decision, only the distinct ancestors that live on
+/// another rank travel; the estimate is identical on every rank.  `ancestry` (optional) receives the ancestor
+/// vector after every section, the argument of beep_particle_sample (Mpi::particle_sample, mpi.cc:331-389).
+inline double particle_filter(Engine &eng, BatchState &particles, const std::vector<double> &theta_all, uint64_t seed, double invT = 1.0,
+                              Comm *comm = nullptr, std::vector<uint32_t> *ancestry = nullptr)
 {
 	particles.set_param(theta_all);
+	const int N = particles.size(), nranks = comm ? comm->size() : 1, rank = comm ? comm->rank() : 0;
 	double loglik = 0;
-	std::vector<uint32_t> back(particles.size());
+	std::vector<uint32_t> back((size_t)N * nranks);
+	std::vector<uint64_t> ids(N);
+	for (int i = 0; i < N; i++) ids[i] = (uint64_t)rank * N + i;          // stream id = global particle index
+	if (ancestry) ancestry->clear();
 	for (int s = 0; s < eng.nsection(); s++) {
 		int ti, tf;
 		eng.section_range(s, ti, tf);
-		if (s > 0) particles.permute(back, BEEP_PERMUTE_SECTION_STATE);
-		particles.simulate(ti, tf, seed);
+		if (s > 0) {
+			if (comm && nranks > 1) comm->end_sec_swap(particles, back);
+			else particles.permute(back, BEEP_PERMUTE_SECTION_STATE);
+		}
+		particles.simulate(ti, tf, seed, s == 0 ? ids.data() : nullptr);
 		std::vector<double> L = particles.obs_loglik(s);
+		if (comm && nranks > 1) L = comm->allgather(L);
 		double inc;
 		check(beep_bootstrap(L.data(), (int)L.size(), invT, seed, s, &inc, back.data()));
 		loglik += inc;
+		if (ancestry) ancestry->insert(ancestry->end(), back.begin(), back.end());
 	}
 	return loglik;
 }

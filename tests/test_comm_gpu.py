@@ -158,3 +158,34 @@ def test_multi_gpu_collectives_equal_one_gpu(name):
             assert res[r]["copy_ok"] and res[r]["mbp_finite"]
         assert res[0]["sample"] == one["sample"], "particle_sample differs from the one-GPU trajectory"
         assert sum(res[r]["swap_bytes"][0] for r in range(world)) == sum(res[r]["swap_bytes"][1] for r in range(world)) > 0
+
+
+def test_cpp_filter_two_ranks(tmp_path):
+    """The C++ host layer over two GPUs (include/beep_b200.hpp: beep::Comm + beep::particle_filter, host/pmcmc_filter.cc,
+    one process per GPU): the same log marginal likelihood, to the last bit, as all particles on one GPU."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from beep_b200.bpk import write_bpk
+    from beep_b200.model import ModelDesc
+    exe = os.path.join(ROOT, "host", "pmcmc_filter")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")])
+    m, d = load_golden("EX_C4")
+    arrays = dict(m.arrays)
+    arrays["stochastic"] = 1
+    out = ModelDesc(arrays).to_prefixed()
+    out["theta"] = np.ascontiguousarray(d["theta"][0], dtype=np.float64)
+    path = str(tmp_path / "model.bpk")
+    write_bpk(path, out)
+    one = subprocess.run([exe, path, "64", "1", "4"], capture_output=True, text=True, timeout=300, env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0"))
+    assert one.returncode == 0, one.stderr
+    idfile = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([exe, path, "64", "1", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                              env=dict(os.environ, WORLD_SIZE="2", RANK=str(r), LOCAL_RANK=str(r), BEEP_NCCL_ID_FILE=idfile)) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    ll1 = one.stdout.split("log-likelihood=")[1].split()[0]
+    ll2 = outs[0][0].split("log-likelihood=")[1].split()[0]
+    assert "ranks=2" in outs[0][0] and ll1 == ll2, (one.stdout, outs[0][0])
