@@ -73,3 +73,32 @@ def test_filter_runs_through_the_adapter():
     ll = [float(ln.split("log-likelihood=")[1].split()[0]) for ln in lines]
     assert all(np.isfinite(ll)) and abs(ll[0] - ll[1]) < 10          # two seeds of the same filter
     assert all(float(ln.split("sampled_events=")[1]) > 0 for ln in lines)
+
+
+def test_abcsmc_england_prior_predictive(tmp_path):
+    """England_AS (BASELINE configs[2]/[3]; obsmodel scale -> normal 10 %, tests/golden/ref_inputs/README.md), the real
+    model shape end to end: generation 0 of ABC-SMC = draws from the prior (the reference's own Model::sample_from_prior
+    in both programs), State::simulate, error function, cut-off at cutoff_frac.  The accepted error functions of the
+    adapter on the engine and of the reference's own run (fixture tests/golden/abcsmc_England_AS.json, 2 000 accepted
+    samples) are two independent samples of ONE distribution: two-sample Kolmogorov-Smirnov below the alpha = 0.001
+    critical distance, and the cut-offs (medians of the prior-predictive error function) agree.  Later generations of
+    the reference are out of reach on England_AS (see tests/golden/make_golden.py)."""
+    from scipy import stats
+    ref = json.load(open(os.path.join(GOLDEN, "abcsmc_England_AS.json")))
+    out = str(tmp_path / "out")
+    _run(["inputfile=COVID 19 England/England_AS.toml", "mode=abcsmc", "nsample=2000", "ngeneration=1", "cutoff_frac=0.5", f"outputdir={out}", "seed=5"], timeout=900)
+    gens = list(csv.DictReader(open(os.path.join(out, "b200_generations.csv"))))
+    cut, ref_cut = float(gens[0]["EFcut"]), ref["EFcut0"]
+    assert abs(cut - ref_cut) <= 2e-5 * ref_cut, (cut, ref_cut)
+    rows = list(csv.DictReader(open(os.path.join(out, "b200_posterior_parameters.csv"))))
+    ef = np.array([float(r["EF"]) for r in rows])
+    ref_ef = np.array(ref["final_EF"])
+    assert ef.size == ref_ef.size == 2000
+    lim = min(cut, ref_cut)                      # both samples truncated at the same point
+    a, b = ef[ef < lim], ref_ef[ref_ef < lim]
+    assert a.size > 1800 and b.size > 1800
+    ks = stats.ks_2samp(a, b)
+    crit = 1.95 * np.sqrt((a.size + b.size) / (a.size * b.size))
+    print(f"England_AS generation 0: cut-off {cut:.2f} vs {ref_cut:.2f}; KS distance {ks.statistic:.4f} (critical {crit:.4f} at alpha = 0.001, p = {ks.pvalue:.3g}); "
+          f"deciles of cut - EF: {np.quantile(lim - a, [0.1, 0.5, 0.9]).round(2)} vs {np.quantile(lim - b, [0.1, 0.5, 0.9]).round(2)}")
+    assert ks.statistic < crit, ks
