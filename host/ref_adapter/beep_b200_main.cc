@@ -14,12 +14,19 @@
 //                 cut-off (:76-79), remove_small_weights (:136-155), terminate on N_eff (:190-206),
 //                 implement_cutoff_frac (:159-186), exchange_samples over the ranks (mpi.cc:169-211) by
 //                 beep_allgather_scalar, normalise_particle_weights (:274-283).
-//   mode=pmcmc    the bootstrap particle filter of PMCMC::obs_prob (pmcmc.cc:180-268) for the model's simulated /
-//                 prior parameter values: sections simulated on the device, weights all-gathered, ancestors moved by
-//                 beep_end_sec_swap, one filtered trajectory drawn by beep_particle_sample (pmcmc.cc:154).
+//   mode=pmcmc    the reference's OWN PMCMC driver -- PMCMC::run (pmcmc.cc:33-110) with its burn-in, its ParamProp
+//                 proposals and adaptation, its outputs -- object code unchanged, with the two members that touch the
+//                 latent state replaced AT LINK TIME (build.sh weakens the two symbols in copies of pmcmc.o / mpi.o):
+//                   PMCMC::obs_prob       pmcmc.cc:180-207  -> the bootstrap particle filter on the device (sections
+//                                         simulated by beep_simulate, section likelihoods, beep_bootstrap, ancestors
+//                                         moved by beep_permute / beep_end_sec_swap)
+//                   Mpi::particle_sample  mpi.cc:331-389    -> beep_particle_sample (backward ancestry walk on the device)
+//                 so every likelihood estimate of the Metropolis-Hastings chain comes from the engine and everything
+//                 else -- acceptance, proposal tuning, trace and posterior files -- is the reference's.
 //
-//   BEEP_RUN=filter with any other mode runs the same filter (BEEP_NPARTICLE particles) on models the reference
-//                 refuses to load in mode=pmcmc (England_AS: observation windows cross its section boundaries).
+//   BEEP_RUN=filter with any mode runs the bare filter (BEEP_NPARTICLE particles, BEEP_FILTER_REPS times, sharded over
+//                 the ranks) -- also on models the reference refuses to load in mode=pmcmc (England_AS: observation
+//                 windows cross its section boundaries).
 //
 // One process per GPU (RANK / WORLD_SIZE / LOCAL_RANK as torchrun or mpirun export them, or rank= nranks= on
 // the command line); the ncclUniqueId travels through a file (BEEP_NCCL_ID_FILE, default /tmp/beep_nccl_id_<port>).
@@ -46,6 +53,9 @@
 #include "model.hh"
 #include "obsmodel.hh"
 #include "mpi.hh"
+#include "state.hh"
+#include "output.hh"
+#include "pmcmc.hh"
 #include "mvn.hh"
 #include "utils.hh"
 #include "timers.hh"
@@ -363,6 +373,93 @@ static void run_filter(const Details &details, const Model &model, Inputs &input
 	(void)obsmodel;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// mode=pmcmc: the reference's PMCMC object on the engine.  The two definitions below replace the reference's own
+// (weak in the linked copies of pmcmc.o / mpi.o, see build.sh); everything else of PMCMC runs as compiled.
+// ---------------------------------------------------------------------------------------------------------
+struct PmcmcEngine {
+	beep::Engine *eng = nullptr;
+	beep::BatchState *part = nullptr;
+	const Ranks *rk = nullptr;
+	const Details *details = nullptr;
+	uint64_t seed = 0, ncall = 0;
+	vector <double> theta;
+	double seconds = 0;
+};
+static PmcmcEngine g_pm;
+
+/// pmcmc.cc:180-207 + bootstrap :211-268 + Mpi::end_sec_swap mpi.cc:215-327
+double PMCMC::obs_prob(vector <double> &paramv)
+{
+	const double t0 = now_s();
+	auto &part = *g_pm.part;
+	const int n = part.size(), nsec = g_pm.eng->nsection();
+	const auto nparam = paramv.size();
+	g_pm.theta.resize((size_t)n*nparam);
+	for(int i = 0; i < n; i++) copy(paramv.begin(),paramv.end(),g_pm.theta.begin()+(size_t)i*nparam);
+	part.set_param(g_pm.theta);
+	const uint64_t seed = g_pm.seed+(++g_pm.ncall);                      // a fresh set of streams per likelihood estimate
+	vector <uint64_t> ids(n); for(int i = 0; i < n; i++) ids[i] = (uint64_t)g_pm.rk->rank*n+i;
+	auto obprob = 0.0;
+	vector <uint32_t> back(Ntot);
+	for(int s = 0; s < nsec; s++){
+		int ti, tf; g_pm.eng->section_range(s,ti,tf);
+		if(s > 0){
+			if(g_pm.rk->comm) beep::check(beep_end_sec_swap(g_pm.rk->comm,part.handle(),back.data(),(int)Ntot));
+			else part.permute(back,BEEP_PERMUTE_SECTION_STATE);
+		}
+		part.simulate(ti,tf,seed,s == 0 ? ids.data() : nullptr);
+		auto Lall = g_pm.rk->allgather(part.obs_loglik(s));                // mpi.gather(L), pmcmc.cc:219
+		double inc;
+		beep::check(beep_bootstrap(Lall.data(),(int)Ntot,invT,seed,s,&inc,back.data()));
+		obprob += inc;
+		for(auto p = 0u; p < Ntot; p++) backpart[s+1][p] = back[p];         // the reference's layout: row sec+1 = ancestors after section sec
+		if(std::isnan(obprob) || std::isinf(obprob)) emsgEC("PMCMC",1);
+	}
+	g_pm.seconds += now_s()-t0;
+	return obprob;
+}
+
+/// mpi.cc:331-389: one filtered trajectory through the ancestry of the LAST obs_prob
+Particle Mpi::particle_sample(const unsigned int ru, const vector < vector <unsigned int> > &backpart, vector <State> &particle, const ObservationModel &obsmodel)
+{
+	const int nsec = (int)obsmodel.nsection, ntot = (int)backpart[0].size();
+	vector <uint32_t> back((size_t)nsec*ntot);
+	for(int s = 0; s < nsec; s++) for(int p = 0; p < ntot; p++) back[(size_t)s*ntot+p] = backpart[s+1][p];
+	const auto &det = *g_pm.details;
+	Particle pa;
+	pa.run = ru; pa.EF = 0;
+	pa.paramval.resize(g_pm.theta.size()/g_pm.part->size());
+	vector <double> tn((size_t)det.ndivision*g_pm.eng->cells_per_step());
+	beep::check(beep_particle_sample(g_pm.rk->comm,g_pm.part->handle(),back.data(),nsec,ntot,pa.paramval.data(),tn.data()));
+	int A = 0, J = 0, D = 0;
+	beep::check(beep_engine_dims(g_pm.eng->handle(),nullptr,&A,nullptr,&J,&D,nullptr,nullptr,nullptr));
+	pa.transnum.resize(det.ndivision);
+	size_t k = 0;
+	for(auto sett = 0u; sett < det.ndivision; sett++){
+		pa.transnum[sett].resize(A);
+		for(int c = 0; c < A; c++){
+			pa.transnum[sett][c].resize(J);
+			for(int tr = 0; tr < J; tr++){ pa.transnum[sett][c][tr].assign(tn.begin()+k,tn.begin()+k+D); k += D;}
+		}
+	}
+	(void)particle;
+	return pa;
+}
+
+static void run_pmcmc(const Details &details, const Data &data, const Model &model, Inputs &inputs, const ObservationModel &obsmodel, Mpi &mpi, beep::Engine &eng, const Ranks &rk)
+{
+	if(rk.nranks != 1) emsgroot("mode=pmcmc through the adapter runs the chain on one rank (the filter itself shards: BEEP_RUN=filter)");
+	Output output(details,data,model,inputs,obsmodel,mpi);
+	PMCMC pmcmc(details,data,model,inputs,output,obsmodel,mpi);          // the reference's object: nparticle, nsample, nburnin, invT from the TOML / command line
+	beep::BatchState part(eng,(int)pmcmc.N,BEEP_KEEP_TRANSNUM);
+	g_pm.eng = &eng; g_pm.part = &part; g_pm.rk = &rk; g_pm.details = &details;
+	g_pm.seed = (uint64_t)inputs.find_integer("seed",0)*1000003ull;
+	const double t0 = now_s();
+	pmcmc.run();
+	cout << "pmcmc on the engine: " << g_pm.ncall << " particle filters of " << pmcmc.Ntot << " particles, " << g_pm.seconds << " s in the filter of " << now_s()-t0 << " s" << endl;
+}
+
 int main(int argc, char **argv)
 {
 	timersinit();
@@ -398,8 +495,8 @@ int main(int argc, char **argv)
 		if(filter_only) run_filter(details,model,inputs,obsmodel,eng,rk);
 		else switch(details.mode){
 		case ABC_SMC: { AbcSmc abc(details,model,inputs,eng,rk); abc.run(); } break;
-		case PMCMC_INF: run_filter(details,model,inputs,obsmodel,eng,rk); break;
-		default: emsgroot("beep_b200_main runs mode=abcsmc and mode=pmcmc (the particle filter)"); break;
+		case PMCMC_INF: run_pmcmc(details,data,model,inputs,obsmodel,mpi,eng,rk); break;
+		default: emsgroot("beep_b200_main runs mode=abcsmc, mode=pmcmc and BEEP_RUN=filter"); break;
 		}
 		if(rk.comm) beep_comm_destroy(rk.comm);
 	}

@@ -16,6 +16,15 @@ mkdir -p "$OUT/obj"
 CXXFLAGS="-O3 -g0 -w -std=c++11 -mfma -I$HERE/mpi_shim -I$REF/toml11 -I$REF/src"
 ls "$REF"/src/*.cc | grep -v -E "indbased_code|runtests|old_code|/main\.cc" | \
   xargs -P "$(nproc)" -I{} sh -c 'f="{}"; b=$(basename "$f" .cc); o="'"$OUT"'/obj/$b.o"; if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then g++ '"$CXXFLAGS"' -c "$f" -o "$o"; fi'
+# mode=pmcmc: the reference's PMCMC driver runs as compiled, with PMCMC::obs_prob (pmcmc.cc:180) and Mpi::particle_sample
+# (mpi.cc:331) supplied by the adapter.  pmcmc.cc is compiled once more as position-independent code (calls to its own
+# global members then go through the symbol instead of being bound or inlined at compile time) and the two symbols are
+# made weak in COPIES of the objects, so the adapter's strong definitions win at link time.  Sources untouched.
+mkdir -p "$OUT/objw"
+g++ $CXXFLAGS -fPIC -fno-inline-functions -c "$REF/src/pmcmc.cc" -o "$OUT/objw/pmcmc.o"
+objcopy --weaken-symbol=_ZN5PMCMC8obs_probERSt6vectorIdSaIdEE "$OUT/objw/pmcmc.o"
+objcopy --weaken-symbol=_ZN3Mpi15particle_sampleEjRKSt6vectorIS0_IjSaIjEESaIS2_EERS0_I5StateSaIS7_EERK16ObservationModel "$OUT/obj/mpi.o" "$OUT/objw/mpi.o"
+OBJS=$(ls "$OUT"/obj/*.o | grep -v -E "/(pmcmc|mpi)\.o$")
 g++ $CXXFLAGS -std=c++14 -I"$ROOT/include" -I"$HERE" -c "$HERE/beep_b200_main.cc" -o "$OUT/beep_b200_main.oo"
-g++ -o "$OUT/BEEP_b200" "$OUT/beep_b200_main.oo" "$OUT"/obj/*.o -L"$ROOT/beep_b200/lib" -lbeep_b200 -Wl,-rpath,'$ORIGIN/../../beep_b200/lib' -lpthread
+g++ -o "$OUT/BEEP_b200" "$OUT/beep_b200_main.oo" $OBJS "$OUT/objw/pmcmc.o" "$OUT/objw/mpi.o" -L"$ROOT/beep_b200/lib" -lbeep_b200 -Wl,-rpath,'$ORIGIN/../../beep_b200/lib' -lpthread
 echo "ref_adapter/build.sh: built $OUT/BEEP_b200"

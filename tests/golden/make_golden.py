@@ -62,6 +62,10 @@ ABCSMC = {"abcsmc_EX_A1": ("examples/EX_A1.toml", 2000, 6),     # ~3 minutes of 
           # simulated, with their error functions.  Later generations are out of reach: at this size the reference's own
           # run does not leave generation 1 (Cholesky of the 170-parameter proposal kernel) within half an hour of CPU.
           "abcsmc_England_AS": ("COVID 19 England/England_AS.toml", 2000, 1)}
+# the reference's own mode=pmcmc (PMCMC::run with its particle filter on the CPU): posterior estimates for the adapter's run
+# of the SAME driver on the engine.  invT is fixed (left unset the reference tunes it during burn-in, and two runs then
+# target different power posteriors).  ~2 minutes of the reference.
+PMCMC_POST = {"pmcmc_EX_A1": ("examples/EX_A1.toml", ["nparticle=32", "nsample=2000", "invT=0.03"])}
 DECISIONS = {"pmcmc": ["mode=pmcmc", "nparticle=24", "nsample=1000"], "abcmbp": ["mode=abcmbp", "nparticle=24", "ngeneration=3"],
              "pas": ["mode=pas", "nparticle=12", "nrun=2", "invT_final=1"], "mc3": ["mode=mc3", "nchain=6", "nrun=2", "invT_final=1", "nsample=1000"]}
 MVN_CASES = {
@@ -209,6 +213,23 @@ def main():
                "final_EF": sorted(ef)}
         json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
         print(f"{name}: {len(gens)} generations, {len(ef)} samples")
+    for name, (toml, args) in PMCMC_POST.items():
+        if only and name not in only:
+            continue
+        import csv
+        import json
+        outdir = os.path.join(work, "out_" + name)
+        cmd = [f"inputfile={toml}", "mode=pmcmc"] + args
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "BEEP")] + cmd + [f"outputdir={outdir}"], cwd=work, capture_output=True, text=True)
+        est = os.path.join(outdir, "Parameter_estimates.csv")
+        if not os.path.exists(est):
+            print(f"{name}: reference run FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        rows = list(csv.DictReader(open(est)))
+        out = {"command": "BEEP " + " ".join(cmd), "parameters": [
+            {"name": x["Name"], "mean": float(x["Mean"]), "sd": float(x["SD"]), "ess": (float(x["ESS"]) if x["ESS"] not in ("---", "") else None), "prior": x["Prior"]} for x in rows]}
+        json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
+        print(f"{name}: {len(rows)} parameters")
     # resampling decisions by the reference's own PMCMC::bootstrap, ABCMBP::EF_cutoff,
     # PAS::bootstrap and MC3::swap_states with ran() injected at link time (oracle/ref/ref_decisions.cc)
     if not only or "decisions" in only:

@@ -8,7 +8,9 @@ cut-offs within 12 %, posterior means within a quarter of the posterior sd, and 
 distance between the final samples' error functions (relative to the cut-off) below 0.1 -- the distance, not the
 p-value: the realised cut-off sequence and proposal kernels differ from run to run of the SAME program, so two
 runs' samples are not draws from one distribution (two seeds of the adapter are compared the same way).
-Needs the prebuilt binary (it travels with the repo)."""
+PMCMC (BASELINE configs[3]'s driver) on EX_A1: the reference's own PMCMC::run with its likelihood estimates coming from
+the engine's particle filter, posterior against the reference's own mode=pmcmc run.  England_AS: generation 0 of
+ABC-SMC against the reference's.  Needs the prebuilt binary (it travels with the repo)."""
 import csv
 import json
 import os
@@ -67,12 +69,40 @@ def test_abcsmc_matches_reference_run(tmp_path):
 
 
 def test_filter_runs_through_the_adapter():
-    out = _run(["inputfile=examples/EX_A1.toml", "mode=pmcmc", "nparticle=512", "nsample=10", "outputdir=/tmp/beep_b200_filter_out"], env={"BEEP_FILTER_REPS": "2"})
+    out = _run(["inputfile=examples/EX_A1.toml", "mode=pmcmc", "nparticle=512", "nsample=10", "outputdir=/tmp/beep_b200_filter_out"],
+               env={"BEEP_RUN": "filter", "BEEP_FILTER_REPS": "2"})
     lines = [ln for ln in out.splitlines() if ln.startswith("filter ")]
     assert len(lines) == 2
     ll = [float(ln.split("log-likelihood=")[1].split()[0]) for ln in lines]
     assert all(np.isfinite(ll)) and abs(ll[0] - ll[1]) < 10          # two seeds of the same filter
     assert all(float(ln.split("sampled_events=")[1]) > 0 for ln in lines)
+
+
+def test_pmcmc_posterior_matches_reference_run(tmp_path):
+    """mode=pmcmc: the reference's OWN PMCMC driver (PMCMC::run, pmcmc.cc:33-110 -- burn-in, ParamProp proposals and their
+    adaptation, Metropolis-Hastings, trace and posterior files, object code unchanged) with PMCMC::obs_prob and
+    Mpi::particle_sample replaced at link time by the engine's particle filter and ancestry walk (host/ref_adapter).
+    Same TOML, nparticle, nsample and fixed invT as the reference's own run behind tests/golden/pmcmc_EX_A1.json:
+    posterior means agree within 4 standard errors (sd / sqrt(ESS), both runs), posterior sds within 35 %."""
+    ref = json.load(open(os.path.join(GOLDEN, "pmcmc_EX_A1.json")))
+    out = str(tmp_path / "out")
+    args = ref["command"].split()[1:]
+    log = _run(args + [f"outputdir={out}"], timeout=900)
+    assert "particle filters of 32 particles" in log
+    rows = {r["Name"]: r for r in csv.DictReader(open(os.path.join(out, "Parameter_estimates.csv")))}
+    msg = []
+    for est in ref["parameters"]:
+        r = rows[est["name"]]
+        mean, sd = float(r["Mean"]), float(r["SD"])
+        if est["sd"] == 0:
+            assert mean == est["mean"]
+            continue
+        ess = float(r["ESS"])
+        se = np.hypot(sd / np.sqrt(ess), est["sd"] / np.sqrt(est["ess"]))
+        msg.append(f"{est['name']}: {mean:.3f} +- {sd:.3f} (ESS {ess:.0f}) vs reference {est['mean']:.3f} +- {est['sd']:.3f} (ESS {est['ess']:.0f})")
+        assert abs(mean - est["mean"]) < 4 * se, msg[-1]
+        assert abs(sd - est["sd"]) < 0.35 * est["sd"], msg[-1]
+    print("; ".join(msg) + "; " + [ln for ln in log.splitlines() if ln.startswith("pmcmc on the engine")][0])
 
 
 def test_abcsmc_england_prior_predictive(tmp_path):
