@@ -110,6 +110,8 @@ struct DevModel {
 	unsigned obs_tr_any;            /* transitions that some observation counts */
 	const unsigned char *cell_npop; /* [T*A] entries of the (sett, area) cell's list that observe a population; they come first */
 	int stochastic, siminf, itr, geo_spline, nR, nefoi, ninf, nmm, ncovar, nlevel, ndir;
+	int ndcc;                       /* demographic changes (data.democat_change, state.cc:339-376) */
+	const int *dcc_info, *dcc_area, *dcc_group; const double *dcc_frac;   /* [ndcc][6] ncat, first area, areas, groups, first dp, first fraction */
 	int nslot, nsection, has_region, has_area_eff, age_fast, M_nnz;
 	int CDp;            /* C*D rounded up to even: tile stride of pop_cur (16-byte async copies) */
 	int mm_packed;      /* every element of the age matrix is hit by at most three spline factors (and nspline < 64) */

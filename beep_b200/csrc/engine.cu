@@ -132,7 +132,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	m.has_region = d->n_region_effect_param > 0; m.has_area_eff = d->n_area_effect_param > 0;
 
 	const int T = m.T, A = m.A, C = m.C, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
-	if (d->n_unsupported > 0) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "the analysis uses democat_change or prediction-mode model modifications, which are outside the hot-path scope"); }
+	if (d->n_unsupported > 0) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "the analysis uses prediction-mode model modifications (state.cc:446-453), which are outside the hot-path scope"); }
 	NEED(T > 0 && A > 0 && C > 0 && J > 0 && D > 0 && G > 0 && S > 0 && Dq > 0 && m.spu > 0 && m.period > 0, "non-positive dimension");
 	NEED(D == S * Dq, "D (%d) != S*Dq (%d*%d)", D, S, Dq);
 	NEED(m.itr >= 0 && m.itr < J, "infection_trans out of range");
@@ -283,6 +283,21 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		}
 	}
 	UP(M_diag, d->M_diag, A); UP(M_factor, d->M_factor, A);
+	{
+		/* demographic changes, state.cc:339-376 (struct.hh:294-304) */
+		NEED(d->n_dcc_info % 6 == 0, "dcc_info must be [ndcc][6]");
+		m.ndcc = (int)(d->n_dcc_info / 6);
+		for (int k = 0; k < m.ndcc; k++) {
+			const int32_t *inf = d->dcc_info + 6 * k;
+			NEED(inf[0] >= 1 && inf[0] <= 32, "democat_change %d: %d categories (1..32)", k, inf[0]);
+			NEED(inf[1] >= 0 && inf[2] >= 0 && (int64_t)inf[1] + inf[2] <= d->n_dcc_area, "democat_change %d: areas out of range", k);
+			NEED(inf[3] >= 0 && inf[4] >= 0 && (int64_t)inf[4] + (int64_t)inf[3] * inf[0] <= d->n_dcc_group, "democat_change %d: groups out of range", k);
+			NEED(inf[5] >= 0 && (int64_t)inf[5] + (int64_t)T * inf[0] <= d->n_dcc_frac, "democat_change %d: fractions must be [T][ncat]", k);
+			for (int i = 0; i < inf[2]; i++) NEED(d->dcc_area[inf[1] + i] >= 0 && d->dcc_area[inf[1] + i] < A, "democat_change %d: area out of range", k);
+			for (int i = 0; i < inf[3] * inf[0]; i++) NEED(d->dcc_group[inf[4] + i] >= 0 && d->dcc_group[inf[4] + i] < D, "democat_change %d: dp out of range", k);
+		}
+		if (m.ndcc) { UP(dcc_info, d->dcc_info, d->n_dcc_info); UP(dcc_area, d->dcc_area, std::max<int64_t>(d->n_dcc_area, 1)); UP(dcc_group, d->dcc_group, std::max<int64_t>(d->n_dcc_group, 1)); UP(dcc_frac, d->dcc_frac, d->n_dcc_frac); }
+	}
 	UP(pop_init, d->pop_init, (size_t)A * C * D);
 	m.CDp = (C * D + 1) & ~1;
 	m.CDp4 = (C * D + 3) & ~3;
@@ -355,7 +370,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		UPV(cell_npop, npop);
 		/* the chunk kernel serves the common model structure (see launch_traj) with integer populations
 		 * and at most CHUNK_NEJ observation entries per (sett, area) cell */
-		eng->chunk_model = npop_fits && max_ent <= CHUNK_NEJ && m.S == 1 && m.Dq == m.G && m.G > 1 && m.stochastic && J * D < 4096 && C * D < 4096;
+		eng->chunk_model = m.ndcc == 0 && npop_fits && max_ent <= CHUNK_NEJ && m.S == 1 && m.Dq == m.G && m.G > 1 && m.stochastic && J * D < 4096 && C * D < 4096;
 		for (int i = 0; i < Dq && eng->chunk_model; i++) if (d->dp_age[i] != i % G) eng->chunk_model = false;
 		for (size_t i = 0; i < (size_t)A * C * D && eng->chunk_model; i++) {
 			const double v = d->pop_init[i];
@@ -458,10 +473,18 @@ static int choose_launch(BeepEngine *eng)
 		else eng->sync_mode = SYNC_GRID;
 	}
 	if (eng->dense_m) eng->sync_mode = SYNC_GRID;           /* one launch per step, between the GEMMs */
-	if (force && !eng->dense_m) {
+	if (force && !eng->dense_m && m.ndcc == 0) {
 		int f = atoi(force);
 		if (f == SYNC_GRID) eng->sync_mode = SYNC_GRID;
 		else if (f == SYNC_CTA && m.M_nnz == 0) { eng->sync_mode = SYNC_CTA; eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A); eng->smem_traj = cta_bytes(eng->nwarp); }
+	}
+	if (m.ndcc > 0 && m.A > 1) {
+		/* a demographic change (state.cc:339-376) sums the population over ITS areas every step: the particle must sit
+		 * in one CTA, whatever the mixing matrix says (and whatever a test forces) */
+		eng->nwarp = std::min(BEEP_TRAJ_NWARP, m.A);
+		if (cta_bytes(eng->nwarp) > 96 * 1024) return fail(BEEP_ERR_UNSUPPORTED, "democat_change over %d areas: the particle does not fit one CTA (%zu B of shared memory)", m.A, cta_bytes(eng->nwarp));
+		eng->sync_mode = SYNC_CTA; eng->smem_traj = cta_bytes(eng->nwarp);
+		eng->dense_m = false;
 	}
 	if (eng->sync_mode == SYNC_GRID) {
 		eng->nwarp = BEEP_TRAJ_NWARP;
@@ -691,7 +714,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.nwarp = eng->nwarp; a.chunk = 1; a.invG = 0; memset(&a.Ls, 0, sizeof a.Ls);
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));
 	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
-	a.fast = (m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
+	a.fast = (m.ndcc == 0 && m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
 	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;

@@ -1172,6 +1172,46 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 }
 
 /* CTA-shared tables at the front of dynamic shared memory */
+/* State::democat_change_pop_adjust, state.cc:339-376, for one particle whose areas all sit in shared memory
+ * (popA[c * CDp + co * D + dp]): the populations of a demographic change's areas are shifted between the categories
+ * of its classification so that their fractions follow the data.  Same loops and the same ORDER of sums as the
+ * reference (the oracle restates them): lane f accumulates category f over (area, group, compartment) in sequence,
+ * the total is summed over f in sequence, then the (area, group, compartment) cells are shifted, `nth` threads of
+ * the caller's group at a time.  scratch: 32 doubles of shared memory visible to the whole group.
+ *   phase 1 is run by the group's first warp; sync() is the group's barrier (__syncwarp / __syncthreads). */
+template <typename SyncFn>
+__device__ __forceinline__ void democat_adjust(const DevModel &m, double *popA, const int CDp, const int t, const int tid, const int nth, double *scratch, SyncFn sync)
+{
+	const int D = m.D, C = m.C;
+#pragma unroll 1
+	for (int k = 0; k < m.ndcc; k++) {
+		const int *inf = m.dcc_info + 6 * k;
+		const int ncat = inf[0], na = inf[2], ng = inf[3];
+		const int *area = m.dcc_area + inf[1], *grp = m.dcc_group + inf[4];
+		if (tid < 32) {
+			double pc = 0;
+			if (tid < ncat)
+				for (int ia = 0; ia < na; ia++) {
+					const double *pa = popA + (size_t)area[ia] * CDp;
+					for (int g = 0; g < ng; g++) { const int dp = grp[g * ncat + tid]; for (int co = 0; co < C; co++) pc += pa[co * D + dp]; }
+				}
+			double tot = 0;
+			for (int f = 0; f < ncat; f++) tot += __shfl_sync(FULLMASK, pc, f);
+			if (tid < ncat) scratch[tid] = m.dcc_frac[inf[5] + (size_t)t * ncat + tid] - pc / tot;
+		}
+		sync();
+		const int nitem = na * ng * C;
+		for (int it = tid; it < nitem; it += nth) {
+			const int ia = it / (ng * C), r = it - ia * (ng * C), g = r / C, co = r - g * C;
+			double *pa = popA + (size_t)area[ia] * CDp + co * D;
+			double sum = 0;
+			for (int f = 0; f < ncat; f++) sum += pa[grp[g * ncat + f]];
+			for (int f = 0; f < ncat; f++) pa[grp[g * ncat + f]] += scratch[f] * sum;
+		}
+		sync();
+	}
+}
+
 __device__ __forceinline__ double *sm_common_init(const DevModel &m, const TrajSm &L, double *smem, TileSm &ts)
 {
 	double *N0R = smem + L.n0;
@@ -1263,6 +1303,12 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 			tile_ctx_area(m.area_info[c], c, tc);
 #pragma unroll 1
 			for (int t = a.ti; t < a.tf; t++) {
+				if (m.ndcc) {
+					/* state.cc:607 / mbp.cc:265 / state.cc:308 (A == 1 here: the launcher puts several areas in one CTA) */
+					democat_adjust(m, pop, CDp, t, lane, 32, ts.ns, [] { __syncwarp(); });
+					for (int i = lane; i < 32 && i < L.JDe; i += 32) ts.ns[i] = 0;
+					__syncwarp();
+				}
 				if (ntw) ntime_refresh(m, tc.ds, t, a.ti, smraw + L.n0, ntw, L.Gs, pop + CDp + L.nbr, lane);
 				tile_step<MODE, KEEP, false, false>(a, tc, t, t / m.spu, lane, ts, dinf + (t & 1) * S * G, dinf + ((t + 1) & 1) * S * G, 1, 0);
 			}
@@ -1287,6 +1333,13 @@ __global__ void __launch_bounds__(BEEP_TRAJ_NWARP * 32, BEEP_TRAJ_MINB) k_traj(c
 #pragma unroll 1
 		for (int t = a.ti; t < a.tf; t++) {
 			const int tday = t / m.spu;
+			if (m.ndcc) {
+				/* state.cc:607 / mbp.cc:265 / state.cc:308: one reduction over the particle's areas, then every thread shifts */
+				double *scr = dinf + BEEP_EVEN(2 * S * A * G) + L.ns;      /* warp 0's mean buffer: idle between steps */
+				democat_adjust(m, popA, CDp, t, (int)threadIdx.x, (int)blockDim.x, scr, [] { __syncthreads(); });
+				if (threadIdx.x < 32 && (int)threadIdx.x < L.JDe) scr[threadIdx.x] = 0;
+				__syncthreads();
+			}
 #pragma unroll 1
 			for (int c = warp; c < A; c += nwarp) {
 				if (fast) tile_step_fast<MODE, KEEP, false, false>(a, p, c, t, tday, lane, wb, pa0 + c * (CDp * 8), ca, dinf, (size_t)(S * A * G), c, ca + L.n0 * 8, m.nmm != 0);

@@ -46,6 +46,10 @@ def _ctypes_fields():
     return out
 
 
+# arrays a description may lack (fixtures written before the feature existed): empty = the analysis does not use it
+OPTIONAL = {"dcc_info", "dcc_area", "dcc_group", "dcc_frac"}
+
+
 class BeepModelDescStruct(ctypes.Structure):
     _fields_ = _ctypes_fields()
 
@@ -58,7 +62,10 @@ class ModelDesc:
         self.c = BeepModelDescStruct()
         for kind, name in FIELDS:
             if name not in arrays:
-                raise KeyError(f"model description lacks field '{name}'")
+                if name not in OPTIONAL:
+                    raise KeyError(f"model description lacks field '{name}'")
+                arrays = dict(arrays)
+                arrays[name] = np.zeros(0)
             v = arrays[name]
             if kind == "I32":
                 val = int(np.asarray(v).reshape(-1)[0])

@@ -43,10 +43,22 @@ static void beep_export_desc(Sink &pk, const Details &details, const Data &data,
 	pk.scalar_i(P+"geo_spline_ref",model.geo_spline_ref);
 	pk.scalar_i(P+"pmcmc_obs_period",details.pmcmc_obs_period);
 	int nunsup = 0;
-	if(data.democat_change.size() > 0) nunsup++;                       // state.cc:339-376 (outside scope)
 	if(details.mode == PREDICTION) nunsup++;                           // modelmod multipliers (outside scope)
 	pk.scalar_i(P+"n_unsupported",nunsup);
 	pk.scalar_d(P+"popsize",data.popsize);
+
+	{ // demographic change, state.cc:339-376
+		vector <int> info, ar, grp; vector <double> fr;
+		for(const auto &dcc : data.democat_change){
+			const int ncat = dcc.frac.size() ? dcc.frac[0].size() : 0;
+			info.push_back(ncat); info.push_back(ar.size()); info.push_back(dcc.area.size());
+			info.push_back(dcc.dp_group.size()); info.push_back(grp.size()); info.push_back(fr.size());
+			for(auto c : dcc.area) ar.push_back(c);
+			for(const auto &g : dcc.dp_group) for(auto dp : g) grp.push_back(dp);
+			for(const auto &f : dcc.frac) for(auto v : f) fr.push_back(v);
+		}
+		pk.i32(P+"dcc_info",info); pk.i32(P+"dcc_area",ar); pk.i32(P+"dcc_group",grp); pk.f64(P+"dcc_frac",fr);
+	}
 
 	{ // Dirichlet groups, model.cc:2685-2695
 		vector <int> off, th; vector <double> frac; off.push_back(0);

@@ -523,6 +523,36 @@ static void update_pop(OracleState *s, int sett)
 		}
 }
 
+/* state.cc:339-376 democat_change_pop_adjust: the population of the areas of a demographic change is shifted between
+ * the categories of its classification so that their fractions follow the data (same loops, same order of sums) */
+static void democat_change_pop_adjust(OracleState *s, int sett)
+{
+	const BeepModelDesc *m = s->m;
+	const int ndcc = (int)(m->n_dcc_info / 6);
+	for (int k = 0; k < ndcc; k++) {
+		const int32_t *inf = m->dcc_info + 6 * k;
+		const int ncat = inf[0], na = inf[2], ng = inf[3];
+		const int32_t *area = m->dcc_area + inf[1], *grp = m->dcc_group + inf[4];
+		const double *frac = m->dcc_frac + inf[5] + (long)sett * ncat;
+		double pop_cat[64], frac_dif[64];
+		for (int f = 0; f < ncat; f++) pop_cat[f] = 0;
+		for (int ia = 0; ia < na; ia++)
+			for (int g = 0; g < ng; g++)
+				for (int co = 0; co < m->C; co++)
+					for (int f = 0; f < ncat; f++) pop_cat[f] += POP(s, sett, area[ia], co, grp[g * ncat + f]);
+		double pop_tot = 0.0;
+		for (int f = 0; f < ncat; f++) pop_tot += pop_cat[f];
+		for (int f = 0; f < ncat; f++) frac_dif[f] = frac[f] - pop_cat[f] / pop_tot;
+		for (int ia = 0; ia < na; ia++)
+			for (int g = 0; g < ng; g++)
+				for (int co = 0; co < m->C; co++) {
+					double sum = 0.0;
+					for (int f = 0; f < ncat; f++) sum += POP(s, sett, area[ia], co, grp[g * ncat + f]);
+					for (int f = 0; f < ncat; f++) POP(s, sett, area[ia], co, grp[g * ncat + f]) += frac_dif[f] * sum;
+				}
+	}
+}
+
 static void pop_init(OracleState *s)
 {
 	const BeepModelDesc *m = s->m;
@@ -543,6 +573,7 @@ int oracle_simulate(OracleState *s, int ti, int tf, uint64_t seed, uint64_t stre
 	beep_stream_init(&seq, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), 0xFFFFFFFFu);
 	if (ti == 0) pop_init(s);
 	for (int sett = ti; sett < tf; sett++) {
+		democat_change_pop_adjust(s, sett);                 /* state.cc:607 */
 		if (sett == ti || s->imap_from_pop) set_I_from_pop(s, sett);
 		else set_Imap_sett(s, sett);
 		for (int c = 0; c < m->A; c++) {
@@ -570,7 +601,7 @@ int oracle_init_from_particle(OracleState *s, const double *transnum)
 	int T = m->T;
 	if (transnum != s->transnum) memcpy(s->transnum, transnum, (size_t)T * m->A * m->J * m->D * sizeof(double));
 	pop_init(s);
-	for (int sett = 0; sett < T; sett++) if (sett < T - 1) update_pop(s, sett);
+	for (int sett = 0; sett < T; sett++) { democat_change_pop_adjust(s, sett); if (sett < T - 1) update_pop(s, sett); }   /* state.cc:307-310 */
 	if (s->imap_from_pop) for (int sett = 0; sett < T; sett++) set_I_from_pop(s, sett);
 	else { /* state.cc:127-160 set_Imap */
 		set_I_from_pop(s, 0);
@@ -625,6 +656,7 @@ int oracle_mbp(const OracleState *init, OracleState *prop, const unsigned char *
 	beep_stream_init(&seq, seed, (uint32_t)stream_id, (uint32_t)(stream_id >> 32), 0xFFFFFFFFu);
 	pop_init(s); /* mbp.cc:414-424 mbp_initialise */
 	for (int sett = 0; sett < T; sett++) {
+		democat_change_pop_adjust(s, sett);                 /* mbp.cc:265 */
 		if (s->imap_from_pop) set_I_from_pop(s, sett);
 		else { /* INF_DIF_UPDATE, state.cc:109-123 set_Imap_using_dI */
 			for (long v = 0; v < nI; v++) {

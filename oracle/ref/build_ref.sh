@@ -14,7 +14,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 REF="${BEEP_REFERENCE:-/root/reference}"
-OUT="$ROOT/oracle/_ref"
+OUT="${BEEP_REF_OUT:-$ROOT/oracle/_ref}"
 OPT="${BEEP_REF_OPT:--O3}"
 if [ ! -d "$REF/src" ]; then echo "build_ref: $REF/src not found (reference absent) - nothing to do"; exit 0; fi
 mkdir -p "$OUT/obj"

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 from beep_b200.bpk import read_bpk  # noqa: E402
 
 REF = os.environ.get("BEEP_REFERENCE", "/root/reference")
-HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+HARNESS = os.environ.get("BEEP_REF_HARNESS") or os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 # name -> (toml relative to the reference root, harness args, ntheta, seed)
 CASES = {
@@ -98,6 +98,30 @@ def convert(bpk_path, out_path):
     return len(out)
 
 
+def write_dcc_inputs(work):
+    ex = os.path.join(REF, "examples")
+    frac = "time,Male,Female\n0,0.5,0.5\n40,0.62,0.38\n90,0.45,0.55\n140,0.3,0.7\n"
+    for name in ("C3", "C2"):
+        ddir = os.path.join(work, "Data_dcc_" + name)
+        shutil.copytree(os.path.join(ex, "Data_EX_" + name), ddir)
+        open(os.path.join(ddir, "sexfrac.csv"), "w").write(frac)
+        txt = open(os.path.join(ex, f"EX_{name}.toml")).read()
+        txt = txt.replace(f'datadir = "examples/Data_EX_{name}"', f'datadir = "Data_dcc_{name}"')
+        txt = txt.replace(f'outputdir = "examples/Output_EX_{name}"', f'outputdir = "Output_dcc_{name}"')
+        if name == "C2":
+            # a second classification for the ten areas: Male / Female counts next to the population column
+            rows = open(os.path.join(ddir, "population.csv")).read().strip().split("\n")
+            out = [rows[0] + ",Male,Female"]
+            for k, r in enumerate(rows[1:]):
+                n = int(r.split(",")[1])
+                male = int(n * (0.44 + 0.01 * k))
+                out.append(f"{r},{male},{n - male}")
+            open(os.path.join(ddir, "population.csv"), "w").write("\n".join(out) + "\n")
+            txt = txt.replace('comps = [', 'democats = [{name="Sex", cats="Male | Female"}]\n\ncomps = [', 1)
+        txt += '\ndemocat_change = [{name="Sex", file="sexfrac.csv"}]\n'
+        open(os.path.join(work, f"dcc_{name}.toml"), "w").write(txt)
+
+
 def main():
     only = sys.argv[1:]
     if not os.path.exists(HARNESS):
@@ -124,11 +148,26 @@ def main():
     CASES["SYN_A12"] = ("synthetic12.toml", ["mode=sim"], 1, 59)
     BIG.add("SYN_A12")
     CASES.update(OBSPATCH)
+    # demographic change (data.democat_change, state.cc:339-376): no input of the reference uses it, so two of its
+    # examples are extended IN THE SCRATCH TREE -- EX_C3 (one area, Sex) and EX_C2 (ten areas, Sex added to its
+    # population file; the change applies to all of them) -- with a table of category fractions over time
+    write_dcc_inputs(work)
+    CASES["DCC_C3"] = ("dcc_C3.toml", ["mode=mcmcmbp", "nsample=10"], 2, 61)
+    CASES["DCC_C2"] = ("dcc_C2.toml", ["mode=mcmcmbp", "nsample=10"], 2, 67)
+    # DCC_C2 comes from the reference's sources compiled -O3 -ffp-contract=off (oracle/_ref/nofma, same recipe, sources
+    # untouched).  With several areas a demographic change couples every area's population to every other's, so in a mixed
+    # SIMU / MBP proposal the means of the MBP areas differ from the initial ones by rounding-level amounts, and whether a
+    # cell consumes a draw from the SEQUENTIAL stream (mbp.cc:286-311: rate_p >, ==, < rate_i) then depends on the last
+    # bit: the reference's own flags (-mfma, contraction on) fuse pop += frac_dif * sum (state.cc:368) where the oracle
+    # rounds twice.  Every other quantity of the fixture agrees with the contracted build to 1e-9 (checked once by hand).
+    nofma = os.path.join(ROOT, "oracle", "_ref", "nofma")
+    if (not only or "DCC_C2" in only) and not os.path.exists(os.path.join(nofma, "ref_harness")):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "ref", "build_ref.sh")], env=dict(os.environ, BEEP_REF_OUT=nofma, BEEP_REF_OPT="-O3 -ffp-contract=off"))
     for name, (toml, args, ntheta, seed) in CASES.items():
         if only and name not in only:
             continue
         bpk = os.path.join(work, name + ".bpk")
-        cmd = [HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
+        cmd = [os.path.join(nofma, "ref_harness") if name == "DCC_C2" else HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
         env = dict(os.environ)
         if name in OBSPATCH:
             env["BEEP_HARNESS_OBSPATCH"] = "1"
@@ -145,7 +184,7 @@ def main():
         if only and name not in only:
             continue
         bpk = os.path.join(work, name + ".bpk")
-        cmd = [HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
+        cmd = [os.path.join(nofma, "ref_harness") if name == "DCC_C2" else HARNESS, bpk, str(ntheta), str(seed), f"inputfile={toml}"] + args
         env = dict(os.environ, BEEP_HARNESS_REPS=str(reps), BEEP_HARNESS_BIG="1")
         r = subprocess.run(cmd, cwd=work, capture_output=True, text=True, env=env)
         if r.returncode != 0 or not os.path.exists(bpk):

@@ -255,7 +255,8 @@ def test_mbp(name, sync):
     ms = _variant(m, stochastic=1)
     eng = _engine(ms, force_sync=sync)
     if sync == 2:
-        assert eng.sync_scope == "GRID"
+        # a demographic change (state.cc:339-376) keeps the particle where its areas can be summed each step, whatever is forced
+        assert eng.sync_scope == ("GRID" if ms.arrays["dcc_info"].size == 0 else ("CTA" if ms.A > 1 else "NONE"))
     P = 4
     th0 = np.repeat(d["theta"][:1], P, axis=0)
     th1 = np.repeat(d["theta"][1:2], P, axis=0)
