@@ -295,7 +295,7 @@ BEEP_HD_COLD int beep_ptrs_accept(double lam, double a, double b, double us, dou
 			lf = (kf + 0.5) * log(kf) - kf + 9.189385332046727417803297364056e-01 +
 			     ik * (8.333333333333333333e-02 + ik2 * (-2.777777777777777778e-03 + ik2 * (7.936507936507936508e-04 + ik2 * -5.952380952380952381e-04)));
 		}
-		const double lhs = log(V) + log(inva) - log(tt);
+		const double lhs = log(V * inva / tt);                /* = log V + log(1/alpha) - log(a/us^2 + b): one logarithm, not three */
 		const double klam = kf * ll;
 		const double rhs = klam - lam - lf;
 		const double scale = fabs(klam) + lam + fabs(lf) + fabs(lhs) + 1.0;
