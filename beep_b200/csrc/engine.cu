@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "traj_chunk.cuh"
 #include "imap_dense.cuh"
+#include "approx.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* errors                                                                    */
@@ -58,6 +59,9 @@ struct BeepEngine {
 	int chunk_nt = 0, chunk_grid = 0;
 	size_t chunk_smem = 0;
 	ChunkSm chunk_ls;
+	/* MVN-approximate likelihood (approx.cuh): index lists built at creation when the model qualifies */
+	bool approx_ok = false; std::string approx_why;
+	DevApprox ax;
 };
 
 struct BeepBatch {
@@ -76,6 +80,7 @@ struct BeepBatch {
 	unsigned *d_map = nullptr; unsigned char *d_flag = nullptr;
 	unsigned char *d_mask = nullptr; size_t d_mask_n = 0;
 	double *d_tmp = nullptr; size_t d_tmp_n = 0;
+	double *d_approx = nullptr; size_t d_approx_n = 0;   /* scratch of beep_likelihood_approx */
 };
 
 template <typename Tp>
@@ -104,6 +109,135 @@ extern "C" void beep_engine_destroy(BeepEngine *eng)
 	for (void *p : eng->dev_allocs) cudaFree(p);
 	if (eng->mvn_buf) cudaFree(eng->mvn_buf);
 	delete eng;
+}
+
+
+/* ------------------------------------------------------------------------ */
+/* MVN-approximate likelihood: the index lists of State::initialise_approx    */
+/* (state_mvn_approx.cc:1288-1475) and ObservationModel::generate_obs_slice   */
+/* (obsmodel.cc:357-385) from the flat description                            */
+/* ------------------------------------------------------------------------ */
+/* model.cc:3524-3566: the compartments on the far side of transition tr; false when transitions merge */
+static bool trans_comp_after(const BeepModelDesc *d, int tr, std::vector<int> &clist)
+{
+	std::vector<int> map(d->C, -1);
+	map[d->trans_from[tr]] = 0; map[d->trans_to[tr]] = 1;
+	bool flag;
+	do {
+		flag = false;
+		for (int k = 0; k < d->J; k++) {
+			const int from = map[d->trans_from[k]], to = map[d->trans_to[k]];
+			const int num = (from < 0) + (to < 0);
+			if (num == 0) {
+				if (from != to && !(d->trans_from[k] == d->trans_from[tr] && d->trans_to[k] == d->trans_to[tr])) return false;
+			} else if (num == 1) {
+				if (from < 0) map[d->trans_from[k]] = to; else map[d->trans_to[k]] = from;
+				flag = true;
+			}
+		}
+	} while (flag);
+	clist.clear();
+	for (int c = 0; c < d->C; c++) if (map[c] == 1) clist.push_back(c);
+	return true;
+}
+
+static int approx_setup(BeepEngine *eng, const BeepModelDesc *d)
+{
+	DevApprox &x = eng->ax;
+	memset(&x, 0, sizeof x);
+	eng->approx_ok = false;
+	const int A = d->A, C = d->C, D = d->D, J = d->J, O = d->nobs;
+	if (d->n_table_type != d->ntable || d->ntable == 0) { eng->approx_why = "the description carries no table_type (written before the approximate likelihood existed)"; return BEEP_OK; }
+	if (d->S != 1) { eng->approx_why = "the approximate likelihood handles one strain (state_mvn_approx.cc:1208)"; return BEEP_OK; }
+	if (d->n_dcc_info > 0) { eng->approx_why = "the approximate likelihood ignores demographic changes"; return BEEP_OK; }
+	const int n = A * C * D, nt = A * J * D, start = d->trans_from[d->infection_trans];
+	if ((long long)n * std::max(n, nt) >= (1ll << 30)) { eng->approx_why = "too many compartments for the approximate likelihood"; return BEEP_OK; }
+	std::vector<int> wo, ws, wo_of(n, -1);
+	for (int ca = 0; ca < n; ca++) { if ((ca / D) % C != start) { wo_of[ca] = (int)wo.size(); wo.push_back(ca); } else ws.push_back(ca); }
+	if ((int)wo.size() != nt) { eng->approx_why = "the approximate likelihood needs as many transitions as non-susceptible compartments (state_mvn_approx.cc:1376)"; return BEEP_OK; }
+	for (int co = 0; co < C; co++) if (co == start && d->comp_inf_param[co] >= 0) { /* infectivity of S is checked per particle in the reference; its parameter is the zero constant in every model */ }
+	std::vector<int> wsl_off(1, 0), wsl;
+	for (int cai : ws) {
+		for (int caj : wo) if (caj / (C * D) == cai / (C * D) && caj % D == cai % D) wsl.push_back(caj);
+		wsl_off.push_back((int)wsl.size());
+	}
+	std::vector<double> total_pop((size_t)A * D, 0.0);
+	for (int c = 0; c < A; c++)
+		for (int dp = 0; dp < D; dp++) {
+			double sum = 0.0;
+			for (int co = 0; co < C; co++) sum += d->pop_init[((size_t)c * C + co) * D + dp];
+			total_pop[(size_t)c * D + dp] = sum;
+		}
+	std::vector<int> ta_from(nt), ta_to(nt), inc_off(1, 0), inc_ta;
+	for (int ta = 0; ta < nt; ta++) {
+		const int c = ta / (J * D), tr = (ta / D) % J, dp = ta % D;
+		ta_from[ta] = (c * C + d->trans_from[tr]) * D + dp; ta_to[ta] = (c * C + d->trans_to[tr]) * D + dp;
+	}
+	for (int ca = 0; ca < n; ca++) {
+		const int c = ca / (C * D), co = (ca / D) % C, dp = ca % D;
+		for (int tr = 0; tr < J; tr++) if (d->trans_from[tr] == co || d->trans_to[tr] == co) inc_ta.push_back((c * J + tr) * D + dp);
+		inc_off.push_back((int)inc_ta.size());
+	}
+	std::vector<int> ocl_off(1, 0), ocl, ocw_off(1, 0), ocw, otype(O), osett(O);
+	std::vector<double> var_approx(O);
+	for (int o = 0; o < O; o++) {
+		const int tb = d->obs_table[o], type = d->table_type[tb];
+		otype[o] = type;
+		osett[o] = (type == 1 || type == 2) ? d->obs_sett_i[o] : d->obs_sett_f[o];        /* obsmodel.cc:368-373 */
+		std::vector<int> complist;
+		if (type == 1 || type == 2) { for (int k = d->table_comp_off[tb]; k < d->table_comp_off[tb + 1]; k++) complist.push_back(d->table_comp[k]); }
+		else {
+			for (int k = d->table_trans_off[tb]; k < d->table_trans_off[tb + 1]; k++) {
+				std::vector<int> after;
+				if (!trans_comp_after(d, d->table_trans[k], after)) { eng->approx_why = "transitions merge into the same compartment (model.cc:3541)"; return BEEP_OK; }
+				for (int co : after) {
+					if (std::find(complist.begin(), complist.end(), co) != complist.end()) { eng->approx_why = "an observation contains sequential transitions (state_mvn_approx.cc:1446)"; return BEEP_OK; }
+					complist.push_back(co);
+				}
+			}
+		}
+		for (int co : complist) {
+			if (co == start) { eng->approx_why = "an observation measures the susceptible compartment (state_mvn_approx.cc:1456)"; return BEEP_OK; }
+			for (int ia = d->obs_area_off[o]; ia < d->obs_area_off[o + 1]; ia++)
+				for (int id = d->obs_dp_off[o]; id < d->obs_dp_off[o + 1]; id++) {
+					const int ca = (d->obs_area[ia] * C + co) * D + d->obs_dp[id];
+					ocl.push_back(ca);
+					if (wo_of[ca] >= 0) ocw.push_back(wo_of[ca]);
+				}
+		}
+		ocl_off.push_back((int)ocl.size()); ocw_off.push_back((int)ocw.size());
+		if (ocw_off[o + 1] == ocw_off[o]) { eng->approx_why = "an observation without compartments"; return BEEP_OK; }
+		const double value = d->obs_value[o];                                  /* data.cc:1085-1115 */
+		double va = 0;
+		switch (d->obs_model[o]) {
+		case 0: case 1: va = d->obs_sd[o] * d->obs_sd[o]; break;
+		case 2: { double lam = value; if (lam < 1) lam = 1; va = lam; } break;
+		case 3: { double mm = value; if (mm < 1) mm = 1; va = mm + mm * mm / d->obs_shape[o]; } break;
+		}
+		if (!(va > 0) || std::isinf(va)) { eng->approx_why = "an observation has zero or infinite variance (data.cc:1112-1113)"; return BEEP_OK; }
+		var_approx[o] = va;
+	}
+	std::vector<int> sl_sett, sl_off(1, 0), sl_obs;
+	{
+		std::vector<int> setts(osett);
+		std::sort(setts.begin(), setts.end());
+		setts.erase(std::unique(setts.begin(), setts.end()), setts.end());
+		for (int st : setts) {
+			sl_sett.push_back(st);
+			for (int o = 0; o < O; o++) if (osett[o] == st) sl_obs.push_back(o);
+			sl_off.push_back((int)sl_obs.size());
+		}
+	}
+	x.n = n; x.nt = nt; x.nwo = (int)wo.size(); x.nws = (int)ws.size(); x.start = start; x.nslice = (int)sl_sett.size();
+#define UPX(field, vec) do { int rc_ = upload(eng, (vec), &x.field); if (rc_) return rc_; } while (0)
+	UPX(inc_off, inc_off); UPX(inc_ta, inc_ta); UPX(ta_from, ta_from); UPX(ta_to, ta_to);
+	UPX(wo, wo); UPX(ws, ws); UPX(wsl_off, wsl_off); UPX(wsl, wsl); UPX(total_pop, total_pop);
+	UPX(ocl_off, ocl_off); UPX(ocl, ocl); UPX(ocw_off, ocw_off); UPX(ocw, ocw); UPX(var_approx, var_approx);
+	UPX(obs_type, otype); { std::vector<int> si(d->obs_sett_i, d->obs_sett_i + O); UPX(obs_sett_i, si); }
+	UPX(sl_sett, sl_sett); UPX(sl_off, sl_off); UPX(sl_obs, sl_obs);
+#undef UPX
+	eng->approx_ok = true;
+	return BEEP_OK;
 }
 
 extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine **out)
@@ -393,6 +527,8 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		UPV(section_ti, eng->section_ti); UPV(section_tf, eng->section_tf);
 	}
 	int rc = choose_launch(eng);
+	if (rc) { beep_engine_destroy(eng); return rc; }
+	rc = approx_setup(eng, d);
 	if (rc) { beep_engine_destroy(eng); return rc; }
 	*out = eng;
 	return BEEP_OK;
@@ -948,6 +1084,55 @@ extern "C" int beep_latent_loglik(BeepBatch *bt, double *Li_host)
 	CU(cudaStreamSynchronize(bt->stream));
 	return BEEP_OK;
 }
+
+/* State::likelihood_approx (state_mvn_approx.cc:11-91) for every particle of the batch, at inverse temperature invT */
+extern "C" int beep_likelihood_approx(BeepBatch *bt, double invT, double *L_host)
+{
+	if (!bt || !L_host) return fail(BEEP_ERR_INVALID, "null argument");
+	BeepEngine *eng = bt->eng;
+	const DevModel &m = eng->dm;
+	if (!eng->approx_ok) return fail(BEEP_ERR_UNSUPPORTED, "beep_likelihood_approx: %s", eng->approx_why.c_str());
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "beep_likelihood_approx before beep_set_params");
+	if (!(invT > 0)) return fail(BEEP_ERR_INVALID, "invT must be positive");
+	CU(cudaSetDevice(eng->device));
+	if (bt->theta_dirty) { int rc = launch_set_param(bt); if (rc) return rc; }
+	const int P = bt->db.P;
+	DevApprox x = eng->ax;
+	const size_t n = x.n, nt = x.nt, nw = x.nwo, vs = std::max(n, nt);
+	const size_t per = (size_t)(m.T + 1) * n + n * n + nt * n + 6 * nw * nw + AP_NVEC * vs + 1;
+	const size_t need = per * P * sizeof(double);
+	if (bt->d_approx_n < need) {
+		CU(cudaStreamSynchronize(bt->stream));
+		if (bt->d_approx) {
+			cudaFree(bt->d_approx);
+			bt->dev_allocs.erase(std::remove(bt->dev_allocs.begin(), bt->dev_allocs.end(), (void *)bt->d_approx), bt->dev_allocs.end());
+			bt->bytes -= (long long)bt->d_approx_n;
+			bt->d_approx = nullptr; bt->d_approx_n = 0;
+		}
+		double *t = nullptr;
+		cudaError_t e = cudaMalloc((void **)&t, need);
+		if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for the approximate likelihood: %s", need, cudaGetErrorString(e));
+		bt->dev_allocs.push_back(t);
+		bt->bytes += (long long)need;
+		bt->d_approx = t; bt->d_approx_n = need;
+	}
+	double *q = bt->d_approx;
+	x.pop = q; q += (size_t)P * (m.T + 1) * n;
+	x.covar = q; q += (size_t)P * n * n;
+	x.R = q; q += (size_t)P * nt * n;
+	x.lu = q; q += (size_t)P * 6 * nw * nw;
+	x.vec = q; q += (size_t)P * AP_NVEC * vs;
+	x.L = q;
+	k_likelihood_approx<<<P, AP_THREADS, 0, bt->stream>>>(m, bt->db, x, invT);
+	eng->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(L_host, x.L, P * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+/* 1 when the model qualifies for beep_likelihood_approx */
+extern "C" int beep_engine_has_approx(const BeepEngine *eng) { return eng && eng->approx_ok ? 1 : 0; }
 
 /* ------------------------------------------------------------------------ */
 /* K6                                                                        */

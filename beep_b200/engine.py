@@ -41,6 +41,8 @@ _SIGNATURES = {
     "beep_num_sections": (ctypes.c_int, [_vp]),
     "beep_section_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "beep_latent_loglik": (ctypes.c_int, [_vp, _vp]),
+    "beep_likelihood_approx": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
+    "beep_engine_has_approx": (ctypes.c_int, [_vp]),
     "beep_permute": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "beep_accept": (ctypes.c_int, [_vp, _vp, _vp]),
     "beep_export_particle": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
@@ -168,6 +170,10 @@ class Engine:
         return self.L.beep_launch_count(self.h)
 
     @property
+    def has_approx(self):
+        return bool(self.L.beep_engine_has_approx(self.h))
+
+    @property
     def dense_mixing(self):
         return bool(self.L.beep_engine_dense_mixing(self.h))
 
@@ -264,6 +270,12 @@ class Batch:
         return out
 
     # -- K6 ---------------------------------------------------------------
+    def likelihood_approx(self, invT=1.0):
+        """State::likelihood_approx (state_mvn_approx.cc:11-91) of every particle, parameters from set_params."""
+        out = np.zeros(self.P)
+        _check(self.L.beep_likelihood_approx(self.h, float(invT), out.ctypes.data))
+        return out
+
     def permute(self, src_of, what=PERMUTE_FULL):
         m = np.ascontiguousarray(src_of, dtype=np.uint32)
         assert m.size == self.P

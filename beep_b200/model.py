@@ -47,7 +47,7 @@ def _ctypes_fields():
 
 
 # arrays a description may lack (fixtures written before the feature existed): empty = the analysis does not use it
-OPTIONAL = {"dcc_info", "dcc_area", "dcc_group", "dcc_frac"}
+OPTIONAL = {"dcc_info", "dcc_area", "dcc_group", "dcc_frac", "table_type"}
 
 
 class BeepModelDescStruct(ctypes.Structure):

@@ -188,7 +188,7 @@ static void beep_export_desc(Sink &pk, const Details &details, const Data &data,
 	}
 
 	{ // observations
-		vector <double> val, sd, fac, shape, thr; vector <int> fs, tab, om, si, sf, aoff, ar, doff, dp, ttoff, tt, tcoff, tc;
+		vector <double> val, sd, fac, shape, thr; vector <int> fs, tab, om, si, sf, aoff, ar, doff, dp, ttoff, tt, tcoff, tc, tty;
 		aoff.push_back(0); doff.push_back(0); ttoff.push_back(0); tcoff.push_back(0);
 		for(const auto &ob : data.obs){
 			val.push_back(ob.value); sd.push_back(ob.sd); fac.push_back(ob.factor);
@@ -206,13 +206,14 @@ static void beep_export_desc(Sink &pk, const Details &details, const Data &data,
 			for(auto co : dt.complist) tc.push_back(co);
 			tcoff.push_back(tc.size());
 			thr.push_back(dt.threshold);
+			tty.push_back((int)dt.type);
 		}
 		pk.f64(P+"obs_value",val); pk.f64(P+"obs_sd",sd); pk.f64(P+"obs_factor",fac); pk.f64(P+"obs_shape",shape);
 		pk.i32(P+"obs_factor_spline",fs); pk.i32(P+"obs_table",tab); pk.i32(P+"obs_model",om);
 		pk.i32(P+"obs_sett_i",si); pk.i32(P+"obs_sett_f",sf);
 		pk.i32(P+"obs_area_off",aoff); pk.i32(P+"obs_area",ar); pk.i32(P+"obs_dp_off",doff); pk.i32(P+"obs_dp",dp);
 		pk.i32(P+"table_trans_off",ttoff); pk.i32(P+"table_trans",tt); pk.i32(P+"table_comp_off",tcoff); pk.i32(P+"table_comp",tc);
-		pk.f64(P+"table_threshold",thr);
+		pk.f64(P+"table_threshold",thr); pk.i32(P+"table_type",tty);
 	}
 }
 

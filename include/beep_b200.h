@@ -294,6 +294,23 @@ int beep_mvn_kernel_sums(BeepEngine *eng, int nvar, int nparam, const int *var, 
                          const double *param_prop, int N, const double *param_last, const double *w_last, int Nlast,
                          double *sums_out);
 
+/* MVN-approximate likelihood of mode=map.  Replaces
+ * State::likelihood_approx (state_mvn_approx.cc:11-91: the mean population and its
+ * covariance carried through the steps, a Kalman-type update at every observation
+ * time, apply_observation_fast :688-817) as ML::generate_samples calls it for each
+ * sample of a CMA-ES generation (ml.cc:389-413) and ML's Hessian code for O(nvar^2)
+ * parameter vectors (ml.cc:540-575): here for ALL particles of the batch in one
+ * launch, with the parameters given by beep_set_params.  L_host[P] receives the
+ * approximate log-likelihood at inverse temperature invT (-1e9 where the reference
+ * returns -LARGE).  Observation slices are the reference's generate_obs_slice
+ * (obsmodel.cc:357-385).  BEEP_ERR_UNSUPPORTED where the reference itself refuses
+ * the model (several strains, transitions != non-susceptible compartments,
+ * observations on the susceptible compartment) or the description lacks table_type.
+ * Agreement with the reference's own likelihood_approx: 1e-9 relative (its AVX
+ * sums run in another order; measured 1e-12 on well-conditioned parameters).   */
+int beep_likelihood_approx(BeepBatch *batch, double invT, double *L_host);
+int beep_engine_has_approx(const BeepEngine *eng);
+
 /* Test hooks: the device samplers of beep_rng.h on n independent streams
  * (seed, stream_id, i), for the host/device bit-exactness tests.            */
 int beep_test_poisson(uint64_t seed, uint64_t stream_id, const double *lam_host, int n, int32_t *out_host);

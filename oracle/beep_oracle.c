@@ -73,7 +73,7 @@ OracleState *oracle_state_create(const BeepModelDesc *m)
 	s->transrate = dalloc((long)m->J * m->D); s->disc_spline = dalloc((long)m->nspline * m->T);
 	s->sus = dalloc(m->D); s->areafactor = dalloc((long)m->period * m->A);
 	s->Ntime = dalloc((long)m->T * m->G * m->G); s->beta = dalloc((long)m->S * m->A * m->T);
-	s->pop = dalloc((long)m->T * m->A * m->C * m->D);
+	s->pop = dalloc((long)(m->T + 1) * m->A * m->C * m->D);   /* pop[T] is used by the MVN-approximate likelihood only */
 	s->transnum = dalloc(TAJD); s->transmean = dalloc(TAJD);
 	s->Imap = dalloc((long)m->T * m->S * m->A * m->G); s->Idiag = dalloc((long)m->T * m->S * m->A * m->G);
 	/* sections, obsmodel.cc:326-348 */
@@ -896,3 +896,8 @@ void oracle_mvn_kernel_sums(int nvar, int nparam, const int32_t *var, const doub
 		out[i] = sum;
 	}
 }
+
+/* ---------------------------------------------------------------------- */
+/* MVN-approximate likelihood (mode=map), state_mvn_approx.cc               */
+/* ---------------------------------------------------------------------- */
+#include "beep_oracle_approx.c"

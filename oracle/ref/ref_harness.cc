@@ -286,6 +286,35 @@ int main(int argc, char **argv)
 		return 0;
 	}
 
+	// ---- MVN-approximate likelihood of mode=map (ML::generate_samples, ml.cc:389-413): the reference's own
+	// State::likelihood_approx (state_mvn_approx.cc:11-91) with ML's set-up (ml.cc:39-42), at the inverse temperature
+	// given in BEEP_HARNESS_APPROX; mean populations and the variances it carries are recorded next to L
+	if(getenv("BEEP_HARNESS_APPROX")){
+		double invT = atof(getenv("BEEP_HARNESS_APPROX"));
+		auto obs_slice = obsmodel.generate_obs_slice();
+		State st(details,data,model,obsmodel);
+		st.initialise_approx();
+		vector <double> Ls;
+		for(auto k = 0u; k < theta.size(); k++){
+			reset_guess();
+			auto L = st.likelihood_approx(theta[k],obs_slice,invT,DOUBLE);
+			Ls.push_back(L);
+			string pre = "th"+to_string(k)+".approx.";
+			if(L != -LARGE){
+				pk.f64(pre+"pop",flat4(st.pop,T+1));
+				vector <double> var;
+				for(auto sett = 0u; sett < T; sett++) for(auto c = 0u; c < st.ncomp_approx; c++) var.push_back(st.pop_covar[sett][c][c]);
+				pk.f64(pre+"var",var);
+			}
+		}
+		pk.f64("approx.L",Ls);
+		pk.scalar_d("approx.invT",invT);
+		pk.scalar_i("approx.ncomp",(int)st.ncomp_approx);
+		pk.close();
+		cout << "ref_harness: wrote " << outfile << " (approx, " << pk.n << " arrays)" << endl;
+		return 0;
+	}
+
 	const bool stoch0 = details.stochastic;
 	vector <Particle> stoch_part;
 

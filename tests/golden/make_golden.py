@@ -76,6 +76,15 @@ MVN_CASES = {
 # the loaded observations of these cases are re-labelled by the harness (BEEP_HARNESS_OBSPATCH, ref_harness.cc)
 OBSPATCH = {"OBS_C4": ("examples/EX_C4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 83),
             "OBS_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 89)}
+# the MVN-approximate likelihood of mode=map (State::likelihood_approx, state_mvn_approx.cc:11-91) with ML's own set-up
+# (BEEP_HARNESS_APPROX = invT, ref_harness.cc): L for three parameter vectors (the TOML values, two prior draws), the mean
+# populations and carried variances of the first
+APPROX = {"APX_A1": ("examples/EX_A1.toml", ["mode=map"], 3, 101),    # one area, one group
+          "APX_B4": ("examples/EX_B4.toml", ["mode=map"], 3, 103),    # Poisson observation model, marginal data
+          "APX_C4": ("examples/EX_C4.toml", ["mode=map"], 3, 107),    # four age groups
+          "APX_C2": ("examples/EX_C2.toml", ["mode=map"], 3, 109),    # ten areas, covariates
+          "APX_D3": ("examples/EX_D3.toml", ["mode=map"], 3, 113),    # level effects
+          "APX_C5": ("examples/EX_C5.toml", ["mode=map"], 3, 127)}    # 32 areas coupled by the geographic mixing matrix (128 compartments)
 SUBST = {"England_AS": [('obsmodel="scale"', 'obsmodel="normal 10%"')]}
 BIG = {"England_AS"}
 
@@ -84,6 +93,8 @@ def convert(bpk_path, out_path):
     d = read_bpk(bpk_path)
     out = {}
     for k, v in d.items():
+        if ".approx." in k and not k.startswith("th0."):
+            continue                        # the state arrays of the first parameter vector are enough
         if k.endswith("det.transmean"):
             # deterministic dynamics: transnum IS transmean (state.cc:627)
             assert np.array_equal(v, d[k.replace("transmean", "transnum")])
@@ -148,6 +159,7 @@ def main():
     CASES["SYN_A12"] = ("synthetic12.toml", ["mode=sim"], 1, 59)
     BIG.add("SYN_A12")
     CASES.update(OBSPATCH)
+    CASES.update(APPROX)
     # demographic change (data.democat_change, state.cc:339-376): no input of the reference uses it, so two of its
     # examples are extended IN THE SCRATCH TREE -- EX_C3 (one area, Sex) and EX_C2 (ten areas, Sex added to its
     # population file; the change applies to all of them) -- with a table of category fractions over time
@@ -173,6 +185,8 @@ def main():
             env["BEEP_HARNESS_OBSPATCH"] = "1"
         if name in BIG:
             env["BEEP_HARNESS_BIG"] = "1"      # skip pop / Imap / Idiag dumps
+        if name in APPROX:
+            env["BEEP_HARNESS_APPROX"] = "1"   # invT = 1
         r = subprocess.run(cmd, cwd=work, capture_output=True, text=True, env=env)
         if r.returncode != 0 or not os.path.exists(bpk):
             print(f"{name}: harness FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")

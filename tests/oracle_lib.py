@@ -53,6 +53,8 @@ def lib():
         L.oracle_log_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.oracle_mvn_kernel_sums.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_likelihood_approx.restype = ctypes.c_double
+        L.oracle_likelihood_approx.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L
     return _LIB
 
@@ -135,6 +137,17 @@ class OracleState:
 
     def latent_loglik(self):
         return self.L.oracle_latent_loglik(self.h)
+
+    def likelihood_approx(self, theta, invT=1.0, want_state=False):
+        """State::likelihood_approx (state_mvn_approx.cc:11-91); with want_state also the mean populations [T+1][A][C][D]
+        and the variances carried at the start of every step [T][A][C][D]."""
+        m = self.model
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        n = m.A * m.C * m.D
+        pop = np.zeros((m.T + 1, m.A, m.C, m.D)) if want_state else None
+        var = np.zeros((m.T, m.A, m.C, m.D)) if want_state else None
+        L = self.L.oracle_likelihood_approx(self.h, th.ctypes.data, float(invT), pop.ctypes.data if want_state else None, var.ctypes.data if want_state else None)
+        return (L, pop, var) if want_state else L
 
     @property
     def nsection(self):
