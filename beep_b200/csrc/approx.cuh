@@ -15,13 +15,15 @@
  * inversions.  ML::generate_samples (ml.cc:389-413) evaluates it for every sample of a CMA-ES generation, and the
  * Hessian code (ml.cc:540-575) for O(nvar^2) parameter vectors: that loop is the batch dimension here.
  *
- * Mapping: ONE CTA PER PARTICLE, the whole time loop inside the kernel (no launch per step); the particle's
- * covariance, the product R = J covar and the LU factors live in a per-particle scratch in HBM that the CTA
- * re-reads through L1/L2 (n <= a few hundred: tens to hundreds of KB); every phase is a block-wide pass over
- * n x n (or transitions x n) outputs with unit-stride lanes, separated by __syncthreads.  The Jacobian is never
- * formed: its few non-zeros per row are recomputed from the step's tables while R is accumulated (ascending
- * compartment index = the reference's order of sums).  Sums that the reference does sequentially are sequential
- * here too (one thread per output), so results agree with the CPU restatement to rounding.
+ * Mapping: ONE CTA PER PARTICLE (one to eight warps, by the size of the covariance), the whole time loop inside
+ * the kernel (no launch per step).  The step vectors, and the covariance with the product R = J covar when they
+ * leave room for several CTAs per SM, live in shared memory; otherwise (and for the LU factors and the mean
+ * populations of all steps) in a per-particle scratch in HBM that the CTA re-reads through L1/L2.  Every phase is a
+ * block-wide pass over (row, column) outputs -- a row per group of lanes, unit-stride columns, no index divisions --
+ * separated by __syncthreads.  The Jacobian's dense part (the infection rows: one entry per source area, infectious
+ * compartment and group) is rebuilt every step as (column, value) lists in ascending compartment order = the
+ * reference's order of sums; the other rows have a single entry.  Sums that the reference does sequentially are
+ * sequential here too (one thread per output), so results agree with the CPU restatement to rounding.
  *
  * As in the reference: one strain; as many transitions as non-susceptible compartments (state_mvn_approx.cc:1376);
  * no observation on the susceptible compartment.  The infectivity map is recomputed from the mean population
@@ -52,6 +54,10 @@ struct DevApprox {
 	double *lu;                               /* [P][6][nwo][nwo]: M (in/out), l, u, linv, uinv, second matrix */
 	double *vec;                              /* [P][AP_NVEC][max(n,nt)]                                       */
 	double *L;                                /* [P]                                                           */
+	double *jval; int *jcol;                  /* [P][jcap] the infection rows of the Jacobian, rebuilt every step      */
+	long long jcap;
+	int logW;                                 /* lanes per matrix row in the (row, column) passes: 2^logW, at most 32 */
+	int sm_vec, sm_mat;                       /* the step vectors / covar and R live in dynamic shared memory          */
 };
 #define AP_NVEC 12
 enum { AV_DINF = 0, AV_IV, AV_NMI, AV_BE, AV_MU, AV_DS, AV_SIG, AV_MU1, AV_MINVMU, AV_MUN, AV_VEC, AV_TMP };
@@ -66,64 +72,69 @@ __device__ __forceinline__ double ap_bcast(double v, double *slot)
 	return r;
 }
 
-/* matrix.cc:18-62 + 564-579: Minv = M^-1 by Crout LU without pivoting (a zero pivot becomes TINY), det = sum log|l_ii|.
- * M, Minv, l, u, li, ui are nw x nw in the particle's scratch; every thread of the CTA calls this. */
-__device__ void ap_invert_det(const double *M, double *Minv, double *l, double *u, double *li, double *ui, const int nw, double *det_out, double *sm_slot)
+/* matrix.cc:18-62 + 564-579: Minv = M^-1 by Crout LU without pivoting (a zero pivot divides as TINY), det = sum log|l_ii|.
+ * Right-looking form of the same elimination: at step i the row of U is scaled and the trailing block loses the
+ * outer product l_:i u_i: -- every element sees its products one fused multiply-add at a time in ascending i, the
+ * sequence of the CPU restatement -- so all threads work at every step.  L (with its diagonal) and U (unit diagonal)
+ * share W; the inverses of the two triangular factors (the reference's row recurrence, invert_lower_triangular)
+ * advance together, row i updating all rows below it.  M, Minv, W, li, ui: nw x nw; fv: nw.  Called by every thread. */
+__device__ void ap_invert_det(const double *M, double *Minv, double *Wk, double *fv, double *li, double *ui, const int nw, const int logW, double *det_out, double *sm_slot)
 {
 	const int tid = threadIdx.x, nth = blockDim.x;
+	const int W = 1 << logW, col0 = tid & (W - 1), row0 = tid >> logW, rstep = nth >> logW;
+	for (int e = tid; e < nw * nw; e += nth) Wk[e] = M[e];
+	__syncthreads();
 	for (int i = 0; i < nw; i++) {
-		for (int j = i + tid; j < nw; j += nth) {
-			double s = 0;
-			for (int k = 0; k < i; k++) s += l[j * nw + k] * u[i * nw + k];
-			l[j * nw + i] = M[j * nw + i] - s;
-		}
-		__syncthreads();
-		double val = l[i * nw + i];
+		double val = Wk[i * nw + i];
 		if (val == 0) val = AP_TINY;
-		if (tid == 0) u[i * nw + i] = 1;
-		for (int j = i + 1 + tid; j < nw; j += nth) {
-			double s = 0;
-			for (int k = 0; k < i; k++) s += l[i * nw + k] * u[j * nw + k];
-			u[j * nw + i] = (M[i * nw + j] - s) / val;
+		for (int k = i + 1 + tid; k < nw; k += nth) Wk[i * nw + k] = Wk[i * nw + k] / val;
+		__syncthreads();
+		for (int j = i + 1 + row0; j < nw; j += rstep) {
+			const double lji = -Wk[j * nw + i];
+			for (int k = i + 1 + col0; k < nw; k += W) Wk[j * nw + k] = fma(lji, Wk[i * nw + k], Wk[j * nw + k]);
 		}
 		__syncthreads();
 	}
+	/* det = sum_i log(|u_ii| |l_ii|), u_ii = 1 (matrix.cc:44-48): the logarithms in parallel, the sum in index order */
+	for (int i = tid; i < nw; i += nth) {
+		double vall = Wk[i * nw + i];
+		fv[i] = 1.0 / vall;
+		if (vall < 0) vall = -vall;
+		Minv[i] = log(1.0 * vall);
+	}
+	for (int e = tid; e < nw * nw; e += nth) { li[e] = 0; ui[e] = 0; }
+	__syncthreads();
 	if (tid == 0) {
 		double d = 0;
-		for (int i = 0; i < nw; i++) { double vall = l[i * nw + i]; if (vall < 0) vall = -vall; d += log(1.0 * vall); }
+		for (int i = 0; i < nw; i++) d += Minv[i];
 		*sm_slot = d;
 	}
-	/* inverses of the two lower-triangular factors, one column per thread (the reference's row recurrence,
-	 * matrix.cc:564-579, element by element: x_jk = [j==k] f_j - sum_{i<j} (l_ji f_j) x_ik, f_j = 1/l_jj) */
-	for (int k = tid; k < 2 * nw; k += nth) {
-		const bool second = k >= nw;
-		const int kk = second ? k - nw : k;
-		const double *Lm = second ? u : l;
-		double *X = second ? ui : li;
-		for (int j = 0; j < kk; j++) X[j * nw + kk] = 0;
-		for (int j = kk; j < nw; j++) {
-			const double f = 1.0 / Lm[j * nw + j];
-			double acc = (j == kk) ? f : 0.0;
-			for (int i = kk; i < j; i++) acc += (-(Lm[j * nw + i] * f)) * X[i * nw + kk];
-			X[j * nw + kk] = acc;
-		}
-	}
+	for (int j = tid; j < nw; j += nth) { li[j * nw + j] = fv[j]; ui[j * nw + j] = 1.0; }
 	__syncthreads();
 	*det_out = *sm_slot;
+	/* x_j: += -(l_ji f_j) x_i: for i < j, columns 0..i (matrix.cc:573-577); the second factor is U^T, f = 1 */
+	for (int i = 0; i + 1 < nw; i++) {
+		for (int j = i + 1 + row0; j < nw; j += rstep) {
+			const double fl = -(Wk[j * nw + i] * fv[j]), fu = -(Wk[i * nw + j] * 1.0);
+			for (int k = col0; k <= i; k += W) {
+				li[j * nw + k] = fma(fl, li[i * nw + k], li[j * nw + k]);
+				ui[j * nw + k] = fma(fu, ui[i * nw + k], ui[j * nw + k]);
+			}
+		}
+		__syncthreads();
+	}
 	/* Minv[j][i] = sum_{k >= j} uinv[k][j] linv[k][i]  (i <= j), mirrored: matrix.cc:55-61 */
-	for (int e = tid; e < nw * nw; e += nth) {
-		const int j = e / nw, i = e - j * nw;
-		if (i <= j) {
+	for (int j = row0; j < nw; j += rstep)
+		for (int i = col0; i <= j; i += W) {
 			double s = 0;
-			for (int k = j; k < nw; k++) s += ui[k * nw + j] * li[k * nw + i];
+			for (int k = j; k < nw; k++) s = fma(ui[k * nw + j], li[k * nw + i], s);
 			Minv[j * nw + i] = s; Minv[i * nw + j] = s;
 		}
-	}
 	__syncthreads();
 }
 
 /* state_mvn_approx.cc:1133-1155 valid_matrix */
-__device__ void ap_valid(double *M, const double *mean, double *sigma, const int n)
+__device__ void ap_valid(double *M, const double *mean, double *sigma, const int n, const int logW)
 {
 	const int tid = threadIdx.x, nth = blockDim.x;
 	const double diag_min = 0.001, cormax = 0.8;
@@ -136,13 +147,15 @@ __device__ void ap_valid(double *M, const double *mean, double *sigma, const int
 		sigma[c] = sqrt(v);
 	}
 	__syncthreads();
-	for (int e = tid; e < n * n; e += nth) {
-		const int c = e / n, cc = e - c * n;
-		if (cc > c) {
-			const double sigmult = cormax * sigma[c] * sigma[cc], val = M[c * n + cc];
-			if (val > sigmult) { M[c * n + cc] = sigmult; M[cc * n + c] = sigmult; }
-			if (val < -sigmult) { M[c * n + cc] = -sigmult; M[cc * n + c] = -sigmult; }
-		}
+	const int W = 1 << logW, col0 = tid & (W - 1);
+	for (int c = tid >> logW; c < n; c += nth >> logW) {
+		const double sc = cormax * sigma[c];
+		for (int cc = col0; cc < n; cc += W)
+			if (cc > c) {
+				const double sigmult = sc * sigma[cc], val = M[c * n + cc];
+				if (val > sigmult) { M[c * n + cc] = sigmult; M[cc * n + c] = sigmult; }
+				if (val < -sigmult) { M[c * n + cc] = -sigmult; M[cc * n + c] = -sigmult; }
+			}
 	}
 	__syncthreads();
 }
@@ -183,7 +196,7 @@ __device__ double ap_observation(const DevModel &m, const DevBatch &b, const Dev
 	for (int e = tid; e < nw * nw; e += nth) { const int j = e / nw, i = e - j * nw; M1[e] = covar[x.wo[j] * n + x.wo[i]]; }
 	__syncthreads();
 	double det1, det;
-	ap_invert_det(M1, Mi, l, u, li, ui, nw, &det1, sm);          /* Mi = Minv */
+	ap_invert_det(M1, Mi, l, u, li, ui, nw, x.logW, &det1, sm);          /* Mi = Minv */
 	double mu2 = 0.0, log_factor = 0.0;                          /* kept by thread 0 */
 	for (int k = x.sl_off[slice]; k < x.sl_off[slice + 1]; k++) {
 		const int ob = x.sl_obs[k];
@@ -216,7 +229,7 @@ __device__ double ap_observation(const DevModel &m, const DevBatch &b, const Dev
 		}
 		__syncthreads();
 	}
-	ap_invert_det(Mi, M1, l, u, li, ui, nw, &det, sm);           /* M1 = the combined covariance M */
+	ap_invert_det(Mi, M1, l, u, li, ui, nw, x.logW, &det, sm);           /* M1 = the combined covariance M */
 	for (int j = tid; j < nw; j += nth) { double s = 0; for (int i = 0; i < nw; i++) s += M1[j * nw + i] * Minv_mu[i]; mu[j] = s; }
 	__syncthreads();
 	for (int i = tid; i < nw; i += nth) { double v = mu[i] + mu1[i]; if (v < 0) v = 0; vec[x.wo[i]] = v; }
@@ -231,7 +244,7 @@ __device__ double ap_observation(const DevModel &m, const DevBatch &b, const Dev
 	for (int e = tid; e < nw * nw; e += nth) { const int j = e / nw, i = e - j * nw; covar[x.wo[j] * n + x.wo[i]] = M1[e]; }
 	__syncthreads();
 	ap_fill_S(x, covar);
-	ap_valid(covar, vec, vecs + AV_SIG * vstride, n);
+	ap_valid(covar, vec, vecs + AV_SIG * vstride, n, x.logW);
 	for (int i = tid; i < n; i += nth) pv[i] = vec[i];
 	double dL = 0;
 	if (tid == 0) {
@@ -251,10 +264,18 @@ __global__ void __launch_bounds__(AP_THREADS) k_likelihood_approx(const DevModel
 	const int p = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
 	const int n = x.n, nt = x.nt, T = m.T, A = m.A, C = m.C, J = m.J, D = m.D, G = m.G;
 	const int vstride = n > nt ? n : nt;
+	extern __shared__ __align__(16) double ap_dyn[];
 	double *popbase = x.pop + (size_t)p * (T + 1) * n;
-	double *covar = x.covar + (size_t)p * n * n, *R = x.R + (size_t)p * nt * n;
+	double *vecs = x.sm_vec ? ap_dyn : x.vec + (size_t)p * AP_NVEC * vstride;
+	double *covar = x.sm_mat ? ap_dyn + AP_NVEC * vstride : x.covar + (size_t)p * n * n;
+	double *R = x.sm_mat ? covar + n * n : x.R + (size_t)p * nt * n;
 	double *lu = x.lu + (size_t)p * 6 * x.nwo * x.nwo;
-	double *vecs = x.vec + (size_t)p * AP_NVEC * vstride;
+	double *Sm = lu;                                              /* n x n, free between observations (6 nwo^2 >= n^2) */
+	double *jval = x.jval + (size_t)p * x.jcap;
+	/* (row, column) passes: a row per group of W = 2^logW lanes (W = 32 from 32 columns on), no index divisions */
+	const int logW = x.logW, W = 1 << logW, col0 = tid & (W - 1);
+	const int row0 = tid >> logW, rstep = nth >> logW;
+	int *jcol = x.jcol + (size_t)p * x.jcap;
 	double *dinf = vecs + AV_DINF * vstride, *Iv = vecs + AV_IV * vstride, *nmi = vecs + AV_NMI * vstride, *bes = vecs + AV_BE * vstride,
 	       *mu = vecs + AV_MU * vstride, *dS = vecs + AV_DS * vstride;
 	const double *ds = b.disc_spline + (size_t)p * m.nspline * T;
@@ -263,6 +284,8 @@ __global__ void __launch_bounds__(AP_THREADS) k_likelihood_approx(const DevModel
 	const int ninf = il[0];
 	const int itr = m.itr, sfrom = m.trans_from[itr];
 	const double dt = m.dt;
+	bool failed = false;
+	for (int k = 1; k <= ninf; k++) if (il[k] == sfrom) failed = true;     /* "The start compartment cannot be infectious", state_mvn_approx.cc:1238 */
 
 	for (int i = tid; i < n; i += nth) popbase[i] = m.pop_init[i];
 	for (int e = tid; e < n * n; e += nth) covar[e] = 0;
@@ -271,8 +294,7 @@ __global__ void __launch_bounds__(AP_THREADS) k_likelihood_approx(const DevModel
 
 	double L = 0.0;
 	int o = 0;
-	bool failed = false;
-	for (int sett = 0; sett <= T; sett++) {
+	for (int sett = 0; sett <= T && !failed; sett++) {
 		if (o < x.nslice && sett == x.sl_sett[o]) {
 			if (sett > 0) {
 				const double dL = ap_observation(m, b, x, p, o, invT, popbase, covar, lu, vecs, vstride, sm_slot);
@@ -343,68 +365,106 @@ __global__ void __launch_bounds__(AP_THREADS) k_likelihood_approx(const DevModel
 		}
 		__syncthreads();
 
-		/* ---- R = J covar, the Jacobian's non-zeros recomputed on the fly in ascending compartment order ---- */
-		for (int e = tid; e < nt * n; e += nth) {
-			const int ta = e / n, i = e - ta * n;
-			const int c2 = ta / (J * D), tr = (ta / D) % J, dp2 = ta - (c2 * J + tr) * D;
-			double r = 0;
-			if (tr != itr) {
-				const double val = dt * transrate[tr * D + dp2];
-				if (val != 0) r += val * covar[((c2 * C + m.trans_from[tr]) * D + dp2) * n + i];
-			} else {
-				const int a2 = m.dp_age[dp2];
-				const AreaInfo ai = m.area_info[c2];
-				const double pref = dt * sus[dp2] * bes[c2];
-				const double pS = pop[(c2 * C + sfrom) * D + dp2];
-				int j = 0;
-				bool self_done = false;
-				while (true) {
-					int c; double va;
-					const int cn = (j < ai.nn) ? (int)(m.nbr[ai.j0 + j].off >> 3) / G : A;
-					if (!self_done && c2 < cn) { c = c2; va = ai.diag; self_done = true; }
-					else if (j < ai.nn) { c = cn; va = m.nbr[ai.j0 + j].val; j++; }
-					else break;
-					for (int co = 0; co < C; co++) {
-						if (co == sfrom) {
-							if (c == c2) { const double val = dS[c2 * D + dp2]; if (val != 0) r += val * covar[((c2 * C + sfrom) * D + dp2) * n + i]; }
-							continue;
-						}
-						const double inf = infco[co];
-						if (inf == 0) continue;
-						for (int dp = 0; dp < D; dp++) {
-							const double valu = pref * nts[m.dp_age[dp] * G + a2] * va * inf;
-							const double val = valu * pS;
-							if (val != 0) r += val * covar[((c * C + co) * D + dp) * n + i];
-						}
+		/* ---- the infection rows of the Jacobian (state_mvn_approx.cc:1213-1266): one thread per row lists its
+		 * non-zeros (column, value) in ascending compartment order = the reference's order of sums ---- */
+		for (int r = tid; r < A * D; r += nth) {
+			const int c2 = r / D, dp2 = r - c2 * D, a2 = m.dp_age[dp2];
+			const AreaInfo ai = m.area_info[c2];
+			const int len = (ai.nn + 1) * ninf * D + 1;
+			int k = D * ((ai.j0 + c2) * ninf * D + c2) + dp2 * len;
+			const double pref = dt * sus[dp2] * bes[c2];
+			const double pS = pop[(c2 * C + sfrom) * D + dp2];
+			const int colS = (c2 * C + sfrom) * D + dp2;
+			const double valS = dS[c2 * D + dp2];
+			int j = 0;
+			bool self_done = false;
+			while (true) {
+				int c; double va;
+				const int cn = (j < ai.nn) ? (int)(m.nbr[ai.j0 + j].off >> 3) / G : A;
+				if (!self_done && c2 < cn) { c = c2; va = ai.diag; self_done = true; }
+				else if (j < ai.nn) { c = cn; va = m.nbr[ai.j0 + j].val; j++; }
+				else break;
+				bool s_done = (c != c2);
+				for (int q = 1; q <= ninf; q++) {
+					const int co = il[q];
+					const double inf = infco[co];
+					if (!s_done && co > sfrom) { jcol[k] = colS; jval[k] = valS; k++; s_done = true; }
+					for (int dp = 0; dp < D; dp++) {
+						const double valu = pref * nts[m.dp_age[dp] * G + a2] * va * inf;
+						jcol[k] = (c * C + co) * D + dp; jval[k] = valu * pS; k++;
 					}
 				}
+				if (!s_done) { jcol[k] = colS; jval[k] = valS; k++; }
 			}
-			R[e] = r;
+		}
+		__syncthreads();
+		/* ---- R = J covar (covar_matrix_mult_SIMD, matrix.cc:211-236): a row of R per group of W lanes ---- */
+		for (int ta = row0; ta < nt; ta += rstep) {
+			const int c2 = ta / (J * D), tr = (ta / D) % J, dp2 = ta - (c2 * J + tr) * D;
+			double *Rrow = R + ta * n;
+			if (tr != itr) {
+				const double val = dt * transrate[tr * D + dp2];
+				const double *crow = covar + ((c2 * C + m.trans_from[tr]) * D + dp2) * n;
+				for (int i = col0; i < n; i += W) Rrow[i] = (val != 0) ? fma(val, crow[i], 0.0) : 0.0;
+			} else {
+				const AreaInfo ai = m.area_info[c2];
+				const int len = (ai.nn + 1) * ninf * D + 1;
+				const int k0 = D * ((ai.j0 + c2) * ninf * D + c2) + dp2 * len;
+				const double *jv = jval + k0;
+				const int *jc = jcol + k0;
+				for (int i = col0; i < n; i += 4 * W) {
+					/* four columns per lane: the row's (column, value) entries are fetched once for all of them */
+					const int i1 = i + W, i2 = i + 2 * W, i3 = i + 3 * W;
+					const bool h1 = i1 < n, h2 = i2 < n, h3 = i3 < n;
+					double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll 2
+					for (int k = 0; k < len; k++) {
+						const double val = jv[k];
+						if (val != 0) {
+							const double *crow = covar + jc[k] * n;
+							r0 = fma(val, crow[i], r0);
+							if (h1) r1 = fma(val, crow[i1], r1);
+							if (h2) r2 = fma(val, crow[i2], r2);
+							if (h3) r3 = fma(val, crow[i3], r3);
+						}
+					}
+					Rrow[i] = r0;
+					if (h1) Rrow[i1] = r1;
+					if (h2) Rrow[i2] = r2;
+					if (h3) Rrow[i3] = r3;
+				}
+			}
 		}
 		__syncthreads();
 
-		/* ---- covar += mu terms + S + S^T, S[j][:] = sum over the transitions of j of +-R[ta][:]  (state_mvn_approx.cc:1083-1101) ---- */
-		for (int e = tid; e < n * n; e += nth) {
-			const int j = e / n, i = e - j * n;
-			double v = covar[e];
-			double sji = 0, sij = 0;
-			for (int q = x.inc_off[j]; q < x.inc_off[j + 1]; q++) {
-				const int ta = x.inc_ta[q];
-				const int fr = x.ta_from[ta], to = x.ta_to[ta];
-				const double val = mu[ta];
-				if (i == j) v += val;
-				else if ((fr == j ? to : fr) == i) v -= val;
-				sji += (to == j ? 1.0 : -1.0) * R[ta * n + i];
+		/* ---- S = Tm R: row j is the signed sum of the rows of R of j's transitions (covar_matrix_mult_SIMD with the
+		 * incidence matrix, state_mvn_approx.cc:1098) ---- */
+		for (int j = row0; j < n; j += rstep) {
+			const int q0 = x.inc_off[j], q1 = x.inc_off[j + 1];
+			for (int i = col0; i < n; i += W) {
+				double sj = 0;
+				for (int q = q0; q < q1; q++) { const int ta = x.inc_ta[q]; sj += (x.ta_to[ta] == j ? 1.0 : -1.0) * R[ta * n + i]; }
+				Sm[j * n + i] = sj;
 			}
-			for (int q = x.inc_off[i]; q < x.inc_off[i + 1]; q++) {
-				const int ta = x.inc_ta[q];
-				sij += (x.ta_to[ta] == i ? 1.0 : -1.0) * R[ta * n + j];
-			}
-			v += sji + sij;
-			covar[e] = v;
 		}
 		__syncthreads();
-		ap_valid(covar, pop, vecs + AV_SIG * vstride, n);
+		/* ---- covar += mu terms (state_mvn_approx.cc:1083-1094) + S + S^T (covar_add_mat, matrix.cc:199-208) ---- */
+		for (int j = row0; j < n; j += rstep) {
+			const int q0 = x.inc_off[j], q1 = x.inc_off[j + 1];
+			for (int i = col0; i < n; i += W) {
+				double v = covar[j * n + i];
+				for (int q = q0; q < q1; q++) {
+					const int ta = x.inc_ta[q];
+					const int fr = x.ta_from[ta], to = x.ta_to[ta];
+					if (i == j) v += mu[ta];
+					else if ((fr == j ? to : fr) == i) v -= mu[ta];
+				}
+				v += Sm[j * n + i] + Sm[i * n + j];
+				covar[j * n + i] = v;
+			}
+		}
+		__syncthreads();
+		ap_valid(covar, pop, vecs + AV_SIG * vstride, n, x.logW);
 
 		/* ---- state.cc:460-485 update_pop with transnum = transmean ---- */
 		for (int ca = tid; ca < n; ca += nth) {

@@ -1099,7 +1099,14 @@ extern "C" int beep_likelihood_approx(BeepBatch *bt, double invT, double *L_host
 	const int P = bt->db.P;
 	DevApprox x = eng->ax;
 	const size_t n = x.n, nt = x.nt, nw = x.nwo, vs = std::max(n, nt);
-	const size_t per = (size_t)(m.T + 1) * n + n * n + nt * n + 6 * nw * nw + AP_NVEC * vs + 1;
+	/* entries of the infection rows of the Jacobian: D ((nnz + A) ninf D + A), ninf <= C - 1 */
+	const size_t jcap = (size_t)m.D * (((size_t)m.M_nnz + m.A) * (size_t)(m.C - 1) * m.D + m.A);
+	/* the step vectors, and the covariance with the product R when they leave room for several CTAs per SM, live in shared memory */
+	const size_t sm_vec_b = AP_NVEC * vs * sizeof(double), sm_mat_b = (n * n + nt * n) * sizeof(double);
+	x.sm_vec = sm_vec_b <= 40 * 1024;
+	x.sm_mat = x.sm_vec && sm_vec_b + sm_mat_b <= 72 * 1024;
+	const size_t smem = (x.sm_vec ? sm_vec_b : 0) + (x.sm_mat ? sm_mat_b : 0);
+	const size_t per = (size_t)(m.T + 1) * n + (x.sm_mat ? 0 : n * n + nt * n) + 6 * nw * nw + (x.sm_vec ? 0 : AP_NVEC * vs) + 1 + jcap + (jcap + 1) / 2;
 	const size_t need = per * P * sizeof(double);
 	if (bt->d_approx_n < need) {
 		CU(cudaStreamSynchronize(bt->stream));
@@ -1118,12 +1125,19 @@ extern "C" int beep_likelihood_approx(BeepBatch *bt, double invT, double *L_host
 	}
 	double *q = bt->d_approx;
 	x.pop = q; q += (size_t)P * (m.T + 1) * n;
-	x.covar = q; q += (size_t)P * n * n;
-	x.R = q; q += (size_t)P * nt * n;
+	if (!x.sm_mat) { x.covar = q; q += (size_t)P * n * n; x.R = q; q += (size_t)P * nt * n; }
 	x.lu = q; q += (size_t)P * 6 * nw * nw;
-	x.vec = q; q += (size_t)P * AP_NVEC * vs;
-	x.L = q;
-	k_likelihood_approx<<<P, AP_THREADS, 0, bt->stream>>>(m, bt->db, x, invT);
+	if (!x.sm_vec) { x.vec = q; q += (size_t)P * AP_NVEC * vs; }
+	x.L = q; q += P;
+	x.jval = q; q += (size_t)P * jcap;
+	x.jcol = (int *)q;
+	x.jcap = (long long)jcap;
+	/* threads per particle: about four outputs of the n x n passes per thread, one to eight warps */
+	int nth = (int)std::min<size_t>(AP_THREADS, std::max<size_t>(32, ((n * n / 4 + 31) / 32) * 32));
+	x.logW = 0;
+	while (x.logW < 5 && (1u << x.logW) < n) x.logW++;
+	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_likelihood_approx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_likelihood_approx<<<P, nth, smem, bt->stream>>>(m, bt->db, x, invT);
 	eng->launches++;
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(L_host, x.L, P * sizeof(double), cudaMemcpyDeviceToHost, bt->stream));

@@ -15,9 +15,9 @@
  *     Model::trans_comp_divide        model.cc:3524-3566
  *     invert_determinant_SIMD, invert_lower_triangular, covar_matrix_mult_SIMD   matrix.cc:18-62, 564-579, 211-236
  *
- * Plain sequential loops; sums run in index order (the reference's AVX routines keep four partial sums and use
- * fused multiply-adds, so agreement with the reference is to rounding, not bit for bit: tests/test_approx_*.py
- * state the tolerance).  Two deliberate differences, both equal to the reference in exact arithmetic:
+ * Plain sequential loops; sums run in index order, with the fused multiply-adds the reference's AVX routines use
+ * written as fma() (the reference's dot products keep four partial sums, so agreement with the reference is to
+ * rounding, not bit for bit: tests/test_approx_*.py state the tolerance).  Two deliberate differences, both equal to the reference in exact arithmetic:
  *   - the infectivity map is recomputed from the mean population at every step (the reference updates it from
  *     transnum[sett-1], to which apply_observation_fast adds the transitions Tinv_without_S (vec - mu_start) that
  *     reproduce the population change of the observation, state_mvn_approx.cc:803-814: the two maps are equal);
@@ -167,7 +167,8 @@ static int approx_init(const BeepModelDesc *m, ApproxIdx *x)
 	return 0;
 }
 
-/* matrix.cc:564-579 invert_lower_triangular (M is normalised in place) */
+/* matrix.cc:564-579 invert_lower_triangular (M is normalised in place); the row update is the reference's fused
+ * multiply-add (sub_row_SIMD, matrix.cc:769-795: _mm256_fmadd_pd) */
 static void ap_invert_lower(double *M, double *Minv, int n, int ld)
 {
 	for (int j = 0; j < n; j++) {
@@ -177,25 +178,29 @@ static void ap_invert_lower(double *M, double *Minv, int n, int ld)
 		M[j * ld + j] = 1;
 		for (int i = 0; i < j; i++) {
 			double f = -M[j * ld + i];
-			for (int k = 0; k <= i; k++) Minv[j * ld + k] += f * Minv[i * ld + k];
+			for (int k = 0; k <= i; k++) Minv[j * ld + k] = fma(f, Minv[i * ld + k], Minv[j * ld + k]);
 		}
 	}
 }
 
-/* matrix.cc:18-62 invert_determinant_SIMD, DOUBLE branch: Crout LU without pivoting, det = sum log|l_ii| */
+/* matrix.cc:18-62 invert_determinant_SIMD, DOUBLE branch: Crout LU without pivoting, det = sum log|l_ii|.  The
+ * dot products are taken off the matrix element one fused multiply-add at a time in index order (the reference's
+ * dot_SIMD keeps four partial sums, matrix.cc:379-410: same algorithm, another order of rounding). */
 static void ap_invert_det(const double *M, double *Minv, int n, double *det)
 {
 	double *l = dalloc((long)n * n), *u = dalloc((long)n * n), *li = dalloc((long)n * n), *ui = dalloc((long)n * n);
 	for (int i = 0; i < n; i++) {
 		for (int j = i; j < n; j++) {
-			double s = 0; for (int k = 0; k < i; k++) s += l[j * n + k] * u[i * n + k];
-			l[j * n + i] = M[j * n + i] - s;
+			double acc = M[j * n + i];
+			for (int k = 0; k < i; k++) acc = fma(-l[j * n + k], u[i * n + k], acc);
+			l[j * n + i] = acc;
 		}
 		u[i * n + i] = 1;
 		for (int j = i + 1; j < n; j++) {
 			double val = l[i * n + i]; if (val == 0) val = TINY;
-			double s = 0; for (int k = 0; k < i; k++) s += l[i * n + k] * u[j * n + k];
-			u[j * n + i] = (M[i * n + j] - s) / val;
+			double acc = M[i * n + j];
+			for (int k = 0; k < i; k++) acc = fma(-l[i * n + k], u[j * n + k], acc);
+			u[j * n + i] = acc / val;
 		}
 	}
 	double d = 0;
@@ -211,7 +216,7 @@ static void ap_invert_det(const double *M, double *Minv, int n, double *det)
 	for (int j = 0; j < n; j++)
 		for (int i = 0; i <= j; i++) {
 			double s = 0;
-			for (int k = j; k < n; k++) s += ui[k * n + j] * li[k * n + i];
+			for (int k = j; k < n; k++) s = fma(ui[k * n + j], li[k * n + i], s);
 			Minv[j * n + i] = s; Minv[i * n + j] = s;
 		}
 	free(l); free(u); free(li); free(ui);
@@ -420,7 +425,7 @@ double oracle_likelihood_approx(OracleState *s, const double *theta, double invT
 			for (int i = 0; i < n; i++) r[i] = 0;
 			for (int ca = 0; ca < n; ca++) {
 				double val = dtm[(long)ta * n + ca];
-				if (val != 0) { const double *row = old + (long)ca * n; for (int i = 0; i < n; i++) r[i] += val * row[i]; }
+				if (val != 0) { const double *row = old + (long)ca * n; for (int i = 0; i < n; i++) r[i] = fma(val, row[i], r[i]); }   /* sub_row_SIMD: fused */
 			}
 		}
 		for (long q = 0; q < (long)n * n; q++) P[q] = 0;                   /* P = T * R, T[ca][ta] = -1 (from) / +1 (to) */
