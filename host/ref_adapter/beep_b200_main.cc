@@ -56,6 +56,7 @@
 #include "state.hh"
 #include "output.hh"
 #include "pmcmc.hh"
+#include "ml.hh"
 #include "mvn.hh"
 #include "utils.hh"
 #include "timers.hh"
@@ -460,6 +461,57 @@ static void run_pmcmc(const Details &details, const Data &data, const Model &mod
 	cout << "pmcmc on the engine: " << g_pm.ncall << " particle filters of " << pmcmc.Ntot << " particles, " << g_pm.seconds << " s in the filter of " << now_s()-t0 << " s" << endl;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// mode=map: the reference's ML object (CMA-ES, ml.cc:150-385) on the engine.  ML::generate_samples (ml.cc:389-413)
+// -- the loop that evaluates State::likelihood_approx for every sample of a generation -- is replaced at link time
+// (weak in the linked copy of ml.o, see build.sh) by ONE beep_likelihood_approx call for the whole generation;
+// sampling (ML::sample_param), priors, the CMA-ES update, the Hessian and the final posterior samples run as compiled.
+// ---------------------------------------------------------------------------------------------------------
+struct MlEngine {
+	beep::Engine *eng = nullptr;
+	beep::BatchState *part = nullptr;
+	long ncall = 0, nlik = 0;
+	double seconds = 0;
+	vector <double> theta;
+};
+static MlEngine g_ml;
+
+void ML::generate_samples(vector <ParamSample> &ps_per_core, const vector <double> &mean, const vector < vector <double> > &C, const double sigma, Generation &gen)
+{
+	auto psamp = sample_param(mean,C,sigma,ps_per_core.size());          // the reference's own sampler (ml.cc:417-441): same ran() stream
+	if(details.stochastic != true) emsgroot("mode=map through the adapter evaluates the approximate likelihood of stochastic models");
+	const auto n = ps_per_core.size(), nparam = model.param.size();
+	if((int)n != g_ml.part->size()) emsgroot("generation size differs from the engine batch");
+	const double t0 = now_s();
+	g_ml.theta.resize(n*nparam);
+	for(auto i = 0u; i < n; i++) copy(psamp[i].begin(),psamp[i].end(),g_ml.theta.begin()+(size_t)i*nparam);
+	g_ml.part->set_param(g_ml.theta);
+	auto L = g_ml.part->likelihood_approx(invT);
+	g_ml.seconds += now_s()-t0; g_ml.ncall++; g_ml.nlik += n;
+	for(auto i = 0u; i < n; i++){
+		ps_per_core[i].paramval = psamp[i];
+		auto Pr = model.prior(psamp[i]);
+		ps_per_core[i].EF = -2*(L[i] + Pr);
+		if(ps_per_core[i].EF < 0) emsgEC("ML",44);
+		state.paramval = psamp[i];                                         // what set_param leaves behind; EF and the trajectory are diagnostics only
+		gen.param_samp.push_back(state.create_param_sample(0));
+		gen.EF_datatable.push_back(vector <double>(data.datatable.size(),0.0));
+	}
+}
+
+static void run_map(const Details &details, const Data &data, const Model &model, Inputs &inputs, const ObservationModel &obsmodel, Mpi &mpi, beep::Engine &eng, const Ranks &rk)
+{
+	if(rk.nranks != 1) emsgroot("mode=map through the adapter runs on one rank");
+	if(!beep_engine_has_approx(eng.handle())) emsgroot("the engine refuses this model for the approximate likelihood");
+	Output output(details,data,model,inputs,obsmodel,mpi);
+	ML ml(details,data,model,inputs,output,obsmodel,mpi);                // the reference's object: algorithm, nparticle, ngeneration, invT from the TOML / command line
+	beep::BatchState part(eng,(int)ml.npart_per_core);
+	g_ml.eng = &eng; g_ml.part = &part;
+	const double t0 = now_s();
+	ml.run();
+	cout << "map on the engine: " << g_ml.ncall << " generations of " << ml.npart_per_core << " approximate likelihoods, " << g_ml.seconds << " s on the engine of " << now_s()-t0 << " s" << endl;
+}
+
 int main(int argc, char **argv)
 {
 	timersinit();
@@ -496,7 +548,8 @@ int main(int argc, char **argv)
 		else switch(details.mode){
 		case ABC_SMC: { AbcSmc abc(details,model,inputs,eng,rk); abc.run(); } break;
 		case PMCMC_INF: run_pmcmc(details,data,model,inputs,obsmodel,mpi,eng,rk); break;
-		default: emsgroot("beep_b200_main runs mode=abcsmc, mode=pmcmc and BEEP_RUN=filter"); break;
+		case ML_INF: run_map(details,data,model,inputs,obsmodel,mpi,eng,rk); break;
+		default: emsgroot("beep_b200_main runs mode=abcsmc, mode=pmcmc, mode=map and BEEP_RUN=filter"); break;
 		}
 		if(rk.comm) beep_comm_destroy(rk.comm);
 	}

@@ -24,7 +24,10 @@ mkdir -p "$OUT/objw"
 g++ $CXXFLAGS -fPIC -fno-inline-functions -c "$REF/src/pmcmc.cc" -o "$OUT/objw/pmcmc.o"
 objcopy --weaken-symbol=_ZN5PMCMC8obs_probERSt6vectorIdSaIdEE "$OUT/objw/pmcmc.o"
 objcopy --weaken-symbol=_ZN3Mpi15particle_sampleEjRKSt6vectorIS0_IjSaIjEESaIS2_EERS0_I5StateSaIS7_EERK16ObservationModel "$OUT/obj/mpi.o" "$OUT/objw/mpi.o"
-OBJS=$(ls "$OUT"/obj/*.o | grep -v -E "/(pmcmc|mpi)\.o$")
+# mode=map: ML::generate_samples (ml.cc:389) is supplied by the adapter the same way
+g++ $CXXFLAGS -fPIC -fno-inline-functions -c "$REF/src/ml.cc" -o "$OUT/objw/ml.o"
+objcopy --weaken-symbol=_ZN2ML16generate_samplesERSt6vectorI11ParamSampleSaIS1_EERKS0_IdSaIdEERKS0_IS6_SaIS6_EEdR10Generation "$OUT/objw/ml.o"
+OBJS=$(ls "$OUT"/obj/*.o | grep -v -E "/(pmcmc|mpi|ml)\.o$")
 g++ $CXXFLAGS -std=c++14 -I"$ROOT/include" -I"$HERE" -c "$HERE/beep_b200_main.cc" -o "$OUT/beep_b200_main.oo"
-g++ -o "$OUT/BEEP_b200" "$OUT/beep_b200_main.oo" $OBJS "$OUT/objw/pmcmc.o" "$OUT/objw/mpi.o" -L"$ROOT/beep_b200/lib" -lbeep_b200 -Wl,-rpath,'$ORIGIN/../../beep_b200/lib' -lpthread
+g++ -o "$OUT/BEEP_b200" "$OUT/beep_b200_main.oo" $OBJS "$OUT/objw/pmcmc.o" "$OUT/objw/mpi.o" "$OUT/objw/ml.o" -L"$ROOT/beep_b200/lib" -lbeep_b200 -Wl,-rpath,'$ORIGIN/../../beep_b200/lib' -lpthread
 echo "ref_adapter/build.sh: built $OUT/BEEP_b200"

@@ -79,6 +79,13 @@ public:
 		check(beep_latent_loglik(h_, Li.data()));
 		return Li;
 	}
+	/// State::likelihood_approx (state_mvn_approx.cc:11-91) of every particle at inverse temperature invT
+	std::vector<double> likelihood_approx(double invT)
+	{
+		std::vector<double> L(size());
+		check(beep_likelihood_approx(h_, invT, L.data()));
+		return L;
+	}
 	/// Mbp::mbp (mbp.cc:252-330): this batch is the proposal, coupled slot by slot to `initial`
 	void mbp(BatchState &initial, uint64_t seed, const uint8_t *simu_mask = nullptr) { check(beep_mbp(initial.h_, h_, simu_mask, BEEP_INF_DIF_UPDATE, seed, nullptr)); }
 	/// Mbp::swap_initial_propose_state (mbp.cc:243-248) for the accepted slots

@@ -66,6 +66,10 @@ ABCSMC = {"abcsmc_EX_A1": ("examples/EX_A1.toml", 2000, 6),     # ~3 minutes of 
 # of the SAME driver on the engine.  invT is fixed (left unset the reference tunes it during burn-in, and two runs then
 # target different power posteriors).  ~2 minutes of the reference.
 PMCMC_POST = {"pmcmc_EX_A1": ("examples/EX_A1.toml", ["nparticle=32", "nsample=2000", "invT=0.03"])}
+# the reference's own mode=map (ML::run: CMA-ES over State::likelihood_approx, ml.cc:150-385): best log posterior and step size
+# per generation, final estimates and model evidence, for the adapter's run of the SAME driver with the generation's
+# likelihoods coming from beep_likelihood_approx
+MAP_POST = {"map_EX_A1": ("examples/EX_A1.toml", ["nparticle=48", "ngeneration=20", "nsample=50", "seed=7"])}
 DECISIONS = {"pmcmc": ["mode=pmcmc", "nparticle=24", "nsample=1000"], "abcmbp": ["mode=abcmbp", "nparticle=24", "ngeneration=3"],
              "pas": ["mode=pas", "nparticle=12", "nrun=2", "invT_final=1"], "mc3": ["mode=mc3", "nchain=6", "nrun=2", "invT_final=1", "nsample=1000"]}
 MVN_CASES = {
@@ -266,6 +270,27 @@ def main():
                "final_EF": sorted(ef)}
         json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
         print(f"{name}: {len(gens)} generations, {len(ef)} samples")
+    for name, (toml, args) in MAP_POST.items():
+        if only and name not in only:
+            continue
+        import csv
+        import json
+        outdir = os.path.join(work, "out_" + name)
+        cmd = [f"inputfile={toml}", "mode=map"] + args
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "BEEP")] + cmd + [f"outputdir={outdir}"], cwd=work, capture_output=True, text=True)
+        est = os.path.join(outdir, "Parameter_estimates.csv")
+        if not os.path.exists(est):
+            print(f"{name}: reference run FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        gens = []
+        for ln in r.stdout.splitlines():
+            if ln.startswith("Generation ") and "Best log(Post. prob.):" in ln:
+                gens.append({"best": float(ln.split("Best log(Post. prob.):")[1].split()[0]), "sigma": float(ln.split("Sigma:")[1].split()[0])})
+        ev = [ln for ln in r.stdout.splitlines() if ln.startswith("The log of the model evidence is")]
+        out = {"command": "BEEP " + " ".join(cmd), "generations": gens, "evidence": float(ev[0].split()[-1]) if ev else None,
+               "parameters": [{"name": x["Name"], "mean": float(x["Mean"]), "sd": float(x["SD"]), "prior": x["Prior"]} for x in csv.DictReader(open(est))]}
+        json.dump(out, open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w"), indent=1)
+        print(f"{name}: {len(gens)} generations")
     for name, (toml, args) in PMCMC_POST.items():
         if only and name not in only:
             continue

@@ -132,3 +132,32 @@ def test_abcsmc_england_prior_predictive(tmp_path):
     print(f"England_AS generation 0: cut-off {cut:.2f} vs {ref_cut:.2f}; KS distance {ks.statistic:.4f} (critical {crit:.4f} at alpha = 0.001, p = {ks.pvalue:.3g}); "
           f"deciles of cut - EF: {np.quantile(lim - a, [0.1, 0.5, 0.9]).round(2)} vs {np.quantile(lim - b, [0.1, 0.5, 0.9]).round(2)}")
     assert ks.statistic < crit, ks
+
+
+def test_map_matches_reference_run(tmp_path):
+    """mode=map (row N3): the reference's OWN ML driver (ML::run -> cmaes, ml.cc:150-385: sampling, ranking, covariance and step-size
+    adaptation, Hessian, posterior samples, outputs -- object code unchanged) with ML::generate_samples (ml.cc:389-413) replaced at
+    link time by ONE beep_likelihood_approx call per generation.  Same TOML, seed, nparticle and ngeneration as the reference's own
+    run behind tests/golden/map_EX_A1.json.  The sampler's ran() stream is the reference's own and the engine's likelihoods
+    agree with State::likelihood_approx to 1e-12, so the two CMA-ES runs follow the same path: best log posterior and step size of
+    every generation agree to the printed digits (1e-5 relative), and so do the final estimates and the model evidence."""
+    ref = json.load(open(os.path.join(GOLDEN, "map_EX_A1.json")))
+    out = str(tmp_path / "out")
+    log = _run(ref["command"].split()[1:] + [f"outputdir={out}"], timeout=600)
+    gens = []
+    for ln in log.splitlines():
+        if ln.startswith("Generation ") and "Best log(Post. prob.):" in ln:
+            gens.append((float(ln.split("Best log(Post. prob.):")[1].split()[0]), float(ln.split("Sigma:")[1].split()[0])))
+    assert len(gens) == len(ref["generations"]) == 20
+    for (best, sigma), g in zip(gens, ref["generations"]):
+        assert abs(best - g["best"]) <= 1e-5 * abs(g["best"]), (gens, ref["generations"])
+        assert abs(sigma - g["sigma"]) <= 1e-5 * g["sigma"]
+    rows = {r["Name"]: r for r in csv.DictReader(open(os.path.join(out, "Parameter_estimates.csv")))}
+    for est in ref["parameters"]:
+        assert abs(float(rows[est["name"]]["Mean"]) - est["mean"]) <= 2e-3 * max(abs(est["mean"]), 1e-9), est
+        assert abs(float(rows[est["name"]]["SD"]) - est["sd"]) <= 2e-2 * max(est["sd"], 1e-9) + 1e-3, est
+    ev = [ln for ln in log.splitlines() if ln.startswith("The log of the model evidence is")]
+    assert ev and abs(float(ev[0].split()[-1]) - ref["evidence"]) <= 1e-3 * abs(ref["evidence"])
+    line = [ln for ln in log.splitlines() if ln.startswith("map on the engine")][0]
+    assert "20 generations of 48 approximate likelihoods" in line
+    print(line)
