@@ -20,6 +20,7 @@
 #include "traj_chunk.cuh"
 #include "imap_dense.cuh"
 #include "approx.cuh"
+#include "graphs.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* errors                                                                    */
@@ -62,6 +63,10 @@ struct BeepEngine {
 	/* MVN-approximate likelihood (approx.cuh): index lists built at creation when the model qualifies */
 	bool approx_ok = false; std::string approx_why;
 	DevApprox ax;
+	/* state graphs (graphs.cuh) */
+	bool graphs_ok = false, graphs_pop = false, graphs_obs = false;
+	DevGraphs gx;
+	std::vector<int> graph_point_off;
 };
 
 struct BeepBatch {
@@ -237,6 +242,50 @@ static int approx_setup(BeepEngine *eng, const BeepModelDesc *d)
 	UPX(sl_sett, sl_sett); UPX(sl_off, sl_off); UPX(sl_obs, sl_obs);
 #undef UPX
 	eng->approx_ok = true;
+	return BEEP_OK;
+}
+
+
+/* the graphs of data.graph (struct.hh:367-382) and the points ObservationModel::get_graph_state (obsmodel.cc:113-170) gives each */
+static int graphs_setup(BeepEngine *eng, const BeepModelDesc *d)
+{
+	DevGraphs &g = eng->gx;
+	memset(&g, 0, sizeof g);
+	eng->graphs_ok = false;
+	const int ng = (int)d->n_graph_type;
+	if (ng == 0 || d->n_graph_step != 1 || d->graph_step[0] <= 0) return BEEP_OK;
+	if (d->n_graph_table != ng || d->n_graph_factor != ng || d->n_graph_factor_spline != ng || d->n_graph_area_off != ng + 1 || d->n_graph_dp_off != ng + 1 || d->n_graph_point_off != ng + 1)
+		return fail(BEEP_ERR_INVALID, "graph arrays of the description are inconsistent");
+	const int gs = d->graph_step[0];
+	std::vector<int> pt_graph, pt_first;
+	eng->graph_point_off.assign(1, 0);
+	for (int gr = 0; gr < ng; gr++) {
+		const int dt = d->graph_table[gr];
+		if (dt < 0 || dt >= d->ntable || d->graph_factor_spline[gr] >= d->nspline) return fail(BEEP_ERR_INVALID, "graph %d refers to a table or spline out of range", gr);
+		for (int k = d->graph_area_off[gr]; k < d->graph_area_off[gr + 1]; k++) if (d->graph_area[k] < 0 || d->graph_area[k] >= d->A) return fail(BEEP_ERR_INVALID, "graph %d: area out of range", gr);
+		for (int k = d->graph_dp_off[gr]; k < d->graph_dp_off[gr + 1]; k++) if (d->graph_dp[k] < 0 || d->graph_dp[k] >= d->D) return fail(BEEP_ERR_INVALID, "graph %d: demographic group out of range", gr);
+		if (d->graph_type[gr] == 1) {
+			for (int k = d->graph_point_off[gr]; k < d->graph_point_off[gr + 1]; k++) {
+				if (d->graph_point_obs[k] < 0 || d->graph_point_obs[k] >= d->nobs) return fail(BEEP_ERR_INVALID, "graph %d: observation out of range", gr);
+				pt_graph.push_back(gr); pt_first.push_back(d->graph_point_obs[k]);
+			}
+			eng->graphs_obs = true;
+		} else {
+			for (int sett = 0; sett < d->T - gs; sett += gs) { pt_graph.push_back(gr); pt_first.push_back(sett); }
+			if (d->table_comp_off[dt + 1] > d->table_comp_off[dt]) eng->graphs_pop = true;
+		}
+		eng->graph_point_off.push_back((int)pt_graph.size());
+	}
+	g.ngraph = ng; g.npoint = (int)pt_graph.size(); g.gstep = gs;
+#define UPG(field, src, n) do { int rc_ = upload(eng, (src), (size_t)(n), &g.field); if (rc_) return rc_; } while (0)
+	UPG(type, d->graph_type, ng); UPG(table, d->graph_table, ng); UPG(fspline, d->graph_factor_spline, ng); UPG(factor, d->graph_factor, ng);
+	UPG(area_off, d->graph_area_off, ng + 1); UPG(area, d->graph_area, d->n_graph_area); UPG(dp_off, d->graph_dp_off, ng + 1); UPG(dp, d->graph_dp, d->n_graph_dp);
+	UPG(point_off, d->graph_point_off, ng + 1); UPG(point_obs, d->graph_point_obs, d->n_graph_point_obs);
+	UPG(table_trans_off, d->table_trans_off, d->ntable + 1); UPG(table_trans, d->table_trans, d->n_table_trans);
+	UPG(table_comp_off, d->table_comp_off, d->ntable + 1); UPG(table_comp, d->table_comp, d->n_table_comp);
+	UPG(pt_graph, pt_graph.data(), pt_graph.size()); UPG(pt_first, pt_first.data(), pt_first.size());
+#undef UPG
+	eng->graphs_ok = g.npoint > 0;
 	return BEEP_OK;
 }
 
@@ -529,6 +578,8 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	int rc = choose_launch(eng);
 	if (rc) { beep_engine_destroy(eng); return rc; }
 	rc = approx_setup(eng, d);
+	if (rc) { beep_engine_destroy(eng); return rc; }
+	rc = graphs_setup(eng, d);
 	if (rc) { beep_engine_destroy(eng); return rc; }
 	*out = eng;
 	return BEEP_OK;
@@ -1147,6 +1198,73 @@ extern "C" int beep_likelihood_approx(BeepBatch *bt, double invT, double *L_host
 
 /* 1 when the model qualifies for beep_likelihood_approx */
 extern "C" int beep_engine_has_approx(const BeepEngine *eng) { return eng && eng->approx_ok ? 1 : 0; }
+
+/* ObservationModel::get_graph_state (obsmodel.cc:113-170) of every particle: out_host [P][npoint], the graphs' points concatenated */
+extern "C" int beep_graph_layout(const BeepEngine *eng, int *ngraph, int *npoint, int *point_off)
+{
+	if (!eng) return fail(BEEP_ERR_INVALID, "null engine");
+	if (ngraph) *ngraph = eng->graphs_ok ? eng->gx.ngraph : 0;
+	if (npoint) *npoint = eng->graphs_ok ? eng->gx.npoint : 0;
+	if (point_off && eng->graphs_ok) for (size_t k = 0; k < eng->graph_point_off.size(); k++) point_off[k] = eng->graph_point_off[k];
+	return BEEP_OK;
+}
+
+extern "C" int beep_graph_state(BeepBatch *bt, double *out_host)
+{
+	if (!bt || !out_host) return fail(BEEP_ERR_INVALID, "null argument");
+	BeepEngine *eng = bt->eng;
+	const DevModel &m = eng->dm;
+	if (!eng->graphs_ok) return fail(BEEP_ERR_UNSUPPORTED, "the description carries no graphs");
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "beep_graph_state before beep_set_params");
+	if (!bt->db.tn && !bt->db.tm) return fail(BEEP_ERR_STATE, "beep_graph_state needs a batch that keeps transnum");
+	if (eng->graphs_pop && !bt->db.poptraj) return fail(BEEP_ERR_STATE, "a graph plots populations: the batch must keep pop (BEEP_KEEP_POP)");
+	CU(cudaSetDevice(eng->device));
+	if (eng->graphs_obs) { int rc = beep_obs_loglik_dev(bt, -1, bt->db.L, nullptr); if (rc) return rc; }
+	const int P = bt->db.P, np = eng->gx.npoint;
+	const size_t need = (size_t)P * np * sizeof(double);
+	if (bt->d_approx_n < need) {
+		CU(cudaStreamSynchronize(bt->stream));
+		if (bt->d_approx) {
+			cudaFree(bt->d_approx);
+			bt->dev_allocs.erase(std::remove(bt->dev_allocs.begin(), bt->dev_allocs.end(), (void *)bt->d_approx), bt->dev_allocs.end());
+			bt->bytes -= (long long)bt->d_approx_n;
+			bt->d_approx = nullptr; bt->d_approx_n = 0;
+		}
+		double *t = nullptr;
+		cudaError_t e = cudaMalloc((void **)&t, need);
+		if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for the graph states: %s", need, cudaGetErrorString(e));
+		bt->dev_allocs.push_back(t);
+		bt->bytes += (long long)need;
+		bt->d_approx = t; bt->d_approx_n = need;
+	}
+	k_graph_state<<<dim3((unsigned)std::min((np + 7) / 8, 4096), (unsigned)P), 256, 0, bt->stream>>>(m, bt->db, eng->gx, bt->d_approx);
+	eng->launches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out_host, bt->d_approx, need, cudaMemcpyDeviceToHost, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));
+	return BEEP_OK;
+}
+
+/* Output::get_statistic (output.cc:3089-3123) per point over the P samples: mean and the 95 % credible interval by linear
+ * interpolation of the sorted values -- what the reference writes to Posterior/state/<graph>.csv (output.cc:1109-1125) */
+extern "C" int beep_graph_statistics(const double *gs_host, int P, int npoint, double *mean, double *CImin, double *CImax)
+{
+	if (!gs_host || P <= 0 || npoint <= 0 || !mean || !CImin || !CImax) return fail(BEEP_ERR_INVALID, "bad argument to beep_graph_statistics");
+	std::vector<double> v(P);
+	for (int i = 0; i < npoint; i++) {
+		double sum = 0.0;
+		for (int p = 0; p < P; p++) { v[p] = gs_host[(size_t)p * npoint + i]; sum += v[p]; }
+		mean[i] = sum / P;
+		std::sort(v.begin(), v.end());
+		if (P >= 2) {
+			unsigned k = (unsigned)((P - 1) * 0.025); double f = (P - 1) * 0.025 - k;
+			CImin[i] = v[k] * (1 - f) + v[k + 1] * f;
+			k = (unsigned)((P - 1) * 0.975); f = (P - 1) * 0.975 - k;
+			CImax[i] = v[k] * (1 - f) + v[k + 1] * f;
+		} else { CImin[i] = v[0]; CImax[i] = v[0]; }
+	}
+	return BEEP_OK;
+}
 
 /* ------------------------------------------------------------------------ */
 /* K6                                                                        */

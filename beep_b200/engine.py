@@ -43,6 +43,9 @@ _SIGNATURES = {
     "beep_latent_loglik": (ctypes.c_int, [_vp, _vp]),
     "beep_likelihood_approx": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
     "beep_engine_has_approx": (ctypes.c_int, [_vp]),
+    "beep_graph_layout": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "beep_graph_state": (ctypes.c_int, [_vp, _vp]),
+    "beep_graph_statistics": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "beep_permute": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "beep_accept": (ctypes.c_int, [_vp, _vp, _vp]),
     "beep_export_particle": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
@@ -270,6 +273,14 @@ class Batch:
         return out
 
     # -- K6 ---------------------------------------------------------------
+    def graph_state(self):
+        """ObservationModel::get_graph_state (obsmodel.cc:113-170) of every particle: [P][npoint]"""
+        ng, np_ = ctypes.c_int(), ctypes.c_int()
+        _check(self.L.beep_graph_layout(self.engine.h, ctypes.byref(ng), ctypes.byref(np_), None))
+        out = np.zeros((self.P, np_.value))
+        _check(self.L.beep_graph_state(self.h, out.ctypes.data))
+        return out
+
     def likelihood_approx(self, invT=1.0):
         """State::likelihood_approx (state_mvn_approx.cc:11-91) of every particle, parameters from set_params."""
         out = np.zeros(self.P)
@@ -438,6 +449,15 @@ def move_plan(kind, vec_all, N, rank):
         ins.append((peer, [int(x) for x in inf[w + 2:w + 2 + n]]))
         w += 2 + n
     return local, out, ins
+
+
+def graph_statistics(gs):
+    """Output::get_statistic (output.cc:3089-3123) per graph point over the samples: mean, CI min, CI max"""
+    gs = np.ascontiguousarray(gs, dtype=np.float64)
+    P, n = gs.shape
+    mean, lo, hi = np.zeros(n), np.zeros(n), np.zeros(n)
+    _check(lib().beep_graph_statistics(gs.ctypes.data, P, n, mean.ctypes.data, lo.ctypes.data, hi.ctypes.data))
+    return mean, lo, hi
 
 
 def mvn_kernel_sums(engine, var, inv_M, size, param_prop, param_last, w_last):

@@ -29,6 +29,11 @@ Every line also carries two extra objects measured AFTER the headline (they are 
              TOML inputs, priors, MVN proposals of the reference; batched engine calls; one process per GPU,
              samples exchanged by beep_allgather_scalar), with the reference's mode=abcsmc simulations/s beside it.
 
+  "map"      row N3: State::likelihood_approx of mode=map (state_mvn_approx.cc:11-91), the objective ML's CMA-ES and
+             Hessian code evaluate for many parameter vectors (ml.cc:389-413, 540-575), batched: beep_likelihood_approx on
+             the EX_C5 model (32 areas, 128 compartments, 400 steps, 1 792 observations; fixture APX_C5), 592 parameter
+             vectors per GPU through the C ABI with host buffers; the CPU restatement on one host core beside it.
+
 `--impl reference` times the UNMODIFIED reference on all host cores (kind "reference"): oracle/_ref/ref_harness
 (the reference's own objects, built here from /root/reference and shipped as a binary) runs the synthetic
 population written in the reference's own TOML/CSV formats.  Where that is not possible (binary absent, or the
@@ -403,6 +408,40 @@ def filter_extra(rank, world, local, dist, ntot=4096, reps=3):
     return out
 
 
+def map_extra(local, P=592, reps=3, with_cpu=True):
+    """likelihoods/s of the MVN-approximate likelihood (mode=map) on one GPU; see the module docstring"""
+    from beep_b200 import engine as E
+    from beep_b200.model import ModelDesc
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "APX_C5.npz")))
+    m = ModelDesc.from_prefixed(d)
+    eng = E.Engine(m, local)
+    rng = np.random.default_rng(3)
+    th = np.repeat(d["theta"][:1], P, axis=0)
+    free = np.abs(d["theta"][1] - d["theta"][0]) > 0
+    th[:, free] *= 1 + 0.03 * rng.standard_normal((P, int(free.sum())))
+    bt = eng.batch(P)
+    bt.set_params(th)
+    L = bt.likelihood_approx(1.0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        bt.set_params(th)
+        L = bt.likelihood_approx(1.0)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"workload": "EX_C5 (32 areas x 4 compartments = 128 MVN components, 400 steps, 1792 observations), State::likelihood_approx at invT=1",
+           "vectors": P, "seconds_per_batch": dt, "likelihoods_per_s": P / dt, "finite": int(np.isfinite(L).sum())}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import OracleState
+        o = OracleState(m)
+        t0 = time.perf_counter()
+        Lo = o.likelihood_approx(th[0], 1.0)
+        tc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / tc, "unit": "likelihoods/s", "cores": 1, "kind": "port", "sample": "one evaluation of the CPU restatement (oracle/beep_oracle_approx.c)",
+                               "rel_diff_vs_engine": abs(L[0] - Lo) / abs(Lo)}
+    bt.close()
+    return out
+
+
 def abcsmc_extra(rank, world, local, nonce, ntot=16384):
     """Seconds per ABC-SMC generation (abcsmc.cc:26-131) of ntot England_AS simulations in all, by the reference's own
     host code on the engine (host/_ref/BEEP_b200), one process per GPU.  Generation 0 (prior samples): with the
@@ -590,8 +629,13 @@ def main_gpu(args):
 
     value = units * world * args.steps / (ms_dev * 1e-3)
     e2e = units * world * args.steps / (ms_e2e * 1e-3)
-    extra_filter = extra_abcsmc = None
+    extra_filter = extra_abcsmc = extra_map = None
     if not args.no_extras and args.workload == "synthetic" and args.mode == "simulate":
+        if rank == 0:
+            try:
+                extra_map = map_extra(local, with_cpu=not args.no_cpu)
+            except Exception as e:
+                print(f"bench.py: map extra failed: {e!r}", file=sys.stderr)
         try:
             extra_filter = filter_extra(rank, world, local, dist)
         except Exception as e:
@@ -649,6 +693,8 @@ def main_gpu(args):
         if not args.no_cpu and world == 1:
             extra_abcsmc["cpu_baseline"] = abcsmc_reference()
         line["abcsmc"] = extra_abcsmc
+    if extra_map is not None:
+        line["map"] = extra_map
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -60,6 +60,24 @@ static void beep_export_desc(Sink &pk, const Details &details, const Data &data,
 		pk.i32(P+"dcc_info",info); pk.i32(P+"dcc_area",ar); pk.i32(P+"dcc_group",grp); pk.f64(P+"dcc_frac",fr);
 	}
 
+	{ // state graphs, obsmodel.cc:113-170
+		vector <int> ty, tb, fs, aoff, ar, doff, dps, poff, pobs; vector <double> fac;
+		aoff.push_back(0); doff.push_back(0); poff.push_back(0);
+		for(const auto &gr : data.graph){
+			ty.push_back((int)gr.type); tb.push_back(gr.datatable); fac.push_back(gr.factor); fs.push_back(xd_u2i(gr.factor_spline));
+			for(auto c : gr.area) ar.push_back(c);
+			aoff.push_back(ar.size());
+			for(auto dp : gr.dp_sel) dps.push_back(dp);
+			doff.push_back(dps.size());
+			for(const auto &pt : gr.point) pobs.push_back(pt.obs);
+			poff.push_back(pobs.size());
+		}
+		pk.i32(P+"graph_step",vector <int>(1,(int)details.graph_step));
+		pk.i32(P+"graph_type",ty); pk.i32(P+"graph_table",tb); pk.f64(P+"graph_factor",fac); pk.i32(P+"graph_factor_spline",fs);
+		pk.i32(P+"graph_area_off",aoff); pk.i32(P+"graph_area",ar); pk.i32(P+"graph_dp_off",doff); pk.i32(P+"graph_dp",dps);
+		pk.i32(P+"graph_point_off",poff); pk.i32(P+"graph_point_obs",pobs);
+	}
+
 	{ // Dirichlet groups, model.cc:2685-2695
 		vector <int> off, th; vector <double> frac; off.push_back(0);
 		for(const auto &dir : model.dirichlet){

@@ -311,6 +311,17 @@ int beep_mvn_kernel_sums(BeepEngine *eng, int nvar, int nparam, const int *var, 
 int beep_likelihood_approx(BeepBatch *batch, double invT, double *L_host);
 int beep_engine_has_approx(const BeepEngine *eng);
 
+/* Posterior state summaries straight from the device buffers.
+ * beep_graph_state replaces ObservationModel::get_graph_state (obsmodel.cc:113-170) for
+ * every particle of a batch that keeps its trajectory (and pop, when a graph plots
+ * compartments): out_host [P][npoint], the points of the graphs of data.graph
+ * concatenated (beep_graph_layout: point_off[ngraph+1]).  beep_graph_statistics is
+ * Output::get_statistic (output.cc:3089-3123) per point over the P samples -- the Mean /
+ * 95% CI min / 95% CI max columns of Posterior/state/<graph>.csv (output.cc:1109-1125).  */
+int beep_graph_layout(const BeepEngine *eng, int *ngraph, int *npoint, int *point_off);
+int beep_graph_state(BeepBatch *batch, double *out_host);
+int beep_graph_statistics(const double *gs_host, int P, int npoint, double *mean, double *CImin, double *CImax);
+
 /* Test hooks: the device samplers of beep_rng.h on n independent streams
  * (seed, stream_id, i), for the host/device bit-exactness tests.            */
 int beep_test_poisson(uint64_t seed, uint64_t stream_id, const double *lam_host, int n, int32_t *out_host);

@@ -898,6 +898,56 @@ void oracle_mvn_kernel_sums(int nvar, int nparam, const int32_t *var, const doub
 }
 
 /* ---------------------------------------------------------------------- */
+/* ObservationModel::get_graph_state, obsmodel.cc:113-170: the series behind */
+/* the Posterior/state files, one block per graph                            */
+/* ---------------------------------------------------------------------- */
+int oracle_graph_npoints(const BeepModelDesc *m, int g)
+{
+	if (m->graph_type[g] == 1) return m->graph_point_off[g + 1] - m->graph_point_off[g];
+	int gs = m->graph_step[0], n = 0;
+	for (int sett = 0; sett < m->T - gs; sett += gs) n++;
+	return n;
+}
+
+void oracle_graph_state(const OracleState *s, double *out)
+{
+	const BeepModelDesc *m = s->m;
+	int ng = (int)m->n_graph_type, T = m->T, gs = m->graph_step[0];
+	double *obs_value = dalloc(m->nobs);
+	oracle_obs_values(s, obs_value);
+	long k = 0;
+	for (int g = 0; g < ng; g++) {
+		int dt = m->graph_table[g], spl = m->graph_factor_spline[g];
+		if (m->graph_type[g] == 0) {
+			double fac_trans = m->graph_factor[g] * (double)m->spu / gs;
+			double fac_pop = m->graph_factor[g] * 1.0 / gs;
+			for (int sett = 0; sett < T - gs; sett += gs) {
+				double sum = 0.0;
+				for (int step = 0; step < gs; step++) {
+					int sett2 = sett + step;
+					for (int ia = m->graph_area_off[g]; ia < m->graph_area_off[g + 1]; ia++)
+						for (int id = m->graph_dp_off[g]; id < m->graph_dp_off[g + 1]; id++) {
+							int c = m->graph_area[ia], dp = m->graph_dp[id];
+							for (int q = m->table_trans_off[dt]; q < m->table_trans_off[dt + 1]; q++) {
+								double num = fac_trans * TN(s, sett2, c, m->table_trans[q], dp);
+								if (spl < 0) sum += num; else sum += num * s->disc_spline[spl * T + sett2];
+							}
+							for (int q = m->table_comp_off[dt]; q < m->table_comp_off[dt + 1]; q++) {
+								double num = fac_pop * POP(s, sett2, c, m->table_comp[q], dp);
+								if (spl < 0) sum += num; else sum += num * s->disc_spline[spl * T + sett2];
+							}
+						}
+				}
+				out[k++] = sum;
+			}
+		} else {
+			for (int q = m->graph_point_off[g]; q < m->graph_point_off[g + 1]; q++) out[k++] = obs_value[m->graph_point_obs[q]];
+		}
+	}
+	free(obs_value);
+}
+
+/* ---------------------------------------------------------------------- */
 /* MVN-approximate likelihood (mode=map), state_mvn_approx.cc               */
 /* ---------------------------------------------------------------------- */
 #include "beep_oracle_approx.c"

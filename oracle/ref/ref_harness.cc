@@ -182,6 +182,10 @@ static void dump_traj(Pack &pk, const string &pre, const State &st, const Observ
 	pk.f64(pre+"obs_value",obsmodel.get_obs_value(&st));
 	pk.f64(pre+"EF_datatable",obsmodel.get_EF_datatable(&st));
 	pk.scalar_d(pre+"Li",st.likelihood());
+	if(getenv("BEEP_HARNESS_GRAPHS")){                                  // ObservationModel::get_graph_state, obsmodel.cc:113-170
+		vector <double> gs; for(const auto &g : obsmodel.get_graph_state(&st)) for(auto v : g) gs.push_back(v);
+		pk.f64(pre+"graph_state",gs);
+	}
 }
 
 int main(int argc, char **argv)

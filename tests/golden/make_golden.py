@@ -89,6 +89,12 @@ APPROX = {"APX_A1": ("examples/EX_A1.toml", ["mode=map"], 3, 101),    # one area
           "APX_C2": ("examples/EX_C2.toml", ["mode=map"], 3, 109),    # ten areas, covariates
           "APX_D3": ("examples/EX_D3.toml", ["mode=map"], 3, 113),    # level effects
           "APX_C5": ("examples/EX_C5.toml", ["mode=map"], 3, 127)}    # 32 areas coupled by the geographic mixing matrix (128 compartments)
+# ObservationModel::get_graph_state (obsmodel.cc:113-170), the series behind the Posterior/state files: the harness adds the
+# graphs' points of the deterministic and the stochastic trajectory (BEEP_HARNESS_GRAPHS); descriptions carry the graph fields
+GRAPHS = {"GRS_C4": ("examples/EX_C4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 131),    # four age groups: a graph per group
+          "GRS_C2": ("examples/EX_C2.toml", ["mode=mcmcmbp", "nsample=10"], 2, 137),    # ten areas
+          "GRS_B6": ("examples/EX_B6.toml", ["mode=mcmcmbp", "nsample=10"], 2, 139),    # observation factor spline
+          "GRS_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 149)}    # marginal data
 SUBST = {"England_AS": [('obsmodel="scale"', 'obsmodel="normal 10%"')]}
 BIG = {"England_AS"}
 
@@ -164,6 +170,7 @@ def main():
     BIG.add("SYN_A12")
     CASES.update(OBSPATCH)
     CASES.update(APPROX)
+    CASES.update(GRAPHS)
     # demographic change (data.democat_change, state.cc:339-376): no input of the reference uses it, so two of its
     # examples are extended IN THE SCRATCH TREE -- EX_C3 (one area, Sex) and EX_C2 (ten areas, Sex added to its
     # population file; the change applies to all of them) -- with a table of category fractions over time
@@ -191,6 +198,8 @@ def main():
             env["BEEP_HARNESS_BIG"] = "1"      # skip pop / Imap / Idiag dumps
         if name in APPROX:
             env["BEEP_HARNESS_APPROX"] = "1"   # invT = 1
+        if name in GRAPHS:
+            env["BEEP_HARNESS_GRAPHS"] = "1"
         r = subprocess.run(cmd, cwd=work, capture_output=True, text=True, env=env)
         if r.returncode != 0 or not os.path.exists(bpk):
             print(f"{name}: harness FAILED\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")

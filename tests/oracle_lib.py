@@ -53,6 +53,8 @@ def lib():
         L.oracle_log_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.oracle_mvn_kernel_sums.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_graph_npoints.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.oracle_graph_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_likelihood_approx.restype = ctypes.c_double
         L.oracle_likelihood_approx.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L
@@ -137,6 +139,14 @@ class OracleState:
 
     def latent_loglik(self):
         return self.L.oracle_latent_loglik(self.h)
+
+    def graph_state(self):
+        """ObservationModel::get_graph_state (obsmodel.cc:113-170), the graphs' points concatenated"""
+        m = self.model
+        n = sum(self.L.oracle_graph_npoints(ctypes.addressof(m.c), g) for g in range(m.graph_type.size))
+        out = np.zeros(n)
+        self.L.oracle_graph_state(self.h, out.ctypes.data)
+        return out
 
     def likelihood_approx(self, theta, invT=1.0, want_state=False):
         """State::likelihood_approx (state_mvn_approx.cc:11-91); with want_state also the mean populations [T+1][A][C][D]
