@@ -38,6 +38,7 @@ static int fail(int code, const char *fmt, ...)
 
 extern "C" const char *beep_last_error(void) { return g_err.c_str(); }
 extern "C" int beep_version(void) { return 100; }
+extern "C" int beep_desc_size(void) { return (int)sizeof(BeepModelDesc); }
 
 /* ------------------------------------------------------------------------ */
 /* engine                                                                    */
@@ -785,7 +786,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	if (eng->sync_mode == SYNC_GRID) BA(b.sched, ((size_t)P + 1) * 16);
 	else if (eng->sync_mode == SYNC_NONE) BA(b.sched, 16);              /* the tile counter of the persistent warps */
 	BA(bt->d_scratch, (size_t)P * std::max<size_t>(k5_chunks((size_t)m.T * m.A * m.J * m.D), (size_t)OBS_CHUNKS * (1 + std::max(m.ntable, 0))));
-	BA(bt->d_map, P); BA(bt->d_flag, P);
+	BA(bt->d_map, 2 * (size_t)P); BA(bt->d_flag, P);
 	{
 		std::vector<unsigned long long> ids(P);
 		for (int i = 0; i < P; i++) ids[i] = (unsigned long long)i;
@@ -1269,34 +1270,62 @@ extern "C" int beep_graph_statistics(const double *gs_host, int P, int npoint, d
 /* ------------------------------------------------------------------------ */
 /* K6                                                                        */
 /* ------------------------------------------------------------------------ */
-template <typename Tp>
-static int gather_inplace(BeepBatch *bt, Tp *arr, size_t n, const unsigned *d_map)
+static int permute_scratch(BeepBatch *bt, size_t need)
 {
-	if (!arr || n == 0) return BEEP_OK;
-	const int P = bt->db.P;
-	size_t need = (size_t)P * n * sizeof(Tp);
-	if (bt->d_tmp_n < need) {
-		/* one scratch per batch, as large as the largest slab ever permuted: the smaller one is released first
-		 * (stream-ordered after the copies that used it) and the batch's byte count follows */
-		CU(cudaStreamSynchronize(bt->stream));
-		if (bt->d_tmp) {
-			cudaFree(bt->d_tmp);
-			bt->dev_allocs.erase(std::remove(bt->dev_allocs.begin(), bt->dev_allocs.end(), (void *)bt->d_tmp), bt->dev_allocs.end());
-			bt->bytes -= (long long)bt->d_tmp_n;
-			bt->d_tmp = nullptr; bt->d_tmp_n = 0;
-		}
-		double *t = nullptr;
-		cudaError_t e = cudaMalloc((void **)&t, need);
-		if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for permute scratch: %s", need, cudaGetErrorString(e));
-		bt->dev_allocs.push_back(t);
-		bt->bytes += (long long)need;
-		bt->d_tmp = t; bt->d_tmp_n = need;
+	if (bt->d_tmp_n >= need) return BEEP_OK;
+	/* one scratch per batch, as large as the largest set of slabs ever moved: the smaller one is released first
+	 * (stream-ordered after the copies that used it) and the batch's byte count follows */
+	CU(cudaStreamSynchronize(bt->stream));
+	if (bt->d_tmp) {
+		cudaFree(bt->d_tmp);
+		bt->dev_allocs.erase(std::remove(bt->dev_allocs.begin(), bt->dev_allocs.end(), (void *)bt->d_tmp), bt->dev_allocs.end());
+		bt->bytes -= (long long)bt->d_tmp_n;
+		bt->d_tmp = nullptr; bt->d_tmp_n = 0;
 	}
+	double *t = nullptr;
+	cudaError_t e = cudaMalloc((void **)&t, need);
+	if (e != cudaSuccess) return fail(BEEP_ERR_CUDA, "cudaMalloc(%zu bytes) for permute scratch: %s", need, cudaGetErrorString(e));
+	bt->dev_allocs.push_back(t);
+	bt->bytes += (long long)need;
+	bt->d_tmp = t; bt->d_tmp_n = need;
+	return BEEP_OK;
+}
+
+/* the per-particle tables of a list in two launches (gather the moved slots' sources, write them into place) */
+struct SlabAdder {
+	SlabList L;
+	SlabAdder() { memset(&L, 0, sizeof L); }
+	template <typename Tp> void add(Tp *p, size_t n) { if (p && n && L.n < 24) { L.ptr[L.n] = (void *)p; L.words[L.n] = (unsigned)(n * sizeof(Tp) / 4); L.off[L.n + 1] = L.off[L.n] + L.words[L.n]; L.n++; } }
+};
+static int gather_multi(BeepBatch *bt, const SlabList &L, const unsigned *d_map, int nm)
+{
+	if (L.n == 0 || nm == 0) return BEEP_OK;
+	int rc = permute_scratch(bt, (size_t)L.off[L.n] * nm * 4);
+	if (rc) return rc;
+	unsigned wmax = 0;
+	for (int s = 0; s < L.n; s++) wmax = std::max(wmax, L.words[s]);
+	const unsigned nz = std::max(1u, std::min(64u, (wmax + 4095u) / 4096u));
+	k_gather_multi<<<dim3(nm, L.n, nz), 256, 0, bt->stream>>>(L, (unsigned *)bt->d_tmp, d_map, nm);
+	k_scatter_multi<<<dim3(nm, L.n, nz), 256, 0, bt->stream>>>(L, (const unsigned *)bt->d_tmp, d_map + nm, nm);
+	bt->eng->launches += 2;
+	CU(cudaGetLastError());
+	return BEEP_OK;
+}
+
+/* arr[dst[k]] <- arr[src[k]] for the nm slots that change (d_map: nm sources, then nm destinations).  The sources are read
+ * into a compact scratch first, so chains of copies are well defined (mpi.cc:81-165); slots that keep their particle cost
+ * nothing, and the scratch holds nm slabs, not the whole array */
+template <typename Tp>
+static int gather_inplace(BeepBatch *bt, Tp *arr, size_t n, const unsigned *d_map, int nm)
+{
+	if (!arr || n == 0 || nm == 0) return BEEP_OK;
+	int rc0 = permute_scratch(bt, (size_t)nm * n * sizeof(Tp));
+	if (rc0) return rc0;
 	Tp *tmp = (Tp *)bt->d_tmp;
-	CU(cudaMemcpyAsync(tmp, arr, need, cudaMemcpyDeviceToDevice, bt->stream));
 	int gx = (int)std::min<size_t>((n + 255) / 256, 1024);
-	k_gather_slab<Tp><<<dim3(P, gx), 256, 0, bt->stream>>>(arr, tmp, d_map, n, P);
-	bt->eng->launches++;
+	k_gather_slab<Tp><<<dim3(nm, gx), 256, 0, bt->stream>>>(tmp, arr, d_map, n, nm);
+	k_scatter_slab<Tp><<<dim3(nm, gx), 256, 0, bt->stream>>>(arr, tmp, d_map + nm, n);
+	bt->eng->launches += 2;
 	CU(cudaGetLastError());
 	return BEEP_OK;
 }
@@ -1310,30 +1339,32 @@ extern "C" int beep_permute(BeepBatch *bt, const uint32_t *src_of_host, int what
 	CU(cudaSetDevice(bt->eng->device));
 	int rc;
 	if (what != BEEP_PERMUTE_SECTION_STATE && bt->theta_dirty && (rc = launch_set_param(bt))) return rc;   /* derived tables move with the particles */
+	/* the slots that receive another particle: sources first, destinations after them */
+	std::vector<unsigned> mv;
+	for (int p = 0; p < P; p++) if (src_of_host[p] != 0xFFFFFFFFu && src_of_host[p] != (unsigned)p) mv.push_back(src_of_host[p]);
+	const int nm = (int)mv.size();
+	if (nm == 0) return BEEP_OK;
+	for (int p = 0; p < P; p++) if (src_of_host[p] != 0xFFFFFFFFu && src_of_host[p] != (unsigned)p) mv.push_back((unsigned)p);
 	CU(cudaStreamSynchronize(bt->stream));
-	CU(cudaMemcpyAsync(bt->d_map, src_of_host, P * sizeof(unsigned), cudaMemcpyHostToDevice, bt->stream));
+	CU(cudaMemcpyAsync(bt->d_map, mv.data(), mv.size() * sizeof(unsigned), cudaMemcpyHostToDevice, bt->stream));
+	CU(cudaStreamSynchronize(bt->stream));                     /* mv is a local */
 	const DevBatch &b = bt->db;
-	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.CDp, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.popi, (size_t)m.A * m.CDp4, bt->d_map))) return rc;
+	if ((rc = gather_inplace(bt, b.pop_cur, (size_t)m.A * m.CDp, bt->d_map, nm))) return rc;
+	if ((rc = gather_inplace(bt, b.popi, (size_t)m.A * m.CDp4, bt->d_map, nm))) return rc;
 	if (what == BEEP_PERMUTE_SECTION_STATE) return BEEP_OK;      /* mpi.cc:286-288: pop (Imap/Idiag are re-derived from it) */
 	const size_t TAJD = (size_t)m.T * m.A * m.J * m.D;
-	if ((rc = gather_inplace(bt, b.theta, m.nparam, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.pd, m.nparam, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.transrate, (size_t)m.J * m.D, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.disc_spline, (size_t)m.nspline * m.T, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.sus, m.D, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.areafactor, (size_t)m.period * m.A, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.betaR, (size_t)m.S * m.nR * m.T, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.infco, m.C, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.infmask, 1, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.etab, (size_t)m.nefoi * m.T, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.crate, ((size_t)m.J * m.D + 31) & ~(size_t)31, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.inflist, (size_t)m.C + 1, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.poptraj, (size_t)m.T * m.A * m.C * m.D, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.obs_partial, m.nslot, bt->d_map))) return rc;
-	if ((rc = gather_inplace(bt, b.obs_val, m.nobs, bt->d_map))) return rc;
+	{
+		/* the parameters and the derived tables of K0, the observation sums: one pair of launches */
+		SlabAdder sl;
+		sl.add(b.theta, m.nparam); sl.add(b.pd, m.nparam); sl.add(b.transrate, (size_t)m.J * m.D); sl.add(b.disc_spline, (size_t)m.nspline * m.T);
+		sl.add(b.sus, m.D); sl.add(b.areafactor, (size_t)m.period * m.A); sl.add(b.betaR, (size_t)m.S * m.nR * m.T); sl.add(b.infco, m.C);
+		sl.add(b.infmask, 1); sl.add(b.etab, (size_t)m.nefoi * m.T); sl.add(b.crate, ((size_t)m.J * m.D + 31) & ~(size_t)31); sl.add(b.inflist, (size_t)m.C + 1);
+		sl.add(b.obs_partial, m.nslot); sl.add(b.obs_val, m.nobs);
+		if ((rc = gather_multi(bt, sl.L, bt->d_map, nm))) return rc;
+	}
+	if ((rc = gather_inplace(bt, b.tn, TAJD, bt->d_map, nm))) return rc;
+	if ((rc = gather_inplace(bt, b.tm, TAJD, bt->d_map, nm))) return rc;
+	if ((rc = gather_inplace(bt, b.poptraj, (size_t)m.T * m.A * m.C * m.D, bt->d_map, nm))) return rc;
 	return BEEP_OK;
 }
 

@@ -1664,6 +1664,33 @@ __global__ void k_gather_slab(Tp *dst, const Tp *src, const unsigned *map, size_
 	Tp *dp = dst + (size_t)p * n;
 	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) dp[i] = sp[i];
 }
+/* dst[map[k]] <- src[k]: the compact scratch of the moved slots written into place */
+template <typename Tp>
+__global__ void k_scatter_slab(Tp *dst, const Tp *src, const unsigned *map, size_t n)
+{
+	const Tp *sp = src + (size_t)blockIdx.x * n;
+	Tp *dp = dst + (size_t)map[blockIdx.x] * n;
+	for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) dp[i] = sp[i];
+}
+/* the same for a LIST of per-particle tables at once (the derived tables of K0 move with a particle: a dozen small slabs):
+ * block (k, s, chunk) copies a piece of slab s of moved slot k, as 32-bit words */
+struct SlabList { void *ptr[24]; unsigned words[24]; unsigned long long off[25]; int n; };
+__global__ void k_gather_multi(const SlabList L, unsigned *tmp, const unsigned *map, int nm)
+{
+	const int k = blockIdx.x, s = blockIdx.y;
+	const unsigned w = L.words[s];
+	const unsigned *sp = (const unsigned *)L.ptr[s] + (size_t)map[k] * w;
+	unsigned *dp = tmp + L.off[s] * (unsigned long long)nm + (size_t)k * w;
+	for (size_t i = blockIdx.z * (size_t)blockDim.x + threadIdx.x; i < w; i += (size_t)gridDim.z * blockDim.x) dp[i] = sp[i];
+}
+__global__ void k_scatter_multi(const SlabList L, const unsigned *tmp, const unsigned *map, int nm)
+{
+	const int k = blockIdx.x, s = blockIdx.y;
+	const unsigned w = L.words[s];
+	const unsigned *sp = tmp + L.off[s] * (unsigned long long)nm + (size_t)k * w;
+	unsigned *dp = (unsigned *)L.ptr[s] + (size_t)map[k] * w;
+	for (size_t i = blockIdx.z * (size_t)blockDim.x + threadIdx.x; i < w; i += (size_t)gridDim.z * blockDim.x) dp[i] = sp[i];
+}
 /* dst[p] <- src[p] where flag[p] != 0 */
 template <typename Tp>
 __global__ void k_copy_flagged(Tp *dst, const Tp *src, const unsigned char *flag, size_t n, int P)

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "beep_latent_loglik": (ctypes.c_int, [_vp, _vp]),
     "beep_likelihood_approx": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
     "beep_engine_has_approx": (ctypes.c_int, [_vp]),
+    "beep_desc_size": (ctypes.c_int, []),
     "beep_graph_layout": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "beep_graph_state": (ctypes.c_int, [_vp, _vp]),
     "beep_graph_statistics": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
@@ -144,6 +145,8 @@ class Engine:
     def __init__(self, model, device=0):
         self.model = model
         self.L = lib()
+        if self.L.beep_desc_size() != ctypes.sizeof(model.c):
+            raise BeepError(-1, "BeepModelDesc of include/beep_model_fields.def and of libbeep_b200.so differ: rebuild the library")
         h = _vp()
         _check(self.L.beep_engine_create(ctypes.addressof(model.c), device, ctypes.byref(h)))
         self.h = h

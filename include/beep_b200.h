@@ -101,6 +101,9 @@ enum { BEEP_PERMUTE_FULL = 0, BEEP_PERMUTE_SECTION_STATE = 1 };
 
 const char *beep_last_error(void);
 int beep_version(void);
+/* sizeof(BeepModelDesc) the library was built with: a caller compiled against another beep_model_fields.def must not
+ * pass its description (the C++ wrapper checks)                                                        */
+int beep_desc_size(void);
 
 /* Replaces: construction of Data/Model tables per MPI rank (mpi.cc:26-77
  * broadcast) -- uploads the read-only tables once to `device`.              */

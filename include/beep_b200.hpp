@@ -27,7 +27,11 @@ inline void check(int rc) { if (rc != BEEP_OK) throw Error(rc, beep_last_error()
 
 class Engine {
 public:
-	Engine(const BeepModelDesc &desc, int device = 0) { check(beep_engine_create(&desc, device, &h_)); }
+	Engine(const BeepModelDesc &desc, int device = 0)
+	{
+		if (beep_desc_size() != (int)sizeof(BeepModelDesc)) throw Error(BEEP_ERR_INVALID, "BeepModelDesc of this program and of libbeep_b200.so differ (rebuild against the library's beep_model_fields.def)");
+		check(beep_engine_create(&desc, device, &h_));
+	}
 	~Engine() { beep_engine_destroy(h_); }
 	Engine(const Engine &) = delete;
 	Engine &operator=(const Engine &) = delete;

@@ -39,7 +39,23 @@ print(f"parameter proposal (set_param + replay on fixed events + likelihood): {t
 src = np.roll(np.arange(P, dtype=np.uint32), 1)
 t = timed(lambda: a.permute(src, E.PERMUTE_FULL))
 slab = cells * 12 + P * m.A * m.C * m.D * 8
-print(f"K6 permute (every particle copied, out of place): {t*1e3:.2f} ms, {2*slab/t/1e9:.0f} GB/s read+write")
+print(f"K6 permute (every particle replaced: gather into a compact scratch, write into place): {t*1e3:.2f} ms, {2*slab/t/1e9:.0f} GB/s read+write of the slabs once each, {a.engine.launch_count} launches so far")
+n0 = a.engine.launch_count
+rng = np.random.default_rng(1)
+src = np.sort(rng.integers(0, P, size=P)).astype(np.uint32)          # a multinomial resampling: about 1/e of the slots receive another particle
+keep = np.zeros(P, dtype=bool); keep[np.unique(src)] = True
+srcm = np.where(keep, np.arange(P), 0).astype(np.uint32)
+dup = [s_ for s_ in src if True]
+free = [i for i in range(P) if not keep[i]]
+extra = []
+seen = set()
+for s_ in src:
+    if int(s_) in seen: extra.append(int(s_))
+    seen.add(int(s_))
+for i, s_ in zip(free, extra): srcm[i] = s_
+nmoved = int((srcm != np.arange(P)).sum())
+t = timed(lambda: a.permute(srcm, E.PERMUTE_FULL), reps=1)
+print(f"K6 permute after a multinomial resampling ({nmoved} of {P} slots receive another particle): {t*1e3:.2f} ms, {(a.engine.launch_count - n0) // 2} launches per call")
 acc = np.ones(P, dtype=np.uint8)
 t = timed(lambda: a.accept_from(b, acc))
 print(f"K6 accept (swap_initial_propose_state for every chain): {t*1e3:.2f} ms, {2*slab/t/1e9:.0f} GB/s read+write")
