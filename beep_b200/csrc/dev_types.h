@@ -146,6 +146,9 @@ struct DevModel {
 	const unsigned *cell_tab;   /* [J*D] packed (pop offset | tr<<12 | dp<<18 | kind<<24) */
 	const double *table_threshold;
 	const int *section_ti, *section_tf;
+	/* model modifications of mode=prediction (model.modelmod): null = none.  Models that carry one run the general tile kernel */
+	int has_mod;
+	const double *mod_tmean, *mod_beta, *mod_efoi, *mod_spline_mult, *mod_spline_set;
 };
 
 struct DevBatch {

@@ -68,6 +68,7 @@ struct BeepEngine {
 	bool graphs_ok = false, graphs_pop = false, graphs_obs = false;
 	DevGraphs gx;
 	std::vector<int> graph_point_off;
+	std::vector<double> h_mod_beta;    /* host copy: beep_get_derived expands beta to the reference's [S][A][T] */
 };
 
 struct BeepBatch {
@@ -156,6 +157,7 @@ static int approx_setup(BeepEngine *eng, const BeepModelDesc *d)
 	if (d->n_table_type != d->ntable || d->ntable == 0) { eng->approx_why = "the description carries no table_type (written before the approximate likelihood existed)"; return BEEP_OK; }
 	if (d->S != 1) { eng->approx_why = "the approximate likelihood handles one strain (state_mvn_approx.cc:1208)"; return BEEP_OK; }
 	if (d->n_dcc_info > 0) { eng->approx_why = "the approximate likelihood ignores demographic changes"; return BEEP_OK; }
+	if (d->n_mod_transmean || d->n_mod_beta || d->n_mod_efoi) { eng->approx_why = "model modifications belong to mode=prediction, the approximate likelihood to mode=map"; return BEEP_OK; }
 	const int n = A * C * D, nt = A * J * D, start = d->trans_from[d->infection_trans];
 	if ((long long)n * std::max(n, nt) >= (1ll << 30)) { eng->approx_why = "too many compartments for the approximate likelihood"; return BEEP_OK; }
 	std::vector<int> wo, ws, wo_of(n, -1);
@@ -316,7 +318,7 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 	m.has_region = d->n_region_effect_param > 0; m.has_area_eff = d->n_area_effect_param > 0;
 
 	const int T = m.T, A = m.A, C = m.C, J = m.J, D = m.D, G = m.G, S = m.S, Dq = m.Dq;
-	if (d->n_unsupported > 0) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "the analysis uses prediction-mode model modifications (state.cc:446-453), which are outside the hot-path scope"); }
+	if (d->n_unsupported > 0) { beep_engine_destroy(eng); return fail(BEEP_ERR_UNSUPPORTED, "the exporter marked the analysis as using a feature outside the hot-path scope"); }
 	NEED(T > 0 && A > 0 && C > 0 && J > 0 && D > 0 && G > 0 && S > 0 && Dq > 0 && m.spu > 0 && m.period > 0, "non-positive dimension");
 	NEED(D == S * Dq, "D (%d) != S*Dq (%d*%d)", D, S, Dq);
 	NEED(m.itr >= 0 && m.itr < J, "infection_trans out of range");
@@ -575,6 +577,20 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		UPV(cell_off, cell_cnt); UPV(cell_ent, ent);
 		UP(table_threshold, d->table_threshold, m.ntable);
 		UPV(section_ti, eng->section_ti); UPV(section_tf, eng->section_tf);
+	}
+	{
+		/* model modifications of mode=prediction (model.cc:1440-1585): absent arrays = no modification */
+		const size_t TAJD = (size_t)T * A * J * D, TAS = (size_t)T * A * S, NT = (size_t)m.nspline * T;
+		NEED(d->n_mod_transmean == 0 || (size_t)d->n_mod_transmean == TAJD, "mod_transmean has %lld entries, not T*A*J*D", (long long)d->n_mod_transmean);
+		NEED(d->n_mod_beta == 0 || (size_t)d->n_mod_beta == TAS, "mod_beta has %lld entries, not T*A*S", (long long)d->n_mod_beta);
+		NEED(d->n_mod_efoi == 0 || (size_t)d->n_mod_efoi == TAS, "mod_efoi has %lld entries, not T*A*S", (long long)d->n_mod_efoi);
+		NEED((d->n_mod_spline_mult == 0 && d->n_mod_spline_set == 0) || ((size_t)d->n_mod_spline_mult == NT && (size_t)d->n_mod_spline_set == NT), "mod_spline_mult / mod_spline_set must both have nspline*T entries");
+		if (d->n_mod_transmean) UP(mod_tmean, d->mod_transmean, TAJD);
+		if (d->n_mod_beta) { UP(mod_beta, d->mod_beta, TAS); eng->h_mod_beta.assign(d->mod_beta, d->mod_beta + TAS); }
+		if (d->n_mod_efoi) UP(mod_efoi, d->mod_efoi, TAS);
+		if (d->n_mod_spline_mult) { UP(mod_spline_mult, d->mod_spline_mult, NT); UP(mod_spline_set, d->mod_spline_set, NT); }
+		m.has_mod = (m.mod_tmean || m.mod_beta || m.mod_efoi) ? 1 : 0;     /* spline modifications live in K0 alone */
+		if (m.has_mod) { eng->chunk_model = false; eng->dense_m = false; }
 	}
 	int rc = choose_launch(eng);
 	if (rc) { beep_engine_destroy(eng); return rc; }
@@ -902,7 +918,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	a.nwarp = eng->nwarp; a.chunk = 1; a.invG = 0; memset(&a.Ls, 0, sizeof a.Ls);
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));
 	/* tile_step_fast: one strain, dp == age, several ages, stochastic, no population trajectory */
-	a.fast = (m.ndcc == 0 && m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
+	a.fast = (m.ndcc == 0 && !m.has_mod && m.S == 1 && m.age_fast && m.Dq == m.G && m.G > 1 && m.stochastic && !(bt->db.flags & BEEP_KEEP_POP)) ? 1 : 0;
 	if (const char *nf = getenv("BEEP_TRAJ_NOFAST")) if (atoi(nf)) a.fast = 0;
 	for (int tr = 0; tr < 32; tr++) { a.tfrom[tr] = tr < m.J ? eng->h_from[tr] : 0; a.tto[tr] = tr < m.J ? eng->h_to[tr] : 0; a.tkind[tr] = tr < m.J ? eng->h_kind[tr] : 2; }
 	const int P = bt->db.P;
@@ -1064,6 +1080,22 @@ extern "C" int beep_replay(BeepBatch *bt)
 	if (m.stochastic ? !bt->db.tn : !bt->db.tm) return fail(BEEP_ERR_STATE, "beep_replay needs a batch that keeps transnum");
 	CU(cudaSetDevice(bt->eng->device));
 	return launch_traj(bt, MODE_REPLAY, 0, m.T, 0, nullptr, nullptr);
+}
+
+/* The same for the steps [ti, tf) only: afterwards the batch stands at step tf and beep_simulate(batch, tf, ...) carries on from
+ * the replayed population -- State::load followed by State::simulate(pred_start, ndivision) of mode=prediction
+ * (Simulate::model_modification, simulate.cc:141-165) */
+extern "C" int beep_replay_range(BeepBatch *bt, int ti, int tf)
+{
+	if (!bt) return fail(BEEP_ERR_INVALID, "null batch");
+	const DevModel &m = bt->eng->dm;
+	if (!bt->have_params) return fail(BEEP_ERR_STATE, "beep_replay_range before parameters were set");
+	if (m.stochastic ? !bt->db.tn : !bt->db.tm) return fail(BEEP_ERR_STATE, "beep_replay_range needs a batch that keeps transnum");
+	if (ti < 0 || tf > m.T || ti >= tf) return fail(BEEP_ERR_INVALID, "bad step range [%d,%d)", ti, tf);
+	if (ti != 0 && ti != bt->cur_t) return fail(BEEP_ERR_STATE, "replay(%d,..) but the batch stands at step %d", ti, bt->cur_t);
+	CU(cudaSetDevice(bt->eng->device));
+	if (bt->theta_dirty) { int rc = launch_set_param(bt); if (rc) return rc; }
+	return launch_traj(bt, MODE_REPLAY, ti, tf, 0, nullptr, nullptr);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1551,6 +1583,9 @@ extern "C" int beep_get_derived(BeepBatch *bt, int slot, int which, double *out,
 		CU(cudaStreamSynchronize(bt->stream));
 		for (int st = 0; st < m.S; st++) for (int c = 0; c < m.A; c++)
 			memcpy(out + ((size_t)st * m.A + c) * m.T, g.data() + ((size_t)st * m.nR + rg[c]) * m.T, m.T * sizeof(double));
+		if (!bt->eng->h_mod_beta.empty())                              /* model.cc:1349-1357 */
+			for (int st = 0; st < m.S; st++) for (int c = 0; c < m.A; c++) for (int t = 0; t < m.T; t++)
+				out[((size_t)st * m.A + c) * m.T + t] *= bt->eng->h_mod_beta[((size_t)t * m.A + c) * m.S + st];
 		return BEEP_OK;
 	}
 	case BEEP_DERIVED_AGEFACTOR: {

@@ -199,6 +199,14 @@ __global__ void __launch_bounds__(K0_THREADS) k_set_param(DevModel m, DevBatch b
 		}
 	}
 	__syncthreads();
+	if (m.mod_spline_mult) {                                   /* model.cc:1044-1050: modifications of mode=prediction */
+		for (int i = tid; i < m.nspline * T; i += nth) {
+			ds[i] *= m.mod_spline_mult[i];
+			const double set = m.mod_spline_set[i];
+			if (set != 999999999.0) ds[i] = set;
+		}
+		__syncthreads();
+	}
 	/* per-cell multiplier table of the trajectory kernel's scan */
 	{
 		const int JD32 = (J * D + 31) & ~31;
@@ -644,9 +652,11 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 				}
 			}
 			double be = tc.betaR[(st * m.nR + tc.rg) * T + t];
+			if (m.mod_beta) be *= m.mod_beta[((size_t)t * A + tc.c) * S + st];      /* model.cc:1349-1357 */
 			be *= afv;
 			const int ie = (st == 0) ? tc.ie0 : m.efoi_ref[st * A + tc.c];
-			const double et = tc.etab[ie * T + t];
+			double et = tc.etab[ie * T + t];
+			if (m.mod_efoi) et *= m.mod_efoi[((size_t)t * A + tc.c) * S + st];       /* state.cc:415 */
 			if (fastdp) {
 				if (lane < G) foi[st * Dq + lane] = be * nv + et * m.efoi_agedist[ie * G + lane];
 			} else {
@@ -687,6 +697,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 				if (kind == 0) mean = dt * popu * r;
 				else if (kind == 1) { const int dp = (w >> 18) & 63; mean = dt * popu * tc.sus[dp] * foi[dp]; }
 			}
+			if (m.mod_tmean) mean *= m.mod_tmean[((size_t)t * A + tc.c) * JD + e];     /* state.cc:446-453 */
 			if (MODE == MODE_REPLAY) {
 				/* the events are given (state.cc:294-322); only the means are recomputed */
 				const double num = stoch ? (double)b.tn[tbase + e] : b.tm[tbase + e];

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "beep_num_sections": (ctypes.c_int, [_vp]),
     "beep_section_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "beep_latent_loglik": (ctypes.c_int, [_vp, _vp]),
+    "beep_replay_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     "beep_likelihood_approx": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
     "beep_engine_has_approx": (ctypes.c_int, [_vp]),
     "beep_desc_size": (ctypes.c_int, []),
@@ -256,6 +257,9 @@ class Batch:
         _check(self.L.beep_replay(self.h))
 
     # -- K4 / K5 ----------------------------------------------------------
+    def replay_range(self, ti, tf):
+        _check(self.L.beep_replay_range(self.h, ti, tf))
+
     def obs_loglik(self, section=-1, with_tables=False):
         Lh = np.zeros(self.P)
         if with_tables:

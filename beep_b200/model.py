@@ -48,7 +48,7 @@ def _ctypes_fields():
 
 # arrays a description may lack (fixtures written before the feature existed): empty = the analysis does not use it
 OPTIONAL = {"dcc_info", "dcc_area", "dcc_group", "dcc_frac", "table_type", "graph_step", "graph_type", "graph_table", "graph_factor",
-            "graph_factor_spline", "graph_area_off", "graph_area", "graph_dp_off", "graph_dp", "graph_point_off", "graph_point_obs"}
+            "graph_factor_spline", "mod_transmean", "mod_beta", "mod_efoi", "mod_spline_mult", "mod_spline_set", "graph_area_off", "graph_area", "graph_dp_off", "graph_dp", "graph_point_off", "graph_point_obs"}
 
 
 class BeepModelDescStruct(ctypes.Structure):

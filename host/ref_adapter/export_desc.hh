@@ -42,9 +42,24 @@ static void beep_export_desc(Sink &pk, const Details &details, const Data &data,
 	pk.scalar_i(P+"infection_trans",model.infection_trans);
 	pk.scalar_i(P+"geo_spline_ref",model.geo_spline_ref);
 	pk.scalar_i(P+"pmcmc_obs_period",details.pmcmc_obs_period);
-	int nunsup = 0;
-	if(details.mode == PREDICTION) nunsup++;                           // modelmod multipliers (outside scope)
-	pk.scalar_i(P+"n_unsupported",nunsup);
+	pk.scalar_i(P+"n_unsupported",0);
+	{ // model modifications of mode=prediction (model.cc:1440-1585); written only where they differ from "no modification"
+		vector <double> tm, bm, em, sm, ss;
+		if(details.mode == PREDICTION){
+			const auto &mm = model.modelmod;
+			bool any_t = false, any_b = false, any_e = false, any_s = false;
+			for(auto sett = 0u; sett < T; sett++) for(auto c = 0u; c < A; c++){
+				for(auto tr = 0u; tr < J; tr++) for(auto dp = 0u; dp < D; dp++){ auto v = mm.transmean_mult[sett][c][tr][dp]; tm.push_back(v); if(v != 1) any_t = true; }
+				for(auto st = 0u; st < S; st++){ auto v = mm.beta_mult[sett][c][st]; bm.push_back(v); if(v != 1) any_b = true; v = mm.efoi_mult[sett][c][st]; em.push_back(v); if(v != 1) any_e = true; }
+			}
+			for(auto sp = 0u; sp < model.spline.size(); sp++) for(auto sett = 0u; sett < T; sett++){
+				sm.push_back(mm.spline_mult[sp][sett]); ss.push_back(mm.spline_set[sp][sett]);
+				if(mm.spline_mult[sp][sett] != 1 || mm.spline_set[sp][sett] != UNSET) any_s = true;
+			}
+			if(!any_t) tm.clear(); if(!any_b) bm.clear(); if(!any_e) em.clear(); if(!any_s){ sm.clear(); ss.clear(); }
+		}
+		pk.f64(P+"mod_transmean",tm); pk.f64(P+"mod_beta",bm); pk.f64(P+"mod_efoi",em); pk.f64(P+"mod_spline_mult",sm); pk.f64(P+"mod_spline_set",ss);
+	}
 	pk.scalar_d(P+"popsize",data.popsize);
 
 	{ // demographic change, state.cc:339-376

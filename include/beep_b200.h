@@ -144,6 +144,9 @@ int beep_mbp(BeepBatch *init, BeepBatch *prop, const uint8_t *simu_mask_host, in
  * batch's current parameters and stored transnum, recompute pop, transmean
  * and the observation sums.                                                 */
 int beep_replay(BeepBatch *batch);
+/* the steps [ti, tf) only: the batch then stands at step tf and beep_simulate(batch, tf, T, ...) continues from the replayed
+ * population -- State::load + State::simulate(pred_start, ndivision) of mode=prediction (simulate.cc:141-165)          */
+int beep_replay_range(BeepBatch *batch, int ti, int tf);
 
 /* K4.  Replaces ObservationModel::calculate (obsmodel.cc:22-35, section < 0),
  * calculate_section (:39-58, section >= 0) and get_EF_datatable (:309-322).

@@ -233,6 +233,12 @@ int oracle_set_param(OracleState *s, const double *theta)
 			}
 			s->disc_spline[sp * T + st] = v;
 		}
+		if (m->n_mod_spline_mult > 0)                                  /* model.cc:1044-1050: modifications of mode=prediction */
+			for (int st = 0; st < T; st++) {
+				s->disc_spline[sp * T + st] *= m->mod_spline_mult[sp * T + st];
+				double set = m->mod_spline_set[sp * T + st];
+				if (set != 999999999.0) s->disc_spline[sp * T + st] = set;
+			}
 	}
 
 	/* model.cc:1144-1164 create_susceptibility */
@@ -348,6 +354,10 @@ int oracle_set_param(OracleState *s, const double *theta)
 		}
 		free(V); free(Vinv); free(F); free(NGM); free(inf_ref);
 	}
+	if (m->n_mod_beta > 0)                                             /* model.cc:1349-1357 */
+		for (int st = 0; st < S; st++)
+			for (int c = 0; c < A; c++)
+				for (int sett = 0; sett < T; sett++) s->beta[((long)st * A + c) * T + sett] *= m->mod_beta[((long)sett * A + c) * S + st];
 	return 0;
 }
 
@@ -484,6 +494,7 @@ static void set_transmean(OracleState *s, int sett, int c)
 		be *= s->areafactor[(sett / m->spu) * A + c];
 		int ie = m->efoi_ref[st * A + c];
 		double et = s->disc_spline[m->efoi_spline_ref[ie] * T + sett] / m->popsize;
+		if (m->n_mod_efoi > 0) et *= m->mod_efoi[((long)sett * A + c) * S + st];            /* state.cc:415 */
 		for (int a = 0; a < G; a++) eta_age[a] = et * m->efoi_agedist[ie * G + a];
 		for (int dp = 0; dp < Dq; dp++) {
 			int dpp = st * Dq + dp;
@@ -504,6 +515,9 @@ static void set_transmean(OracleState *s, int sett, int c)
 				else TM(s, sett, c, tr, dp) = dt * popu * s->transrate[tr * D + dp];
 			}
 		}
+	if (m->n_mod_transmean > 0)                                        /* state.cc:446-453 */
+		for (int tr = 0; tr < J; tr++)
+			for (int dp = 0; dp < D; dp++) TM(s, sett, c, tr, dp) *= m->mod_transmean[((((long)sett * A + c) * J) + tr) * D + dp];
 	free(NMI); free(eta_age);
 }
 

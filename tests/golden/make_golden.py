@@ -95,6 +95,11 @@ GRAPHS = {"GRS_C4": ("examples/EX_C4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 1
           "GRS_C2": ("examples/EX_C2.toml", ["mode=mcmcmbp", "nsample=10"], 2, 137),    # ten areas
           "GRS_B6": ("examples/EX_B6.toml", ["mode=mcmcmbp", "nsample=10"], 2, 139),    # observation factor spline
           "GRS_B4": ("examples/EX_B4.toml", ["mode=mcmcmbp", "nsample=10"], 2, 149)}    # marginal data
+# model modifications of mode=prediction (model.modelmod, model.cc:1440-1585; state.cc:415,446-453): the reference constructs its
+# Model in prediction mode from TOML files extended IN THE SCRATCH TREE with 'modification' entries of every kind, and the harness
+# records its own set_param / simulate / Mbp::mbp under them (no posterior samples are needed for that)
+PRED = {"PRED_F3": ("pred_F3.toml", ["mode=prediction"], 2, 151),      # the reference's own scenario example: a transition rate doubled from day 80
+        "PRED_C2": ("pred_C2.toml", ["mode=prediction"], 2, 157)}      # ten areas: beta, external force, spline factor, spline set, per-area and per-transition filters
 SUBST = {"England_AS": [('obsmodel="scale"', 'obsmodel="normal 10%"')]}
 BIG = {"England_AS"}
 
@@ -143,6 +148,21 @@ def write_dcc_inputs(work):
         open(os.path.join(work, f"dcc_{name}.toml"), "w").write(txt)
 
 
+def write_pred_inputs(work):
+    ex = os.path.join(REF, "examples")
+    txt = open(os.path.join(ex, "EX_F3.toml")).read()
+    txt = txt.replace('modification = [{type="trans_rate_fac", start="80", trans="S->E", factor="2.0"}]',
+                      'modification = [{type="trans_rate_fac", start="80", trans="S->E", factor="2.0"},\n{type="trans_rate_fac", start="40", end="60", trans="I->R", factor="0.7"},\n{type="efoi_fac", start="20", end="50", factor="3.0"},\n{type="spline_fac", name="R_t", start="85", factor="0.5"},\n{type="spline_set", name="R_t", start="60", end="75", value="1.3"}]')
+    open(os.path.join(work, "pred_F3.toml"), "w").write(txt)
+    txt = open(os.path.join(ex, "EX_C2.toml")).read()
+    assert "prediction_end" not in txt and "\nmodification" not in txt
+    end = [ln for ln in txt.splitlines() if ln.startswith("end")][0]
+    t_end = int(end.split('"')[1])
+    txt = txt.replace(end, end + f'\nprediction_end = "{t_end + 30}"\nmodification = [{{type="beta_fac", start="{t_end // 2}", factor="0.6"}},\n'
+                      f'{{type="efoi_fac", start="10", end="{t_end // 3}", factor="2.5"}},\n{{type="trans_rate_fac", start="{t_end - 20}", trans="I->R", factor="1.4"}}]', 1)
+    open(os.path.join(work, "pred_C2.toml"), "w").write(txt)
+
+
 def main():
     only = sys.argv[1:]
     if not os.path.exists(HARNESS):
@@ -171,6 +191,8 @@ def main():
     CASES.update(OBSPATCH)
     CASES.update(APPROX)
     CASES.update(GRAPHS)
+    write_pred_inputs(work)
+    CASES.update(PRED)
     # demographic change (data.democat_change, state.cc:339-376): no input of the reference uses it, so two of its
     # examples are extended IN THE SCRATCH TREE -- EX_C3 (one area, Sex) and EX_C2 (ten areas, Sex added to its
     # population file; the change applies to all of them) -- with a table of category fractions over time
