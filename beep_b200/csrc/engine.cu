@@ -1745,6 +1745,23 @@ extern "C" int beep_load_sample(BeepBatch *bt, int slot, const char *file_prefix
 	return beep_import_particle(bt, slot, theta.data(), tn.data());
 }
 
+/* Mbp::get_al (mbp.cc:334-361) for n chains: the acceptance probability of a model-based proposal from the error functions
+ * (EF = -2 log observation probability) and log priors of the initial and the proposed state.  mode 0 = CUTOFF (the ABC methods:
+ * accept with the prior ratio when EF_p < EFcut), 1 = INVT (PAS, MC3, MCMC-MBP: power posterior at inverse temperature invT) */
+extern "C" int beep_mbp_al(int mode, double invT, double EFcut, const double *EF_i, const double *EF_p, const double *Pr_i, const double *Pr_p, int n, double *al_out)
+{
+	if (!EF_i || !EF_p || !Pr_i || !Pr_p || !al_out || n < 0 || (mode != 0 && mode != 1)) return fail(BEEP_ERR_INVALID, "bad argument to beep_mbp_al");
+	for (int i = 0; i < n; i++) {
+		double al = 0.0;
+		if (mode == 0) { if (EF_p[i] < EFcut) al = exp(Pr_p[i] - Pr_i[i]); }
+		else al = exp(-invT * 0.5 * (EF_p[i] - EF_i[i]) + Pr_p[i] - Pr_i[i]);
+		if (std::isnan(al)) return fail(BEEP_ERR_NUMERIC, "acceptance probability of chain %d is not a number (emsgEC Mbp 2)", i);
+		if (al > 1) al = 1;
+		al_out[i] = al;
+	}
+	return BEEP_OK;
+}
+
 /* ------------------------------------------------------------------------ */
 /* a12  resampling decisions of the particle methods (host arithmetic)      */
 /* ------------------------------------------------------------------------ */

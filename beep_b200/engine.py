@@ -45,6 +45,7 @@ _SIGNATURES = {
     "beep_likelihood_approx": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
     "beep_engine_has_approx": (ctypes.c_int, [_vp]),
     "beep_desc_size": (ctypes.c_int, []),
+    "beep_mbp_al": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "beep_graph_layout": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "beep_graph_state": (ctypes.c_int, [_vp, _vp]),
     "beep_graph_statistics": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
@@ -456,6 +457,14 @@ def move_plan(kind, vec_all, N, rank):
         ins.append((peer, [int(x) for x in inf[w + 2:w + 2 + n]]))
         w += 2 + n
     return local, out, ins
+
+
+def mbp_al(mode, invT, EFcut, EF_i, EF_p, Pr_i, Pr_p):
+    """Mbp::get_al (mbp.cc:334-361); mode 0 = CUTOFF, 1 = INVT"""
+    a = [np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (EF_i, EF_p, Pr_i, Pr_p)]
+    out = np.zeros(a[0].size)
+    _check(lib().beep_mbp_al(int(mode), float(invT), float(EFcut), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[0].size, out.ctypes.data))
+    return out
 
 
 def graph_statistics(gs):

@@ -277,6 +277,9 @@ int beep_test_move_plan(int kind, const uint32_t *vec_all, int ntot, int N, int 
  *   beep_ef_cutoff      ABCMBP::EF_cutoff   abcmbp.cc:135-217
  *   beep_pas_bootstrap  PAS::bootstrap      pas.cc:127-209   (invT_final < 0: unset)
  *   beep_mc3_swap       MC3::swap_states    mc3.cc:153-217   (ntr/nac: counts to add per position) */
+/* Mbp::get_al (mbp.cc:334-361) for n chains at once: al = min(1, exp(Pr_p - Pr_i)) if EF_p < EFcut else 0 (mode 0, CUTOFF);
+ * al = min(1, exp(-invT (EF_p - EF_i)/2 + Pr_p - Pr_i)) (mode 1, INVT).  EF = -2 L from beep_obs_loglik, Pr = model.prior. */
+int beep_mbp_al(int mode, double invT, double EFcut, const double *EF_i, const double *EF_p, const double *Pr_i, const double *Pr_p, int n, double *al_out);
 int beep_ef_cutoff(const double *EF_all_host, int ntot, double *EFcut, double *EFmin, double *EFmax, uint32_t *partcopy_host);
 int beep_pas_bootstrap(const double *EF_all_host, int nrun, int npart, double invT, double quench_factor, double invT_final,
                        uint64_t seed, int gen, double *DinvT, double *EFmin, double *EFmax, uint32_t *partcopy_host);

@@ -387,6 +387,14 @@ int main(int argc, char **argv)
 			pk.f64("mbp.a.transmean",flat4(mbp.propose->transmean,T));
 			pk.scalar_d("mbp.a.EF",mbp.propose->EF);
 			pk.scalar_d("mbp.a.Li",mbp.propose->likelihood());
+			// Mbp::get_al (mbp.cc:334-361) on this proposal in both modes: INVT at three temperatures, CUTOFF with the cut-off above and below EF_p
+			mbp.initial->set_EF(); mbp.initial->set_Pr();
+			vector <double> al, arg;
+			for(auto it : {1.0,0.37,0.002}){ mbp.obsmodel_mode = INVT; mbp.invT = it; al.push_back(mbp.get_al()); arg.push_back(it);}
+			for(auto dc : {3.0,-3.0}){ mbp.obsmodel_mode = CUTOFF; mbp.EFcut = mbp.propose->EF+dc; al.push_back(mbp.get_al()); arg.push_back(mbp.EFcut);}
+			mbp.obsmodel_mode = INVT; mbp.invT = 1; mbp.EFcut = UNSET;
+			pk.f64("mbp.al.value",al); pk.f64("mbp.al.arg",arg);
+			pk.f64("mbp.al.state",vector <double>{mbp.initial->EF,mbp.propose->EF,mbp.initial->Pr,mbp.propose->Pr});
 		}
 
 		// (vi) mixed SIMU/MBP with the same parameters (mbp_slicetime / mbp_fixedtree pattern, mbp.cc:656-697)

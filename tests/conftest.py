@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 def golden_names():
     """the model fixtures (stat_* are Monte-Carlo replicate fixtures, mvn_* those of the ABC-SMC weight kernel, APX_* those of the MVN-approximate likelihood)"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("stat_", "mvn_", "decisions", "APX_", "GRS_")))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("stat_", "mvn_", "decisions", "APX_", "GRS_", "AL_")))
 
 
 _CACHE = {}
