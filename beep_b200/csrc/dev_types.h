@@ -178,6 +178,7 @@ struct TrajArgs {
 	DevBatch b;
 	int ti, tf;
 	unsigned long long seed;
+	unsigned rk[20];    /* the Philox round keys of `seed` (beep_philox4x32_10_rk): constant-bank operands of the draws */
 	/* MBP: the coupled initial state (same slot of the `init` batch) */
 	const int *init_tn; const double *init_tm; const unsigned char *simu_mask;
 	const double *imap_pre;       /* non-null: Imap of this step for every (particle, strain, area, age), from k_imap_dmma */

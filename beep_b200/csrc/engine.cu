@@ -914,6 +914,7 @@ static int launch_traj(BeepBatch *bt, int mode, int ti, int tf, uint64_t seed, c
 	}
 	TrajArgs a;
 	a.m = m; a.b = bt->db; a.ti = ti; a.tf = tf; a.seed = seed;
+	for (int r = 0; r < 10; r++) { a.rk[2 * r] = (unsigned)seed + (unsigned)r * 0x9E3779B9u; a.rk[2 * r + 1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u; }
 	a.init_tn = init ? init->db.tn : nullptr; a.init_tm = init ? init->db.tm : nullptr; a.simu_mask = d_mask;
 	a.nwarp = eng->nwarp; a.chunk = 1; a.invG = 0; memset(&a.Ls, 0, sizeof a.Ls);
 	a.invA = 1.0f / (float)m.A; a.L = traj_sm_layout(m.G, m.J, m.D, traj_nbr_doubles(m));

@@ -730,6 +730,7 @@ __device__ __forceinline__ unsigned tile_step(const TrajArgs &a, const TileCtx &
 			const double mean = ns[e];
 			BeepStream rs;
 			beep_stream_init_cell(&rs, a.seed, tc.sid, cell0 + e);
+			rs.rk = a.rk;
 			int num;
 			if (MODE == MODE_SIM) num = beep_poisson(&rs, mean);             /* state.cc:624-626 */
 			else {
@@ -1011,6 +1012,7 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 		auto draw = [&](const int e, const double mean) -> int {
 			BeepStream rs;
 			beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
+			rs.rk = a.rk;
 			if (MODE == MODE_SIM) return beep_poisson(&rs, mean);
 			const int num_i = a.init_tn[tbase + e];
 			if (simu) return beep_poisson(&rs, mean);
@@ -1047,7 +1049,7 @@ __device__ __forceinline__ unsigned tile_step_fast(const TrajArgs &a, const int 
 						BeepStream rs;
 						beep_stream_init_cell(&rs, a.seed, sid, cell0 + e);
 						int num;
-						if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num)) finish(e, num);
+						if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num, a.rk)) finish(e, num);
 						else defer = true;
 					}
 					const unsigned bd = __ballot_sync(FULLMASK, defer);

@@ -293,6 +293,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 				const int i = cid >> 12, e = cid & 0xfff;
 				BeepStream rs;
 				beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)(i * JD + e));
+				rs.rk = a.rk;
 				if (MODE == MODE_SIM) return beep_poisson(&rs, mean);
 				const size_t g = tbase0 + (size_t)(i * JD + e);
 				const int num_i = a.init_tn[g];
@@ -352,7 +353,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 							BeepStream rs;
 							beep_stream_init_cell(&rs, a.seed, sid, cell00 + (unsigned long long)((cid >> 12) * JD + (cid & 0xfff)));
 							int num;
-							if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num)) finish(cid, num);
+							if (beep_poisson_ptrs_try(rs.key[0], rs.key[1], rs.ctr[0], rs.ctr[1], rs.ctr[2], rs.ctr[3], mean, &num, a.rk)) finish(cid, num);
 							else defer = true;
 						}
 						const unsigned bd = __ballot_sync(FULLMASK, defer);
