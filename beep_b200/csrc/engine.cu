@@ -797,7 +797,7 @@ extern "C" int beep_batch_create(BeepEngine *eng, int P, unsigned flags, BeepBat
 	BA(b.obs_partial, (size_t)P * std::max(m.nslot, 1)); BA(b.obs_val, (size_t)P * std::max(m.nobs, 1));
 	BA(b.L, P); BA(b.EFtab, (size_t)P * std::max(m.ntable, 1)); BA(b.Li, P);
 	BA(b.stream_id, P); BA(b.infmask, P);
-	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31));
+	BA(b.crate, (size_t)P * (((size_t)m.J * m.D + 31) & ~(size_t)31) + 32);        /* + one warp pass: the chunk kernel requests a pass ahead without a bound test */
 	BA(b.etab, (size_t)P * std::max(m.nefoi, 1) * m.T); BA(b.inflist, (size_t)P * (m.C + 1));
 	if (eng->sync_mode == SYNC_GRID) BA(b.sched, ((size_t)P + 1) * 16);
 	else if (eng->sync_mode == SYNC_NONE) BA(b.sched, 16);              /* the tile counter of the persistent warps */

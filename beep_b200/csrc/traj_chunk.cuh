@@ -217,7 +217,8 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 	const double dt = m.dt;
 	const bool apply = (t < T - 1);
 	const size_t tbase0 = (KEEP || MODE != MODE_SIM) ? (((size_t)p * T + t) * A + c0) * (size_t)JD : 0;
-	const double *crate = b.crate + (size_t)p * L.JD32;
+	const double *crl = b.crate + (size_t)p * L.JD32 + lane;
+	asm volatile("" : "+l"(crl));                       /* kept in registers: not re-derived from the launch arguments every pass */
 	const unsigned long long cell00 = ((unsigned long long)t * A + c0) * (unsigned long long)JD;
 	const unsigned long long sid = b.stream_id[p];
 	const int top = Ls.cap - 1;
@@ -235,12 +236,12 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 				if (MODE == MODE_MBP && a.simu_mask) simu = a.simu_mask[((size_t)p * T + t) * A + c0 + itile];
 				/* the per-cell rate multipliers come through L1/L2 (the shared-memory carve-out leaves little L1): the
 				 * next pass's value is requested while this pass is worked */
-				double crn = crate[lane];
+				double crn = __ldg(crl);
 #pragma unroll 1
 				for (int e0 = 0; e0 < JD; e0 += 32) {
 					const int e = e0 + lane;
 					const double cr = crn;
-					if (e0 + 32 < JD) crn = crate[e + 32];
+					crn = __ldg(crl + (unsigned)(e0 + 32));    /* the allocation is padded by one pass: the last request stays in range */
 					const unsigned w = lds32(ctab_a + e * 4);          /* padded to a multiple of 32 with never-firing cells */
 					const int popi = (int)lds32(pa + ((w & 0xfffu) << 2));
 					if (MODE == MODE_REPLAY) {

@@ -387,13 +387,10 @@ static __device__ __noinline__ int beep_poisson_ptrs_fresh(uint32_t k0, uint32_t
 }
 #endif
 
-/* sequential-search inversion for 0 < lam < 10 from the uniform u */
-BEEP_HD int beep_poisson_inv_u(double u, double lam)
+/* sequential-search inversion for 0 < lam < 10 from the uniform u: the exact search (correctly rounded FP64
+ * operations in a fixed order -- what host and device must agree on) */
+BEEP_HD int beep_poisson_inv_search(double u, double lam)
 {
-	/* exp(-lam) >= 1 - lam, and beep_exp is good to ~1 ulp: a uniform below
-	 * (1 - lam) - 4.5e-16 yields k = 0 whatever beep_exp rounds to, so the
-	 * shortcut never changes a draw (it only skips the exp) */
-	if (u <= BR_SUB(BR_SUB(1.0, lam), 4.5e-16)) return 0;
 	double p = beep_exp(BR_SUB(0.0, lam));
 	double cdf = p;
 	int k = 0;
@@ -406,6 +403,43 @@ BEEP_HD int beep_poisson_inv_u(double u, double lam)
 		ik = ikn;
 	}
 	return k;
+}
+#if defined(__CUDA_ARCH__) && !defined(BEEP_NO_F32_PRESEARCH)
+static __device__ __noinline__ int beep_poisson_inv_search_cold(double u, double lam) { return beep_poisson_inv_search(u, lam); }
+#endif
+
+BEEP_HD int beep_poisson_inv_u(double u, double lam)
+{
+	/* exp(-lam) >= 1 - lam, and beep_exp is good to ~1 ulp: a uniform below
+	 * (1 - lam) - 4.5e-16 yields k = 0 whatever beep_exp rounds to, so the
+	 * shortcut never changes a draw (it only skips the exp) */
+	if (u <= BR_SUB(BR_SUB(1.0, lam), 4.5e-16)) return 0;
+#if defined(__CUDA_ARCH__) && !defined(BEEP_NO_F32_PRESEARCH)
+	/* Device pre-search in single precision (hardware exp2 and reciprocal): the exact search returns the first k with
+	 * u <= cdf_k, its cdf_k within ~1e-14 of the true Poisson sums.  The single-precision sums c_k below carry a relative
+	 * error of at most 1.6e-6 (__expf: 2 + |1.173 x| ulp at |x| < 10) + 6e-7 (lam rounded to float) + 4.3e-7 k (three
+	 * roundings and an approximate reciprocal per step, the summation) < 2.2e-6 + 5e-7 k, and u rounds by 6e-8.  When u is
+	 * further than tol = 5e-6 + 1e-6 k (more than twice that bound; cdf <= 1) from BOTH c_(k-1) and c_k, the exact search
+	 * sees cdf_(k-1) < u <= cdf_k as well (its sums are monotone, so the earlier comparisons follow) and returns this k:
+	 * the draw is unchanged.  Otherwise (probability ~ 4 tol per draw) the exact search decides, out of line. */
+	{
+		const float uf = __double2float_rn(u), lf = __double2float_rn(lam);
+		float p = __expf(-lf), cdf = p, prev = -1.0f, kf = 0.0f;
+		while (uf > cdf && kf < 60.0f) {
+			kf += 1.0f;
+			float rk;
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rk) : "f"(kf));      /* <= 1 ulp */
+			p = __fmul_rn(__fmul_rn(p, lf), rk);
+			prev = cdf;
+			cdf = __fadd_rn(cdf, p);
+		}
+		const float tol = __fadd_rn(5e-6f, __fmul_rn(1e-6f, kf));
+		if (__fsub_rn(cdf, uf) > tol && __fsub_rn(uf, prev) > tol) return (int)kf;
+		return beep_poisson_inv_search_cold(u, lam);
+	}
+#else
+	return beep_poisson_inv_search(u, lam);
+#endif
 }
 
 /* the first two uniforms of a fresh per-cell stream (one Philox block): what the first two calls of

@@ -876,6 +876,11 @@ void oracle_binomial_many(uint64_t seed, uint64_t stream_id, const double *p, co
 		out[i] = beep_binomial(&rs, p[i], nn[i]);
 	}
 }
+/* the exact inversion search from a given uniform (tests/test_rng_math_cpu.py: the device's single-precision pre-search) */
+void oracle_poisson_inv_many(const double *u, const double *lam, int n, int32_t *out)
+{
+	for (int i = 0; i < n; i++) out[i] = beep_poisson_inv_u(u[i], lam[i]);
+}
 void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { beep_philox4x32_10(ctr, key, out); }
 
 /* the shared software exp / log (include/beep_rng.h), exposed so that tests can pin their accuracy against libm */
