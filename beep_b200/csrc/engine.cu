@@ -450,12 +450,17 @@ extern "C" int beep_engine_create(const BeepModelDesc *d, int device, BeepEngine
 		m.M_nnz = nnz;
 		/* the same matrix as the kernel reads it: 16-byte (weight, source offset) entries and one
 		 * 32-byte record of per-area constants */
-		std::vector<Nbr> nb((size_t)nnz);
-		for (int k = 0; k < nnz; k++) { nb[k].val = val[k]; nb[k].off = (unsigned)src[k] * (unsigned)G * 8u; nb[k].pad = 0; }
+		std::vector<Nbr> nb;
+		nb.reserve((size_t)nnz + 8 * (size_t)A);
 		std::vector<AreaInfo> ai((size_t)A);
 		for (int c = 0; c < A; c++) {
 			NEED(d->efoi_ref[c] >= 0 && d->efoi_ref[c] < m.nefoi, "efoi_ref out of range");
-			ai[c].diag = d->M_diag[c]; ai[c].fac = d->M_factor[c]; ai[c].j0 = off[c]; ai[c].nn = off[c + 1] - off[c];
+			/* a row is padded to a multiple of eight entries with zero weights on the area itself: the chunk kernel works
+			 * whole groups of eight (adding +0 changes no bit); the other kernels stop at nn */
+			const int j0 = (int)nb.size();
+			for (int k = off[c]; k < off[c + 1]; k++) { Nbr e; e.val = val[k]; e.off = (unsigned)src[k] * (unsigned)G * 8u; e.pad = 0; nb.push_back(e); }
+			while ((nb.size() - (size_t)j0) & 7) { Nbr e; e.val = 0.0; e.off = (unsigned)c * (unsigned)G * 8u; e.pad = 0; nb.push_back(e); }
+			ai[c].diag = d->M_diag[c]; ai[c].fac = d->M_factor[c]; ai[c].j0 = j0; ai[c].nn = off[c + 1] - off[c];
 			ai[c].rg = eng->h_rgrp[c]; ai[c].ie0 = d->efoi_ref[c];
 		}
 		UPV(nbr, nb); UPV(area_info, ai);

@@ -40,10 +40,6 @@
 #ifndef CHUNK_NWARP
 #define CHUNK_NWARP 4
 #endif
-#ifndef CHUNK_GUNROLL
-#define CHUNK_GUNROLL 4
-#endif
-static constexpr int GUNROLL = CHUNK_GUNROLL;
 
 __device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_shared_add(unsigned a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -121,12 +117,21 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 			const char *dcl = (const char *)(dinf_cur + ag);
 			const Nbr *nb = m.nbr + ai.j0;
 			double Imap = 0;
-#pragma unroll (GUNROLL)
-			for (int j = 0; j < ai.nn; j++) {
-				const double2 raw = __ldg((const double2 *)(nb + j));        /* (weight, byte offset of the source area) */
-				Imap += ld_l2((const double *)(dcl + (unsigned)__double2loint(raw.y))) * raw.x;
+			/* groups of eight sources (the rows of the matrix are padded to eight with zero weights on the area itself:
+			 * adding +0 changes no bit): first the eight L2 requests from the byte offsets alone (eight value registers),
+			 * then the weights (L1) and the sum in the reference's order -- one L2 round trip per group instead of one per
+			 * unrolled quarter, without the 32 registers eight whole entries would hold */
+			const double dg = ld_l2(dinf_cur + c * G + ag);
+			const int nn8 = (ai.nn + 7) & ~7;
+#pragma unroll 1
+			for (int j0 = 0; j0 < nn8; j0 += 8) {
+				double v[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) v[u] = ld_l2((const double *)(dcl + __ldg(&nb[j0 + u].off)));
+#pragma unroll
+				for (int u = 0; u < 8; u++) Imap += v[u] * __ldg(&nb[j0 + u].val);
 			}
-			const double Idiag = ld_l2(dinf_cur + c * G + ag) * ai.diag;
+			const double Idiag = dg * ai.diag;
 			const double Iv = (Idiag + Imap) * d + ai.fac * Idiag * omd;
 			if (valid) {
 				sts64(lm_a + i * GsB + ag * 8, Iv);
