@@ -91,7 +91,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 	const int GsB = L.Gs * 8;
 
 	/* 1a. state.cc:204-216, 547-553: the infectivity vector I of every (tile, age) pair */
-	for (int x = lane; x < nt * (L.Gs - G); x += 32) { const int i = x / (L.Gs - G), k = x - i * (L.Gs - G); sts64(lm_a + i * GsB + (G + k) * 8, 0.0); }
+	if ((G & 1) && lane < nt) sts64(lm_a + lane * GsB + G * 8, 0.0);      /* odd G: the age contraction reads pairs, one element past the vector */
 	if (lane < nt) {
 		/* per-tile scalars, one lane per tile: beta * area factor (state.cc:410-411), external force (:423) */
 		const int c = c0 + lane;
@@ -157,7 +157,7 @@ __device__ __forceinline__ void chunk_step(const TrajArgs &a, const int p, const
 				const unsigned row = n0_a + ag * GsB, ivr = lm_a + i * GsB;
 				double sum = 0;
 				if (!ntfly) {
-					const int h = L.Gs >> 1;
+					const int h = (G + 1) >> 1;                 /* pairs of ages: the padding of the rows (Gs - G elements) is not read */
 #pragma unroll 5
 					for (int k = 0; k < h; k++) { const double2 n2 = lds128(row + k * 16), v2 = lds128(ivr + k * 16); sum += n2.x * v2.x; sum += n2.y * v2.y; }
 				} else {
