@@ -36,9 +36,9 @@ Every line also carries two extra objects measured AFTER the headline (they are 
 
 `--impl reference` times the UNMODIFIED reference on all host cores (kind "reference"): oracle/_ref/ref_harness
 (the reference's own objects, built here from /root/reference and shipped as a binary) runs the synthetic
-population written in the reference's own TOML/CSV formats.  Where that is not possible (binary absent, or the
-England_AS workload, whose data directory is not on the GPU box) it falls back to the CPU restatement of the
-reference algorithm (oracle/liboracle.so, kind "port").
+population written in the reference's own TOML/CSV formats (--workload england_as: the England_AS inputs shipped under
+tests/golden/ref_inputs, one draw from the prior per process).  Where that is not possible (binary absent, MBP mode) it
+falls back to the CPU restatement of the reference algorithm (oracle/liboracle.so, kind "port").
 """
 import argparse
 import json
@@ -210,21 +210,31 @@ def reference_run(args, steps, budget_s=4.0, areas=None):
     looping State::simulate(param) + ObservationModel::calculate with the reference's own samplers.
     Returns (units/s, cores, sample, ms_per_step, areas) or None when the binary is absent or the workload has no
     reference input files."""
-    if args.workload != "synthetic" or args.mode != "simulate" or not os.access(REF_HARNESS, os.X_OK):
+    england = args.workload == "england_as"
+    ref_inputs = os.path.join(ROOT, "tests", "golden", "ref_inputs")
+    if args.mode != "simulate" or not os.access(REF_HARNESS, os.X_OK) or (england and not os.path.isdir(os.path.join(ref_inputs, "COVID 19 England"))):
         return None
     import tempfile
     import shutil
     from beep_b200.synth import write_reference_inputs
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nproc = max(1, min(cores, 64))
-    if areas is None:
+    if areas is None and not england:
         areas = reference_areas(nproc)
     work = tempfile.mkdtemp(prefix="beep_ref_")
     try:
-        toml = write_reference_inputs(work, A=areas)
         env = dict(os.environ, BEEP_HARNESS_BENCH=str(budget_s * max(steps, 1)))
-        procs = [subprocess.Popen(["timeout", "-s", "KILL", "900", REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim", f"outputdir=Output_{i}"],
-                                  cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
+        if england:
+            # England_AS as shipped under tests/golden/ref_inputs (obsmodel scale -> normal 10%, see its README): every process
+            # simulates its own draw from the prior (the reference's Model::sample_from_prior, seed 100 + i), as ABC-SMC does
+            areas = 1
+            procs = [subprocess.Popen(["timeout", "-s", "KILL", "900", REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), "inputfile=COVID 19 England/England_AS.toml",
+                                       "mode=abcsmc", "nsample=10", f"outputdir={os.path.join(work, f'Output_{i}')}"],
+                                      cwd=ref_inputs, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
+        else:
+            toml = write_reference_inputs(work, A=areas)
+            procs = [subprocess.Popen(["timeout", "-s", "KILL", "900", REF_HARNESS, os.path.join(work, f"o{i}.bpk"), "1", str(100 + i), f"inputfile={os.path.basename(toml)}", "mode=sim", f"outputdir=Output_{i}"],
+                                      cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(nproc)]
         units, secs, ok = 0.0, 0.0, 0
         for i, p in enumerate(procs):
             rc = p.wait(timeout=1000)
@@ -244,6 +254,10 @@ def reference_run(args, steps, budget_s=4.0, areas=None):
         return None
     finally:
         shutil.rmtree(work, ignore_errors=True)
+    if england:
+        sample = (f"oracle/_ref/ref_harness (the unmodified reference's State::simulate + ObservationModel::calculate, its own std:: samplers) on England_AS "
+                  f"(tests/golden/ref_inputs, obsmodel scale -> normal 10%), one draw from the prior per process, {nproc} single-rank processes x {secs:.1f} s")
+        return units / secs, nproc, sample, secs / max(steps, 1) * 1e3, areas
     sample = (f"oracle/_ref/ref_harness (the unmodified reference's State::simulate + ObservationModel::calculate, its own std:: samplers), "
               f"synthetic population in the reference's TOML/CSV formats at A={areas} areas x 20 ages x 365 steps (the largest the reference's dense "
               f"geographic-matrix loader and per-State trajectory storage allow on this host), {nproc} single-rank processes x {secs:.1f} s")
@@ -261,8 +275,9 @@ def main_reference(args):
     v, cores, sample, ms, areas = r
     m, theta = load_workload(args, areas=areas)
     cfg = workload_config(args, m, theta.size)
-    cfg["areas"] = int(m.A)                         # what the reference arm actually ran (see reference_areas)
-    cfg["workload"] += f" [reference arm: {int(m.A)} areas, not {args.areas}: the reference cannot load the dense geographic matrix of the full size]"
+    if args.workload == "synthetic":
+        cfg["areas"] = int(m.A)                     # what the reference arm actually ran (see reference_areas)
+        cfg["workload"] += f" [reference arm: {int(m.A)} areas, not {args.areas}: the reference cannot load the dense geographic matrix of the full size]"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -34,3 +34,17 @@ def test_reference_reads_the_synthetic_inputs(tmp_path):
     pop_ref = d["desc.pop_init"].reshape(6, m.C, 20).sum(axis=1)
     pop_syn = np.asarray(m.arrays["pop_init"]).reshape(6, m.C, 20).sum(axis=1)
     assert np.array_equal(pop_ref, pop_syn)
+
+
+@pytest.mark.skipif(not os.access(HARNESS, os.X_OK), reason="oracle/_ref/ref_harness not built (no reference sources here)")
+def test_reference_runs_the_shipped_england_inputs(tmp_path):
+    """bench.py's cpu_baseline of --workload england_as: the unmodified reference loads tests/golden/ref_inputs/COVID 19 England,
+    draws a parameter vector from its prior and times its own State::simulate on the England_AS shape."""
+    work = str(tmp_path)
+    out = os.path.join(work, "o.bpk")
+    env = dict(os.environ, BEEP_HARNESS_BENCH="0.2")
+    r = subprocess.run([HARNESS, out, "1", "100", "inputfile=COVID 19 England/England_AS.toml", "mode=abcsmc", "nsample=10", f"outputdir={os.path.join(work, 'Out')}"],
+                       cwd=os.path.join(ROOT, "tests", "golden", "ref_inputs"), env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    kv = dict(x.split("=") for x in open(out + ".bench").read().split()[1:])
+    assert (int(kv["T"]), int(kv["A"]), int(kv["D"])) == (1050, 1, 18) and int(kv["reps"]) >= 1
